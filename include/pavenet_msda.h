@@ -1,0 +1,151 @@
+/*
+ * pavenet_msda.h — C ABI of the B200-native multi-scale deformable attention
+ * sampling op (forward + backward) used by PAVE-Net's spatial encoder and
+ * pose-aware decoder attention.
+ *
+ * This is the drop-in boundary.  It replaces, entry point for entry point,
+ * the two functions the reference binds into `mmcv._ext`:
+ *
+ *   ms_deform_attn_forward   third_party/mmcv/mmcv/ops/csrc/pytorch/ms_deform_attn.cpp:38-46
+ *                            (pybind: .../csrc/pytorch/pybind.cpp:737-742,
+ *                             CUDA host code: .../csrc/pytorch/cuda/ms_deform_attn_cuda.cu:209-277)
+ *   ms_deform_attn_backward  third_party/mmcv/mmcv/ops/csrc/pytorch/ms_deform_attn.cpp:48-60
+ *                            (pybind: .../csrc/pytorch/pybind.cpp:743-748,
+ *                             CUDA host code: .../csrc/pytorch/cuda/ms_deform_attn_cuda.cu:279-351)
+ *
+ * which `MultiScaleDeformableAttnFunction` calls
+ * (third_party/mmcv/mmcv/ops/multi_scale_deform_attn.py:47-53, 76-86).
+ *
+ * Conventions
+ *  - Plain pointers and sizes only; no torch / ATen types.
+ *  - Every `d_` pointer is a DEVICE pointer on the current CUDA device,
+ *    including `d_spatial_shapes` and `d_level_start_index` (the reference
+ *    reads both inside its kernels, ms_deform_attn_cuda_kernel.cuh:226-229,
+ *    so no host round-trip is introduced here either).
+ *  - All tensors are dense, row-major ("contiguous"), with the reference's
+ *    layouts:
+ *        value               (B, S, M, D)
+ *        spatial_shapes      (L, 2)  int64, (H_l, W_l)
+ *        level_start_index   (L,)    int64
+ *        sampling_locations  (B, Q, M, L, P, 2)   normalised (x, y)
+ *        attention_weights   (B, Q, M, L, P)
+ *        output / grad_output (B, Q, M*D)
+ *  - The caller owns every buffer.  `msda_forward` fully overwrites `d_output`
+ *    (no pre-zeroing needed; the reference zero-fills it itself,
+ *    ms_deform_attn_cuda.cu:247-248).  `msda_backward` ACCUMULATES into
+ *    `d_grad_value` (which the caller must have zeroed, as the reference's
+ *    autograd wrapper does, multi_scale_deform_attn.py:72-74) and fully
+ *    overwrites `d_grad_sampling_loc` / `d_grad_attn_weight`.
+ *  - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default
+ *    stream).  Calls are asynchronous: they enqueue work and return.
+ *  - Every function returns MSDA_OK (0) or a negative MSDA_ERR_* code;
+ *    `msda_last_error()` returns a thread-local human-readable message.  The
+ *    reference swallows launch errors with printf
+ *    (ms_deform_attn_cuda.cu:41-44); this library reports them.
+ *  - Re-entrant, no global mutable state except the launch counter.
+ *
+ * dtype codes: `dtype` is the type of locations, weights, output and their
+ * gradients (MSDA_F32 or MSDA_F64, the two types the reference instantiates,
+ * ms_deform_attn_cuda.cu:258,329).  `value_dtype` / `grad_value_dtype` may
+ * additionally be MSDA_BF16 when `dtype` is MSDA_F32 (bf16 value storage is
+ * a capability the reference does not have).
+ */
+#ifndef PAVENET_MSDA_H_
+#define PAVENET_MSDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_ABI_VERSION 1
+
+enum msda_dtype { MSDA_F32 = 0, MSDA_F64 = 1, MSDA_BF16 = 2 };
+
+enum msda_status {
+  MSDA_OK = 0,
+  MSDA_ERR_INVALID_ARGUMENT = -1, /* NULL pointer, non-positive size, bad dtype combination */
+  MSDA_ERR_UNSUPPORTED = -2,      /* valid request this build has no kernel for */
+  MSDA_ERR_CUDA = -3,             /* CUDA runtime / launch failure; see msda_last_error() */
+  MSDA_ERR_NO_DEVICE = -4         /* no usable CUDA device */
+};
+
+/* ABI version of the loaded library (== MSDA_ABI_VERSION it was built with). */
+int msda_abi_version(void);
+
+/* Thread-local message for the last non-OK status returned on this thread. */
+const char *msda_last_error(void);
+
+/* Number of CUDA kernels this library has launched since load (all threads). */
+uint64_t msda_launch_count(void);
+
+/* Name of the kernel family the dispatcher would use for this problem
+ * ("rows<D=32,f32>", "generic", ...).  Static storage; never NULL. */
+const char *msda_kernel_name(int channels, int dtype, int value_dtype);
+
+/*
+ * Forward.  Replaces ms_deform_attn_forward (ms_deform_attn.cpp:38-46).
+ * out[b,q,m*D+c] = sum_{l,p} w[b,q,m,l,p] * bilinear(value_l[b,:,m,c]; x*W_l-0.5, y*H_l-0.5)
+ * with zero padding outside the map (ms_deform_attn_cuda_kernel.cuh:17-64,200-254).
+ * `im2col_step` of the reference is a batching knob of its host loop and has
+ * no effect on results; it is validated by the Python wrapper, not here.
+ */
+int msda_forward(const void *d_value, const int64_t *d_spatial_shapes,
+                 const int64_t *d_level_start_index,
+                 const void *d_sampling_loc, const void *d_attn_weight,
+                 void *d_output, int batch, int spatial_size, int num_heads,
+                 int channels, int num_levels, int num_query, int num_point,
+                 int dtype, int value_dtype, void *stream);
+
+/*
+ * Backward.  Replaces ms_deform_attn_backward (ms_deform_attn.cpp:48-60).
+ * grad_value += scatter of bilinear weights * grad_output * attention weight,
+ * grad_sampling_loc / grad_attn_weight as in ms_deform_attn_cuda_kernel.cuh:66-131.
+ * `d_grad_value` is accumulated into and must be zero-initialised by the
+ * caller; the other two gradients are fully overwritten.
+ */
+int msda_backward(const void *d_value, const int64_t *d_spatial_shapes,
+                  const int64_t *d_level_start_index,
+                  const void *d_sampling_loc, const void *d_attn_weight,
+                  const void *d_grad_output, void *d_grad_value,
+                  void *d_grad_sampling_loc, void *d_grad_attn_weight,
+                  int batch, int spatial_size, int num_heads, int channels,
+                  int num_levels, int num_query, int num_point, int dtype,
+                  int value_dtype, int grad_value_dtype, void *stream);
+
+/*
+ * Host-buffer convenience entry points (what a cgo / JNI / ctypes caller
+ * without its own device memory management binds).  All pointers are HOST
+ * pointers (pinned memory gives asynchronous copies; pageable memory works
+ * but is slower).  Each call stages inputs host->device, runs the kernels and
+ * copies results device->host on an internal stream, and returns after the
+ * results are in the host buffers.  Device scratch is cached per workspace.
+ */
+typedef struct msda_workspace msda_workspace;
+
+int msda_workspace_create(msda_workspace **out_ws);
+void msda_workspace_destroy(msda_workspace *ws);
+
+int msda_forward_host(msda_workspace *ws, const void *h_value,
+                      const int64_t *h_spatial_shapes,
+                      const int64_t *h_level_start_index,
+                      const void *h_sampling_loc, const void *h_attn_weight,
+                      void *h_output, int batch, int spatial_size,
+                      int num_heads, int channels, int num_levels,
+                      int num_query, int num_point, int dtype, int value_dtype);
+
+/* Forward + backward in one staged call: inputs and grad_output go up once,
+ * output and the three gradients come back.  `h_output` may be NULL. */
+int msda_forward_backward_host(
+    msda_workspace *ws, const void *h_value, const int64_t *h_spatial_shapes,
+    const int64_t *h_level_start_index, const void *h_sampling_loc,
+    const void *h_attn_weight, const void *h_grad_output, void *h_output,
+    void *h_grad_value, void *h_grad_sampling_loc, void *h_grad_attn_weight,
+    int batch, int spatial_size, int num_heads, int channels, int num_levels,
+    int num_query, int num_point, int dtype, int value_dtype);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAVENET_MSDA_H_ */

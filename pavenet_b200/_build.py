@@ -1,0 +1,75 @@
+"""Build recipe for the C-ABI CUDA library (`libpavenet_msda.so`).
+
+Compiles `pavenet_b200/csrc/*.cu` for sm_100a with nvcc into
+`pavenet_b200/lib/` — in-tree, so the built library travels with the
+repository snapshot.  nvcc cross-compiles without a GPU, so this also runs on
+a CPU-only build host.
+
+    python -m pavenet_b200._build [--force] [--verbose]
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, 'csrc')
+LIB_DIR = os.path.join(_HERE, 'lib')
+LIB_PATH = os.path.join(LIB_DIR, 'libpavenet_msda.so')
+INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), 'include')
+
+SOURCES = ['msda_fwd.cu', 'msda_bwd.cu', 'msda_capi.cu']
+HEADERS = ['msda_common.cuh', 'msda_kernels.h']
+
+NVCC_FLAGS = [
+    '-gencode', 'arch=compute_100a,code=sm_100a',
+    '-O3', '-std=c++17', '-lineinfo',
+    '-Xcompiler', '-fPIC', '-shared',
+]
+
+
+def _nvcc():
+    exe = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(exe):
+        raise RuntimeError('nvcc not found; cannot build libpavenet_msda.so')
+    return exe
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    deps.append(os.path.join(INCLUDE_DIR, 'pavenet_msda.h'))
+    return any(os.path.getmtime(d) > built for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile the library if missing or older than its sources.
+
+    Returns the path of the shared library.
+    """
+    if not force and not _stale():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS
+    if verbose:
+        cmd += ['-Xptxas', '-v']
+    tmp = LIB_PATH + '.tmp%d' % os.getpid()
+    cmd += ['-o', tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                          text=True)
+    if verbose or proc.returncode != 0:
+        sys.stderr.write(proc.stdout)
+    if proc.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+        raise RuntimeError('nvcc failed (exit %d):\n%s' %
+                           (proc.returncode, proc.stdout[-4000:]))
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+if __name__ == '__main__':
+    path = build(force='--force' in sys.argv, verbose='--verbose' in sys.argv)
+    print(path)

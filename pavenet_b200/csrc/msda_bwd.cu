@@ -1,0 +1,403 @@
+// msda_bwd.cu — backward kernels of multi-scale deformable attention sampling
+// for sm_100a.
+//
+// Maths (reference: ms_deform_attn_cuda_kernel.cuh:66-131 inside the loop of
+// :256-345), per sample that passes the range test, g = grad_out[b,q,m,c]:
+//   grad_value[corner_i]      += w_i * g * a                 (valid corners only)
+//   grad_attn_weight[b,q,m,l,p] = sum_c g * (w1 v1 + w2 v2 + w3 v3 + w4 v4)
+//   grad_loc[...,0]             = W * sum_c (hh (v2-v1) + lh (v4-v3)) * g * a
+//   grad_loc[...,1]             = H * sum_c (hw (v3-v1) + lw (v4-v2)) * g * a
+// Samples outside the range get zero location / weight gradients.
+//
+// rows<D,VT,GT>: same lane-group-per-row layout as the forward.  The value
+// gradient leaves each lane as ONE 16-byte vector reduction per corner
+// (red.global.add.v4.f32, or v4.bf16x2 when the gradient is stored in bf16)
+// instead of the reference's 4 scalar atomics per channel, and the
+// per-sample channel sums are finished with a transposing shuffle reduction
+// over the G lanes of the group (7 shuffles per 8 samples per quantity)
+// instead of a shared-memory pass with thread 0 summing serially
+// (ms_deform_attn_cuda_kernel.cuh:319-336).
+#include "msda_kernels.h"
+
+namespace msda {
+
+// ---- vector reductions into global memory --------------------------------
+__device__ __forceinline__ void red_add_row(float* p, const float (&v)[4]) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]),
+               "f"(v[2]), "f"(v[3])
+               : "memory");
+}
+__device__ __forceinline__ void red_add_row(float* p, const float (&v)[8]) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]),
+               "f"(v[2]), "f"(v[3])
+               : "memory");
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + 4), "f"(v[4]),
+               "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+__device__ __forceinline__ void red_add_row(__nv_bfloat16* p, const float (&v)[8]) {
+  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(p),
+               "r"(pack_bf16x2(v[0], v[1])), "r"(pack_bf16x2(v[2], v[3])),
+               "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void red_add_row(__nv_bfloat16* p, const float (&v)[4]) {
+  asm volatile("red.global.add.noftz.v2.bf16x2 [%0], {%1, %2};" ::"l"(p),
+               "r"(pack_bf16x2(v[0], v[1])), "r"(pack_bf16x2(v[2], v[3]))
+               : "memory");
+}
+
+// Sum p[j] over the G lanes of a group; lane gl ends up with the total of
+// sample j == gl.  log2(G) rounds, G-1 shuffles in all.
+template <int G>
+__device__ __forceinline__ float group_transpose_reduce(float (&p)[G], int gl) {
+#pragma unroll
+  for (int half = G / 2; half >= 1; half >>= 1) {
+    const bool upper = (gl & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? p[i] : p[i + half];
+      const float keep = upper ? p[i + half] : p[i];
+      p[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return p[0];
+}
+
+constexpr int kRowsThreads = 256;
+constexpr int kRowsWarps = kRowsThreads / 32;
+
+template <int D, typename VT, typename GT>
+__global__ void __launch_bounds__(kRowsThreads)
+msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
+                     const float* __restrict__ aw, const float* __restrict__ grad_out,
+                     GT* __restrict__ grad_value, float* __restrict__ grad_loc,
+                     float* __restrict__ grad_aw, Dims d, int nsplit) {
+  constexpr int VEC = Vec16<VT>::VEC;
+  constexpr int G = D / VEC;
+  static_assert(D % VEC == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0, "bad D");
+
+  __shared__ LevelInfo s_lvl[kMaxSmemLevels];
+  __shared__ SampleRec s_rec[kRowsWarps][32];
+
+  const int MD = d.M * D;
+  for (int l = threadIdx.x; l < d.L; l += blockDim.x) s_lvl[l] = load_level(shapes, lsi, l, MD);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int gl = lane & (G - 1);
+  const int grp = lane / G;
+  const int64_t n_units = static_cast<int64_t>(d.B) * d.Q * d.M;
+  const int64_t gid = (static_cast<int64_t>(blockIdx.x) * kRowsThreads + threadIdx.x) / G;
+  int64_t unit = gid / nsplit;
+  const int split = static_cast<int>(gid % nsplit);
+  const bool live = unit < n_units;
+  if (!live) unit = n_units - 1;
+
+  const int m = static_cast<int>(unit % d.M);
+  const int64_t b = unit / d.M / d.Q;
+  const int64_t boff = b * d.S * MD + m * D + gl * VEC;
+  const VT* vbase = value + boff;
+  GT* gvbase = grad_value + boff;
+  const int LP = d.L * d.P;
+  const float* loc_u = loc + unit * LP * 2;
+  const float* aw_u = aw + unit * LP;
+  float* gloc_u = grad_loc + unit * LP * 2;
+  float* gaw_u = grad_aw + unit * LP;
+
+  float g[VEC];
+  {
+    const float* gp = grad_out + unit * D + gl * VEC;
+#pragma unroll
+    for (int c = 0; c < VEC; c += 4) {
+      const float4 t = __ldcs(reinterpret_cast<const float4*>(gp + c));
+      g[c] = t.x; g[c + 1] = t.y; g[c + 2] = t.z; g[c + 3] = t.w;
+    }
+  }
+
+  const int per = ((LP + nsplit - 1) / nsplit + G - 1) / G * G;
+  const int s_begin = split * per;
+  const int s_end = live ? min(LP, s_begin + per) : 0;  // dead groups touch nothing
+
+  SampleRec* rec = s_rec[warp];
+  for (int s0 = s_begin; s0 < s_begin + per; s0 += G) {
+    const int s = s0 + gl;
+    float Wf = 0.f, Hf = 0.f;
+    {
+      SampleRec r;
+      r.off00 = 0; r.meta = 0; r.lh = 0.f; r.lw = 0.f; r.a = 0.f;
+      if (s < s_end) {
+        const float2 xy = ld_stream_f2(loc_u + 2 * s);
+        r.a = ld_stream_f(aw_u + s);
+        const int l = s / d.P;
+        const LevelInfo lv = s_lvl[l];
+        Wf = static_cast<float>(lv.W);
+        Hf = static_cast<float>(lv.H);
+        make_sample(xy.x, xy.y, r.a, lv, l, MD, r.off00, r.meta, r.lh, r.lw);
+      }
+      *reinterpret_cast<int4*>(&rec[lane]) =
+          make_int4(r.off00, r.meta, __float_as_int(r.lh), __float_as_int(r.lw));
+      rec[lane].a = r.a;
+    }
+    __syncwarp();
+
+    float pw[G], px[G], py[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      pw[j] = 0.f; px[j] = 0.f; py[j] = 0.f;
+      const SampleRec* rj = &rec[grp * G + j];
+      const int4 q = *reinterpret_cast<const int4*>(rj);
+      const int meta = q.y;
+      if (meta & 15) {
+        const float a = rj->a;
+        const float lh = __int_as_float(q.z), lw = __int_as_float(q.w);
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        const int rs = s_lvl[meta >> 4].row_stride;
+        const VT* p = vbase + q.x;
+        GT* gp = gvbase + q.x;
+        float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) v1[c] = v2[c] = v3[c] = v4[c] = 0.f;
+        if (meta & 1) Vec16<VT>::load(p, v1);
+        if (meta & 2) Vec16<VT>::load(p + MD, v2);
+        if (meta & 4) Vec16<VT>::load(p + rs, v3);
+        if (meta & 8) Vec16<VT>::load(p + rs + MD, v4);
+        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+        float tg[VEC];
+        float sw = 0.f, sx = 0.f, sy = 0.f;
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+          tg[c] = g[c] * a;
+          const float val = w1 * v1[c] + w2 * v2[c] + w3 * v3[c] + w4 * v4[c];
+          const float gw = hh * (v2[c] - v1[c]) + lh * (v4[c] - v3[c]);
+          const float gh = hw * (v3[c] - v1[c]) + lw * (v4[c] - v2[c]);
+          sw += g[c] * val;
+          sx += gw * tg[c];
+          sy += gh * tg[c];
+        }
+        pw[j] = sw; px[j] = sx; py[j] = sy;
+        float t[VEC];
+        if (meta & 1) {
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) t[c] = w1 * tg[c];
+          red_add_row(gp, t);
+        }
+        if (meta & 2) {
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) t[c] = w2 * tg[c];
+          red_add_row(gp + MD, t);
+        }
+        if (meta & 4) {
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) t[c] = w3 * tg[c];
+          red_add_row(gp + rs, t);
+        }
+        if (meta & 8) {
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) t[c] = w4 * tg[c];
+          red_add_row(gp + rs + MD, t);
+        }
+      }
+    }
+    // lane gl receives the channel-summed gradients of sample s0 + gl
+    const float tw = group_transpose_reduce<G>(pw, gl);
+    const float tx = group_transpose_reduce<G>(px, gl);
+    const float ty = group_transpose_reduce<G>(py, gl);
+    if (s < s_end) {
+      __stcs(gaw_u + s, tw);
+      __stcs(reinterpret_cast<float2*>(gloc_u + 2 * s), make_float2(Wf * tx, Hf * ty));
+    }
+    __syncwarp();
+  }
+}
+
+// --------------------------------------------------------------------------
+// generic kernel: one block per (b,q,m) row, threads stride the channels
+// --------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T to_T(float v) { return static_cast<T>(v); }
+template <typename T>
+__device__ __forceinline__ T to_T(double v) { return static_cast<T>(v); }
+template <typename T>
+__device__ __forceinline__ T to_T(__nv_bfloat16 v) { return static_cast<T>(__bfloat162float(v)); }
+
+__device__ __forceinline__ void atomic_add_any(float* p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void atomic_add_any(double* p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void atomic_add_any(__nv_bfloat16* p, float v) {
+  atomicAdd(p, __float2bfloat16_rn(v));
+}
+
+constexpr int kGenericBwdThreads = 128;
+
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* s_part) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_part[warp] = v;
+  __syncthreads();
+  T tot = 0;
+#pragma unroll
+  for (int w = 0; w < kGenericBwdThreads / 32; ++w) tot += s_part[w];
+  __syncthreads();
+  return tot;
+}
+
+template <typename T, typename VT, typename GT>
+__global__ void __launch_bounds__(kGenericBwdThreads)
+msda_bwd_generic_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                        const int64_t* __restrict__ lsi, const T* __restrict__ loc,
+                        const T* __restrict__ aw, const T* __restrict__ grad_out,
+                        GT* __restrict__ grad_value, T* __restrict__ grad_loc,
+                        T* __restrict__ grad_aw, Dims d) {
+  __shared__ T s_part[kGenericBwdThreads / 32];
+  const int64_t n_units = static_cast<int64_t>(d.B) * d.Q * d.M;
+  const int64_t MD = static_cast<int64_t>(d.M) * d.D;
+  for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int m = static_cast<int>(unit % d.M);
+    const int64_t b = unit / d.M / d.Q;
+    const int64_t boff = b * d.S * MD + static_cast<int64_t>(m) * d.D;
+    const T* go = grad_out + unit * d.D;
+    const int LP = d.L * d.P;
+    for (int l = 0; l < d.L; ++l) {
+      const int H = static_cast<int>(shapes[2 * l]);
+      const int W = static_cast<int>(shapes[2 * l + 1]);
+      const int64_t loff = boff + lsi[l] * MD;
+      for (int p = 0; p < d.P; ++p) {
+        const int64_t si = unit * LP + static_cast<int64_t>(l) * d.P + p;
+        const T x = loc[2 * si], y = loc[2 * si + 1], a = aw[si];
+        const T h_im = y * H - T(0.5), w_im = x * W - T(0.5);
+        T sw = 0, sx = 0, sy = 0;
+        const bool inside = h_im > T(-1) && w_im > T(-1) && h_im < T(H) && w_im < T(W);
+        if (inside) {
+          const T hf = floor(h_im), wf = floor(w_im);
+          const int h0 = static_cast<int>(hf), w0 = static_cast<int>(wf);
+          const T lh = h_im - hf, lw = w_im - wf, hh = T(1) - lh, hw = T(1) - lw;
+          const bool r0 = h0 >= 0, r1 = h0 + 1 <= H - 1, c0 = w0 >= 0, c1 = w0 + 1 <= W - 1;
+          const int64_t o00 = loff + (static_cast<int64_t>(h0) * W + w0) * MD;
+          const int64_t o01 = o00 + MD, o10 = o00 + W * MD, o11 = o10 + MD;
+          const T w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+          for (int c = threadIdx.x; c < d.D; c += kGenericBwdThreads) {
+            const T gc = go[c];
+            const T tg = gc * a;
+            const T v1 = (r0 && c0) ? to_T<T>(value[o00 + c]) : T(0);
+            const T v2 = (r0 && c1) ? to_T<T>(value[o01 + c]) : T(0);
+            const T v3 = (r1 && c0) ? to_T<T>(value[o10 + c]) : T(0);
+            const T v4 = (r1 && c1) ? to_T<T>(value[o11 + c]) : T(0);
+            if (r0 && c0) atomic_add_any(grad_value + o00 + c, w1 * tg);
+            if (r0 && c1) atomic_add_any(grad_value + o01 + c, w2 * tg);
+            if (r1 && c0) atomic_add_any(grad_value + o10 + c, w3 * tg);
+            if (r1 && c1) atomic_add_any(grad_value + o11 + c, w4 * tg);
+            sw += gc * (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4);
+            sx += (hh * (v2 - v1) + lh * (v4 - v3)) * tg;
+            sy += (hw * (v3 - v1) + lw * (v4 - v2)) * tg;
+          }
+        }
+        // `inside` is block-uniform, so the barriers inside block_sum are safe
+        sw = block_sum(sw, s_part);
+        sx = block_sum(sx, s_part);
+        sy = block_sum(sy, s_part);
+        if (threadIdx.x == 0) {
+          grad_aw[si] = sw;
+          grad_loc[2 * si] = T(W) * sx;
+          grad_loc[2 * si + 1] = T(H) * sy;
+        }
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------
+// launchers
+// --------------------------------------------------------------------------
+template <int D, typename VT, typename GT>
+static cudaError_t launch_bwd_rows(const void* value, const int64_t* shapes, const int64_t* lsi,
+                                   const float* loc, const float* aw, const float* go, void* gv,
+                                   float* gloc, float* gaw, const Dims& d, int nsplit,
+                                   cudaStream_t st) {
+  constexpr int G = D / Vec16<VT>::VEC;
+  const int64_t threads = static_cast<int64_t>(d.B) * d.Q * d.M * nsplit * G;
+  const int64_t blocks = (threads + kRowsThreads - 1) / kRowsThreads;
+  msda_bwd_rows_kernel<D, VT, GT><<<static_cast<unsigned>(blocks), kRowsThreads, 0, st>>>(
+      static_cast<const VT*>(value), shapes, lsi, loc, aw, go, static_cast<GT*>(gv), gloc, gaw, d,
+      nsplit);
+  note_launches(1);
+  return cudaGetLastError();
+}
+
+static int choose_bwd_split(const Dims& d, int G, int sm_count) {
+  if (tuning().bwd_split > 0) return tuning().bwd_split;
+  const int64_t units = static_cast<int64_t>(d.B) * d.Q * d.M;
+  const int64_t want_groups = static_cast<int64_t>(sm_count) * 64 * (32 / G);
+  const int LP = d.L * d.P;
+  int split = 1;
+  while (split < 64 && units * split < want_groups && LP / (split * 2) >= G) split *= 2;
+  return split;
+}
+
+cudaError_t launch_backward(const void* value, const int64_t* shapes, const int64_t* lsi,
+                            const void* loc, const void* aw, const void* grad_out,
+                            void* grad_value, void* grad_loc, void* grad_aw, const Dims& d,
+                            int dtype, int value_dtype, int grad_value_dtype, int sm_count,
+                            int force_generic, cudaStream_t st) {
+  if (dtype == MSDA_F32 && !force_generic && d.L <= kMaxSmemLevels &&
+      rows_supported(d.D, value_dtype) &&
+      (grad_value_dtype == MSDA_F32 || (grad_value_dtype == MSDA_BF16 && value_dtype == MSDA_BF16))) {
+    const float* locf = static_cast<const float*>(loc);
+    const float* awf = static_cast<const float*>(aw);
+    const float* gof = static_cast<const float*>(grad_out);
+    float* glocf = static_cast<float*>(grad_loc);
+    float* gawf = static_cast<float*>(grad_aw);
+#define MSDA_BWD_CASE(DD)                                                                         \
+  case DD:                                                                                        \
+    if (value_dtype == MSDA_F32) {                                                                \
+      return launch_bwd_rows<DD, float, float>(value, shapes, lsi, locf, awf, gof, grad_value,    \
+                                               glocf, gawf, d,                                    \
+                                               choose_bwd_split(d, DD / 4, sm_count), st);        \
+    } else if (grad_value_dtype == MSDA_F32) {                                                    \
+      return launch_bwd_rows<DD, __nv_bfloat16, float>(value, shapes, lsi, locf, awf, gof,        \
+                                                       grad_value, glocf, gawf, d,                \
+                                                       choose_bwd_split(d, DD / 8, sm_count), st); \
+    } else {                                                                                      \
+      return launch_bwd_rows<DD, __nv_bfloat16, __nv_bfloat16>(                                   \
+          value, shapes, lsi, locf, awf, gof, grad_value, glocf, gawf, d,                         \
+          choose_bwd_split(d, DD / 8, sm_count), st);                                             \
+    }
+    switch (d.D) {
+      MSDA_BWD_CASE(16)
+      MSDA_BWD_CASE(32)
+      MSDA_BWD_CASE(64)
+      default: break;
+    }
+#undef MSDA_BWD_CASE
+  }
+  const int64_t n_units = static_cast<int64_t>(d.B) * d.Q * d.M;
+  const unsigned blocks = static_cast<unsigned>(n_units < (1 << 20) ? n_units : (1 << 20));
+#define MSDA_GEN(T, VT, GT)                                                                    \
+  msda_bwd_generic_kernel<T, VT, GT><<<blocks, kGenericBwdThreads, 0, st>>>(                   \
+      static_cast<const VT*>(value), shapes, lsi, static_cast<const T*>(loc),                  \
+      static_cast<const T*>(aw), static_cast<const T*>(grad_out), static_cast<GT*>(grad_value), \
+      static_cast<T*>(grad_loc), static_cast<T*>(grad_aw), d)
+  if (dtype == MSDA_F32 && value_dtype == MSDA_F32 && grad_value_dtype == MSDA_F32) {
+    MSDA_GEN(float, float, float);
+  } else if (dtype == MSDA_F32 && value_dtype == MSDA_BF16 && grad_value_dtype == MSDA_F32) {
+    MSDA_GEN(float, __nv_bfloat16, float);
+  } else if (dtype == MSDA_F32 && value_dtype == MSDA_BF16 && grad_value_dtype == MSDA_BF16) {
+    MSDA_GEN(float, __nv_bfloat16, __nv_bfloat16);
+  } else if (dtype == MSDA_F64 && value_dtype == MSDA_F64 && grad_value_dtype == MSDA_F64) {
+    MSDA_GEN(double, double, double);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+#undef MSDA_GEN
+  note_launches(1);
+  return cudaGetLastError();
+}
+
+}  // namespace msda

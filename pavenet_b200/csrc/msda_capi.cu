@@ -1,0 +1,330 @@
+// msda_capi.cu — the extern "C" boundary declared in include/pavenet_msda.h.
+// Argument validation, dtype dispatch, error reporting, and the host-buffer
+// convenience entry points.  No torch / ATen here: plain pointers and sizes.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "msda_kernels.h"
+
+namespace msda {
+
+static std::atomic<uint64_t> g_launches{0};
+void note_launches(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+static thread_local char t_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+
+const Tuning& tuning() {
+  static Tuning t = [] {
+    Tuning x;
+    x.force_generic = env_int("PAVENET_MSDA_FORCE_GENERIC", 0);
+    x.fwd_split = env_int("PAVENET_MSDA_FWD_SPLIT", 0);
+    x.bwd_split = env_int("PAVENET_MSDA_BWD_SPLIT", 0);
+    return x;
+  }();
+  return t;
+}
+
+// SM count of the current device, cached per device ordinal.
+static int current_sm_count(int* out) {
+  static std::mutex mu;
+  static int cache[64];
+  static bool have[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(MSDA_ERR_NO_DEVICE, "cudaGetDevice: %s", cudaGetErrorString(e));
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev >= 0 && dev < 64 && have[dev]) {
+    *out = cache[dev];
+    return MSDA_OK;
+  }
+  int n = 0;
+  e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess)
+    return fail(MSDA_ERR_NO_DEVICE, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+  if (dev >= 0 && dev < 64) {
+    cache[dev] = n;
+    have[dev] = true;
+  }
+  *out = n;
+  return MSDA_OK;
+}
+
+static size_t dtype_size(int dt) {
+  switch (dt) {
+    case MSDA_F32: return 4;
+    case MSDA_F64: return 8;
+    case MSDA_BF16: return 2;
+    default: return 0;
+  }
+}
+
+static int check_dims(int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                      int num_query, int num_point, Dims* d) {
+  if (batch <= 0 || spatial_size <= 0 || num_heads <= 0 || channels <= 0 || num_levels <= 0 ||
+      num_query <= 0 || num_point <= 0)
+    return fail(MSDA_ERR_INVALID_ARGUMENT,
+                "all sizes must be positive (batch=%d spatial_size=%d num_heads=%d channels=%d "
+                "num_levels=%d num_query=%d num_point=%d)",
+                batch, spatial_size, num_heads, channels, num_levels, num_query, num_point);
+  // in-kernel offsets inside one batch entry are int32
+  if (static_cast<int64_t>(spatial_size) * num_heads * channels >= (int64_t(1) << 31))
+    return fail(MSDA_ERR_UNSUPPORTED, "spatial_size*num_heads*channels must be < 2^31");
+  if (static_cast<int64_t>(num_levels) * num_point >= (int64_t(1) << 24))
+    return fail(MSDA_ERR_UNSUPPORTED, "num_levels*num_point must be < 2^24");
+  d->B = batch; d->S = spatial_size; d->M = num_heads; d->D = channels;
+  d->L = num_levels; d->Q = num_query; d->P = num_point;
+  return MSDA_OK;
+}
+
+static int check_dtypes(int dtype, int value_dtype, int grad_value_dtype) {
+  if (dtype != MSDA_F32 && dtype != MSDA_F64)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "dtype must be MSDA_F32 or MSDA_F64, got %d", dtype);
+  const bool v_ok = value_dtype == dtype || (dtype == MSDA_F32 && value_dtype == MSDA_BF16);
+  if (!v_ok)
+    return fail(MSDA_ERR_INVALID_ARGUMENT,
+                "value_dtype %d incompatible with dtype %d (same type, or bf16 with f32)",
+                value_dtype, dtype);
+  if (grad_value_dtype >= 0) {
+    const bool g_ok = grad_value_dtype == dtype ||
+                      (value_dtype == MSDA_BF16 && grad_value_dtype == MSDA_BF16);
+    if (!g_ok)
+      return fail(MSDA_ERR_INVALID_ARGUMENT,
+                  "grad_value_dtype %d incompatible with dtype %d / value_dtype %d",
+                  grad_value_dtype, dtype, value_dtype);
+  }
+  return MSDA_OK;
+}
+
+static bool misaligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+
+}  // namespace msda
+
+using namespace msda;
+
+extern "C" {
+
+int msda_abi_version(void) { return MSDA_ABI_VERSION; }
+
+const char* msda_last_error(void) { return t_err; }
+
+uint64_t msda_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char* msda_kernel_name(int channels, int dtype, int value_dtype) {
+  if (dtype == MSDA_F32 && !tuning().force_generic && rows_supported(channels, value_dtype)) {
+    if (value_dtype == MSDA_BF16)
+      return channels == 16 ? "rows<D=16,bf16>" : channels == 32 ? "rows<D=32,bf16>" : "rows<D=64,bf16>";
+    return channels == 16 ? "rows<D=16,f32>" : channels == 32 ? "rows<D=32,f32>" : "rows<D=64,f32>";
+  }
+  return "generic";
+}
+
+int msda_forward(const void* d_value, const int64_t* d_spatial_shapes,
+                 const int64_t* d_level_start_index, const void* d_sampling_loc,
+                 const void* d_attn_weight, void* d_output, int batch, int spatial_size,
+                 int num_heads, int channels, int num_levels, int num_query, int num_point,
+                 int dtype, int value_dtype, void* stream) {
+  if (!d_value || !d_spatial_shapes || !d_level_start_index || !d_sampling_loc || !d_attn_weight ||
+      !d_output)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_forward: NULL pointer argument");
+  Dims d;
+  int rc = check_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, &d);
+  if (rc) return rc;
+  rc = check_dtypes(dtype, value_dtype, -1);
+  if (rc) return rc;
+  int sms = 0;
+  rc = current_sm_count(&sms);
+  if (rc) return rc;
+  // the vector kernels need 16-byte aligned rows; fall back to scalar access otherwise
+  const int generic = tuning().force_generic || misaligned16(d_value) || misaligned16(d_output) ||
+                      misaligned16(d_sampling_loc);
+  const cudaError_t e =
+      launch_forward(d_value, d_spatial_shapes, d_level_start_index, d_sampling_loc, d_attn_weight,
+                     d_output, d, dtype, value_dtype, sms, generic, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess)
+    return fail(MSDA_ERR_CUDA, "msda_forward launch failed: %s", cudaGetErrorString(e));
+  return MSDA_OK;
+}
+
+int msda_backward(const void* d_value, const int64_t* d_spatial_shapes,
+                  const int64_t* d_level_start_index, const void* d_sampling_loc,
+                  const void* d_attn_weight, const void* d_grad_output, void* d_grad_value,
+                  void* d_grad_sampling_loc, void* d_grad_attn_weight, int batch,
+                  int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                  int num_point, int dtype, int value_dtype, int grad_value_dtype, void* stream) {
+  if (!d_value || !d_spatial_shapes || !d_level_start_index || !d_sampling_loc || !d_attn_weight ||
+      !d_grad_output || !d_grad_value || !d_grad_sampling_loc || !d_grad_attn_weight)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_backward: NULL pointer argument");
+  Dims d;
+  int rc = check_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, &d);
+  if (rc) return rc;
+  rc = check_dtypes(dtype, value_dtype, grad_value_dtype);
+  if (rc) return rc;
+  int sms = 0;
+  rc = current_sm_count(&sms);
+  if (rc) return rc;
+  const int generic = tuning().force_generic || misaligned16(d_value) ||
+                      misaligned16(d_grad_output) || misaligned16(d_grad_value) ||
+                      misaligned16(d_sampling_loc) || misaligned16(d_grad_sampling_loc);
+  const cudaError_t e = launch_backward(
+      d_value, d_spatial_shapes, d_level_start_index, d_sampling_loc, d_attn_weight, d_grad_output,
+      d_grad_value, d_grad_sampling_loc, d_grad_attn_weight, d, dtype, value_dtype,
+      grad_value_dtype, sms, generic, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess)
+    return fail(MSDA_ERR_CUDA, "msda_backward launch failed: %s", cudaGetErrorString(e));
+  return MSDA_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer entry points
+// ---------------------------------------------------------------------------
+struct msda_workspace {
+  cudaStream_t stream = nullptr;
+  void* buf = nullptr;   // one grow-only device arena
+  size_t cap = 0;
+};
+
+int msda_workspace_create(msda_workspace** out_ws) {
+  if (!out_ws) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_workspace_create: NULL out pointer");
+  msda_workspace* ws = new msda_workspace();
+  const cudaError_t e = cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ws;
+    return fail(MSDA_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  *out_ws = ws;
+  return MSDA_OK;
+}
+
+void msda_workspace_destroy(msda_workspace* ws) {
+  if (!ws) return;
+  if (ws->buf) cudaFree(ws->buf);
+  if (ws->stream) cudaStreamDestroy(ws->stream);
+  delete ws;
+}
+
+namespace {
+struct Arena {
+  char* base;
+  size_t off = 0;
+  void* take(size_t bytes) {
+    void* p = base + off;
+    off += (bytes + 255) & ~size_t(255);
+    return p;
+  }
+};
+size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
+
+int ws_reserve(msda_workspace* ws, size_t bytes) {
+  if (bytes <= ws->cap) return MSDA_OK;
+  if (ws->buf) cudaFree(ws->buf);
+  ws->buf = nullptr;
+  ws->cap = 0;
+  const cudaError_t e = cudaMalloc(&ws->buf, bytes);
+  if (e != cudaSuccess) return fail(MSDA_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  ws->cap = bytes;
+  return MSDA_OK;
+}
+
+#define MSDA_CU(expr)                                                                     \
+  do {                                                                                    \
+    const cudaError_t e_ = (expr);                                                        \
+    if (e_ != cudaSuccess) return fail(MSDA_ERR_CUDA, #expr ": %s", cudaGetErrorString(e_)); \
+  } while (0)
+}  // namespace
+
+int msda_forward_backward_host(msda_workspace* ws, const void* h_value,
+                               const int64_t* h_spatial_shapes, const int64_t* h_level_start_index,
+                               const void* h_sampling_loc, const void* h_attn_weight,
+                               const void* h_grad_output, void* h_output, void* h_grad_value,
+                               void* h_grad_sampling_loc, void* h_grad_attn_weight, int batch,
+                               int spatial_size, int num_heads, int channels, int num_levels,
+                               int num_query, int num_point, int dtype, int value_dtype) {
+  const bool do_bwd = h_grad_output != nullptr;
+  if (!ws || !h_value || !h_spatial_shapes || !h_level_start_index || !h_sampling_loc ||
+      !h_attn_weight || (!do_bwd && !h_output) ||
+      (do_bwd && (!h_grad_value || !h_grad_sampling_loc || !h_grad_attn_weight)))
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_*_host: NULL pointer argument");
+  Dims d;
+  int rc = check_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, &d);
+  if (rc) return rc;
+  rc = check_dtypes(dtype, value_dtype, do_bwd ? dtype : -1);
+  if (rc) return rc;
+  const size_t es = dtype_size(dtype), vs = dtype_size(value_dtype);
+  const size_t n_val = static_cast<size_t>(batch) * spatial_size * num_heads * channels;
+  const size_t n_smp = static_cast<size_t>(batch) * num_query * num_heads * num_levels * num_point;
+  const size_t n_out = static_cast<size_t>(batch) * num_query * num_heads * channels;
+  const size_t b_val = n_val * vs, b_loc = n_smp * 2 * es, b_aw = n_smp * es, b_out = n_out * es;
+  const size_t b_shp = static_cast<size_t>(num_levels) * 2 * 8, b_lsi = static_cast<size_t>(num_levels) * 8;
+  // grad_value is accumulated in `dtype` on the device and returned in `dtype`
+  const size_t b_gval = n_val * es;
+  size_t need = pad256(b_val) + pad256(b_loc) + pad256(b_aw) + pad256(b_out) + pad256(b_shp) + pad256(b_lsi);
+  if (do_bwd) need += pad256(b_out) + pad256(b_gval) + pad256(b_loc) + pad256(b_aw);
+  rc = ws_reserve(ws, need);
+  if (rc) return rc;
+  Arena ar{static_cast<char*>(ws->buf)};
+  void* d_val = ar.take(b_val);
+  void* d_loc = ar.take(b_loc);
+  void* d_aw = ar.take(b_aw);
+  void* d_out = ar.take(b_out);
+  int64_t* d_shp = static_cast<int64_t*>(ar.take(b_shp));
+  int64_t* d_lsi = static_cast<int64_t*>(ar.take(b_lsi));
+  cudaStream_t st = ws->stream;
+  MSDA_CU(cudaMemcpyAsync(d_shp, h_spatial_shapes, b_shp, cudaMemcpyHostToDevice, st));
+  MSDA_CU(cudaMemcpyAsync(d_lsi, h_level_start_index, b_lsi, cudaMemcpyHostToDevice, st));
+  MSDA_CU(cudaMemcpyAsync(d_val, h_value, b_val, cudaMemcpyHostToDevice, st));
+  MSDA_CU(cudaMemcpyAsync(d_loc, h_sampling_loc, b_loc, cudaMemcpyHostToDevice, st));
+  MSDA_CU(cudaMemcpyAsync(d_aw, h_attn_weight, b_aw, cudaMemcpyHostToDevice, st));
+  if (h_output) {
+    rc = msda_forward(d_val, d_shp, d_lsi, d_loc, d_aw, d_out, batch, spatial_size, num_heads,
+                      channels, num_levels, num_query, num_point, dtype, value_dtype, st);
+    if (rc) return rc;
+    MSDA_CU(cudaMemcpyAsync(h_output, d_out, b_out, cudaMemcpyDeviceToHost, st));
+  }
+  if (do_bwd) {
+    void* d_go = ar.take(b_out);
+    void* d_gval = ar.take(b_gval);
+    void* d_gloc = ar.take(b_loc);
+    void* d_gaw = ar.take(b_aw);
+    MSDA_CU(cudaMemcpyAsync(d_go, h_grad_output, b_out, cudaMemcpyHostToDevice, st));
+    MSDA_CU(cudaMemsetAsync(d_gval, 0, b_gval, st));
+    rc = msda_backward(d_val, d_shp, d_lsi, d_loc, d_aw, d_go, d_gval, d_gloc, d_gaw, batch,
+                       spatial_size, num_heads, channels, num_levels, num_query, num_point, dtype,
+                       value_dtype, dtype, st);
+    if (rc) return rc;
+    MSDA_CU(cudaMemcpyAsync(h_grad_value, d_gval, b_gval, cudaMemcpyDeviceToHost, st));
+    MSDA_CU(cudaMemcpyAsync(h_grad_sampling_loc, d_gloc, b_loc, cudaMemcpyDeviceToHost, st));
+    MSDA_CU(cudaMemcpyAsync(h_grad_attn_weight, d_gaw, b_aw, cudaMemcpyDeviceToHost, st));
+  }
+  MSDA_CU(cudaStreamSynchronize(st));
+  return MSDA_OK;
+}
+
+int msda_forward_host(msda_workspace* ws, const void* h_value, const int64_t* h_spatial_shapes,
+                      const int64_t* h_level_start_index, const void* h_sampling_loc,
+                      const void* h_attn_weight, void* h_output, int batch, int spatial_size,
+                      int num_heads, int channels, int num_levels, int num_query, int num_point,
+                      int dtype, int value_dtype) {
+  return msda_forward_backward_host(ws, h_value, h_spatial_shapes, h_level_start_index,
+                                    h_sampling_loc, h_attn_weight, nullptr, h_output, nullptr,
+                                    nullptr, nullptr, batch, spatial_size, num_heads, channels,
+                                    num_levels, num_query, num_point, dtype, value_dtype);
+}
+
+}  // extern "C"

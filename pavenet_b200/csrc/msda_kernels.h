@@ -1,0 +1,38 @@
+// msda_kernels.h — internal interface between the C ABI (msda_capi.cu) and
+// the kernel translation units.  Not installed; the public contract is
+// include/pavenet_msda.h.
+#pragma once
+
+#include "../../include/pavenet_msda.h"
+#include "msda_common.cuh"
+
+namespace msda {
+
+// Tuning knobs, settable through environment variables read once at load
+// (PAVENET_MSDA_FORCE_GENERIC=1, PAVENET_MSDA_BWD_SPLIT=n) — used by tests
+// to pin a kernel family and by the bench to sweep.
+struct Tuning {
+  int force_generic = 0;
+  int fwd_split = 0;  // 0 = heuristic
+  int bwd_split = 0;  // 0 = heuristic
+};
+const Tuning& tuning();
+
+bool rows_supported(int D, int value_dtype);
+int choose_split(const Dims& d, int G, int sm_count);
+
+cudaError_t launch_forward(const void* value, const int64_t* shapes, const int64_t* lsi,
+                           const void* loc, const void* aw, void* out, const Dims& d, int dtype,
+                           int value_dtype, int sm_count, int force_generic, cudaStream_t st);
+
+cudaError_t launch_backward(const void* value, const int64_t* shapes, const int64_t* lsi,
+                            const void* loc, const void* aw, const void* grad_out,
+                            void* grad_value, void* grad_loc, void* grad_aw, const Dims& d,
+                            int dtype, int value_dtype, int grad_value_dtype, int sm_count,
+                            int force_generic, cudaStream_t st);
+
+// number of kernel launches the last launch_* call on this thread enqueued
+int last_launches();
+void note_launches(int n);
+
+}  // namespace msda

@@ -1,0 +1,235 @@
+"""Operator boundary: `MultiScaleDeformableAttnFunction` and the `ext_module`
+shim, with the reference's exact names, argument order and error behaviour,
+running on the sm_100a kernels behind the C ABI (`include/pavenet_msda.h`).
+
+Reference being mirrored:
+  * `MultiScaleDeformableAttnFunction`  third_party/mmcv/mmcv/ops/multi_scale_deform_attn.py:20-89
+  * `ext_module.ms_deform_attn_forward/backward` (pybind kwargs)
+        third_party/mmcv/mmcv/ops/csrc/pytorch/pybind.cpp:737-748
+  * host-side checks  third_party/mmcv/mmcv/ops/csrc/pytorch/cuda/ms_deform_attn_cuda.cu:209-245, 279-318
+
+There is deliberately no CPU / PyTorch fallback in this module.
+"""
+import torch
+from torch.autograd.function import Function, once_differentiable
+
+from . import _capi
+
+__all__ = [
+    'MultiScaleDeformableAttnFunction', 'ext_module', 'ms_deform_attn_forward',
+    'ms_deform_attn_backward', 'fuse_frames_as_levels', 'BF16_GRAD_VALUE_ATOMICS',
+]
+
+#: When value is stored in bf16, accumulate grad_value in an fp32 scratch
+#: buffer and round once at the end (False, default, accurate) or let the
+#: kernel reduce straight into a bf16 tensor with packed bf16x2 atomics
+#: (True: half the scatter bytes, every partial sum rounded to 8 bits).
+BF16_GRAD_VALUE_ATOMICS = False
+
+_DTYPE_CODE = {
+    torch.float32: _capi.MSDA_F32,
+    torch.float64: _capi.MSDA_F64,
+    torch.bfloat16: _capi.MSDA_BF16,
+}
+
+
+def _check_inputs(value, spatial_shapes, level_start_index, sampling_loc,
+                  attn_weight, im2col_step):
+    """The reference's AT_ASSERTM / device-consistency checks, as RuntimeError."""
+    named = (('value', value), ('spatial_shapes', spatial_shapes),
+             ('level_start_index', level_start_index),
+             ('sampling_loc', sampling_loc), ('attn_weight', attn_weight))
+    for name, t in named:
+        if not isinstance(t, torch.Tensor):
+            raise TypeError('%s must be a torch.Tensor, got %s' % (name, type(t)))
+        if not t.is_contiguous():
+            raise RuntimeError('%s tensor has to be contiguous' % name)
+        if not t.is_cuda:
+            raise RuntimeError('%s must be a CUDA tensor' % name)
+        if t.device != value.device:
+            # pytorch_device_registry.hpp:116-122
+            raise RuntimeError('%s is on %s but value is on %s: all tensors must '
+                               'be on the same device' % (name, t.device, value.device))
+    if value.dim() != 4:
+        raise RuntimeError('value must have shape (bs, num_keys, num_heads, dim_per_head), '
+                           'got %s' % (tuple(value.shape),))
+    if sampling_loc.dim() != 6 or sampling_loc.shape[-1] != 2:
+        raise RuntimeError('sampling_locations must have shape (bs, num_queries, num_heads, '
+                           'num_levels, num_points, 2), got %s' % (tuple(sampling_loc.shape),))
+    B, S, M, D = value.shape
+    Bq, Q, Mq, L, P, _ = sampling_loc.shape
+    if (Bq, Mq) != (B, M):
+        raise RuntimeError('sampling_locations %s does not match value %s in batch / heads'
+                           % (tuple(sampling_loc.shape), tuple(value.shape)))
+    if tuple(attn_weight.shape) != (B, Q, M, L, P):
+        raise RuntimeError('attention_weights must have shape %s, got %s'
+                           % ((B, Q, M, L, P), tuple(attn_weight.shape)))
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise RuntimeError('spatial_shapes and level_start_index must be int64 tensors')
+    if tuple(spatial_shapes.shape) != (L, 2) or tuple(level_start_index.shape) != (L,):
+        raise RuntimeError('spatial_shapes must be (%d, 2) and level_start_index (%d,), got %s / %s'
+                           % (L, L, tuple(spatial_shapes.shape), tuple(level_start_index.shape)))
+    if sampling_loc.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError('sampling_locations must be float32 or float64, got %s'
+                           % sampling_loc.dtype)
+    if attn_weight.dtype != sampling_loc.dtype:
+        raise RuntimeError('attention_weights dtype %s != sampling_locations dtype %s'
+                           % (attn_weight.dtype, sampling_loc.dtype))
+    if value.dtype != sampling_loc.dtype and not (
+            value.dtype == torch.bfloat16 and sampling_loc.dtype == torch.float32):
+        raise RuntimeError('value dtype %s incompatible with sampling_locations dtype %s '
+                           '(same dtype, or bfloat16 value with float32 locations)'
+                           % (value.dtype, sampling_loc.dtype))
+    step = min(B, int(im2col_step))
+    if B > 0 and (step <= 0 or B % step != 0):
+        # ms_deform_attn_cuda.cu:242-245
+        raise RuntimeError('batch(%d) must divide im2col_step(%d)' % (B, step))
+    return B, S, M, D, L, Q, P
+
+
+def ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index,
+                           sampling_locations, attention_weights, im2col_step=64):
+    """Drop-in for `ext_module.ms_deform_attn_forward` (pybind.cpp:737-742).
+
+    Returns a new tensor of shape (bs, num_queries, num_heads*dim_per_head)
+    in the dtype of `sampling_locations`.
+    """
+    B, S, M, D, L, Q, P = _check_inputs(value, value_spatial_shapes, value_level_start_index,
+                                        sampling_locations, attention_weights, im2col_step)
+    lib = _capi.load()
+    if min(B, S, M, D, L, Q, P) == 0:
+        # nothing to sample (or nothing to write): the sum over an empty set
+        return torch.zeros((B, Q, M * D), dtype=sampling_locations.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        output = torch.empty((B, Q, M * D), dtype=sampling_locations.dtype, device=value.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        status = lib.msda_forward(
+            value.data_ptr(), value_spatial_shapes.data_ptr(), value_level_start_index.data_ptr(),
+            sampling_locations.data_ptr(), attention_weights.data_ptr(), output.data_ptr(),
+            B, S, M, D, L, Q, P, _DTYPE_CODE[sampling_locations.dtype], _DTYPE_CODE[value.dtype],
+            stream)
+    _capi.check(status, 'msda_forward')
+    return output
+
+
+def ms_deform_attn_backward(value, value_spatial_shapes, value_level_start_index,
+                            sampling_locations, attention_weights, grad_output, grad_value,
+                            grad_sampling_loc, grad_attn_weight, im2col_step=64):
+    """Drop-in for `ext_module.ms_deform_attn_backward` (pybind.cpp:743-748).
+
+    Accumulates into `grad_value` (caller zero-fills it, as
+    multi_scale_deform_attn.py:72-74 does) and overwrites the other two.
+    """
+    B, S, M, D, L, Q, P = _check_inputs(value, value_spatial_shapes, value_level_start_index,
+                                        sampling_locations, attention_weights, im2col_step)
+    for name, t, like in (('grad_output', grad_output, None),
+                          ('grad_value', grad_value, value),
+                          ('grad_sampling_loc', grad_sampling_loc, sampling_locations),
+                          ('grad_attn_weight', grad_attn_weight, attention_weights)):
+        if not t.is_contiguous():
+            raise RuntimeError('%s tensor has to be contiguous' % name)
+        if not t.is_cuda or t.device != value.device:
+            raise RuntimeError('%s must be a CUDA tensor on %s' % (name, value.device))
+        if like is not None and t.shape != like.shape:
+            raise RuntimeError('%s has shape %s, expected %s'
+                               % (name, tuple(t.shape), tuple(like.shape)))
+    if grad_output.numel() != B * Q * M * D or grad_output.dtype != sampling_locations.dtype:
+        raise RuntimeError('grad_output must hold %d %s elements, got %s %s'
+                           % (B * Q * M * D, sampling_locations.dtype,
+                              tuple(grad_output.shape), grad_output.dtype))
+    if (grad_sampling_loc.dtype != sampling_locations.dtype or
+            grad_attn_weight.dtype != sampling_locations.dtype):
+        raise RuntimeError('location / weight gradients must have dtype %s'
+                           % sampling_locations.dtype)
+    if grad_value.dtype not in (sampling_locations.dtype, value.dtype):
+        raise RuntimeError('grad_value dtype %s must be %s or %s'
+                           % (grad_value.dtype, sampling_locations.dtype, value.dtype))
+    lib = _capi.load()
+    if min(B, S, M, D, L, Q, P) == 0:
+        grad_sampling_loc.zero_()
+        grad_attn_weight.zero_()
+        return
+    with torch.cuda.device(value.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        status = lib.msda_backward(
+            value.data_ptr(), value_spatial_shapes.data_ptr(), value_level_start_index.data_ptr(),
+            sampling_locations.data_ptr(), attention_weights.data_ptr(), grad_output.data_ptr(),
+            grad_value.data_ptr(), grad_sampling_loc.data_ptr(), grad_attn_weight.data_ptr(),
+            B, S, M, D, L, Q, P, _DTYPE_CODE[sampling_locations.dtype], _DTYPE_CODE[value.dtype],
+            _DTYPE_CODE[grad_value.dtype], stream)
+    _capi.check(status, 'msda_backward')
+
+
+class _ExtModule(object):
+    """Stands in for `mmcv._ext` as far as this op is concerned
+    (multi_scale_deform_attn.py:16-17 loads exactly these two attributes)."""
+    ms_deform_attn_forward = staticmethod(ms_deform_attn_forward)
+    ms_deform_attn_backward = staticmethod(ms_deform_attn_backward)
+
+
+ext_module = _ExtModule()
+
+
+class MultiScaleDeformableAttnFunction(Function):
+    """Same `apply` signature and return shape as the reference
+    (multi_scale_deform_attn.py:20-89)."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index,
+                sampling_locations, attention_weights, im2col_step):
+        """
+        Args:
+            value: (bs, num_keys, num_heads, embed_dims // num_heads)
+            value_spatial_shapes: (num_levels, 2) int64 on the GPU, (h, w)
+            value_level_start_index: (num_levels,) int64 on the GPU
+            sampling_locations: (bs, num_queries, num_heads, num_levels, num_points, 2),
+                normalised (x, y)
+            attention_weights: (bs, num_queries, num_heads, num_levels, num_points)
+            im2col_step: int; only validated (batch % min(batch, step) == 0),
+                it never changes results
+
+        Returns:
+            (bs, num_queries, embed_dims)
+        """
+        ctx.im2col_step = im2col_step
+        output = ext_module.ms_deform_attn_forward(
+            value, value_spatial_shapes, value_level_start_index, sampling_locations,
+            attention_weights, im2col_step=ctx.im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index,
+                              sampling_locations, attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, value_spatial_shapes, value_level_start_index, \
+            sampling_locations, attention_weights = ctx.saved_tensors
+        acc_dtype = sampling_locations.dtype
+        if value.dtype == torch.bfloat16 and BF16_GRAD_VALUE_ATOMICS:
+            acc_dtype = torch.bfloat16
+        grad_value = torch.zeros(value.shape, dtype=acc_dtype, device=value.device)
+        # fully overwritten by the kernels: no zero-fill needed
+        grad_sampling_loc = torch.empty_like(sampling_locations)
+        grad_attn_weight = torch.empty_like(attention_weights)
+        ext_module.ms_deform_attn_backward(
+            value, value_spatial_shapes, value_level_start_index, sampling_locations,
+            attention_weights, grad_output.contiguous(), grad_value, grad_sampling_loc,
+            grad_attn_weight, im2col_step=ctx.im2col_step)
+        if grad_value.dtype != value.dtype:
+            grad_value = grad_value.to(value.dtype)
+        return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
+
+
+def fuse_frames_as_levels(spatial_shapes, level_start_index, num_frames, num_keys):
+    """Level tables for sampling T frames in ONE op call.
+
+    The T frames of a clip are adjacent in the batch dimension, so
+    `value.view(clips, T*num_keys, heads, dim)` is a zero-copy view in which
+    frame t's level l is "level" t*L+l, starting at `t*num_keys + start_l`
+    (SURVEY.md section 3.3).  Built with device ops only: no host sync.
+    """
+    shapes = spatial_shapes.repeat(num_frames, 1)
+    frame_base = torch.arange(num_frames, device=level_start_index.device,
+                              dtype=level_start_index.dtype) * num_keys
+    starts = (frame_base[:, None] + level_start_index[None, :]).reshape(-1)
+    return shapes.contiguous(), starts.contiguous()

@@ -1,0 +1,154 @@
+"""Pins the CPU oracle (oracle/) to the golden vectors produced by executing
+the reference (tests/golden/gen_golden.py).  CPU only."""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import msda_oracle as O
+
+OP_CASES = ['mmcv_f64', 'mmcv_f32', 'gradcheck_c4', 'gradcheck_c30', 'gradcheck_c32',
+            'gradcheck_c64', 'gradcheck_c71', 'gradcheck_c1025', 'enc_f32', 'enc_f64',
+            'pose17_f32', 'pose15_f64', 'd16_f32', 'd64_f32', 'edge_f32', 'edge_f64']
+
+
+def _tol(dtype):
+    return 2e-6 if dtype == torch.float32 else 1e-13
+
+
+def _grad_queries(name, t):
+    """Exact-border / exact-pixel-centre locations are points where the
+    bilinear surface has a kink: the location gradient is one-sided there, so
+    for the hand-placed edge cases only the nudged queries are compared."""
+    return slice(1, None) if name.startswith('edge') else slice(None)
+
+
+@pytest.mark.parametrize('name', OP_CASES)
+def test_c_oracle_matches_reference(op_golden, name):
+    c = op_golden.case(name)
+    lsi = O.level_start_index(c['shapes'])
+    tol = _tol(c['loc'].dtype)
+    out = O.c_forward(c['value'], c['shapes'], lsi, c['loc'], c['aw'])
+    assert out.dtype == c['out'].dtype
+    assert rel_err(out, c['out']) < tol
+    gv, gl, ga = O.c_backward(c['value'], c['shapes'], lsi, c['loc'], c['aw'], c['grad_out'])
+    q = _grad_queries(name, c)
+    assert rel_err(gv[:, :], c['grad_value']) < tol or name.startswith('edge')
+    assert rel_err(gl[:, q], c['grad_loc'][:, q]) < tol
+    assert rel_err(ga, c['grad_aw']) < tol
+
+
+@pytest.mark.parametrize('name', OP_CASES)
+def test_grid_sample_port_matches_reference(op_golden, name):
+    c = op_golden.case(name)
+    v = c['value'].clone().requires_grad_()
+    loc = c['loc'].clone().requires_grad_()
+    aw = c['aw'].clone().requires_grad_()
+    out = O.grid_sample_port(v, c['shapes'], loc, aw)
+    out.backward(c['grad_out'])
+    tol = _tol(loc.dtype)
+    assert rel_err(out, c['out']) < tol
+    assert rel_err(v.grad, c['grad_value']) < tol
+    assert rel_err(loc.grad, c['grad_loc']) < tol
+    assert rel_err(aw.grad, c['grad_aw']) < tol
+
+
+def test_mmcv_float_tolerances(op_golden):
+    """The bounds of test_forward_equal_with_pytorch_float
+    (test_ms_deformable_attn.py:106-135), applied to the C oracle in fp32."""
+    c = op_golden.case('mmcv_f32')
+    out = O.c_forward(c['value'], c['shapes'], None, c['loc'], c['aw'])
+    assert torch.allclose(out, c['out'], rtol=1e-2, atol=1e-3)
+    assert (out - c['out']).abs().max() < 1e-9
+    assert ((out - c['out']).abs() / c['out'].abs()).max() < 1e-6
+
+
+def test_nonfinite_locations_are_skipped(op_golden):
+    """NaN / Inf locations fail the range test and contribute nothing
+    (SURVEY.md Appendix A).  The clean output is the reference's; poisoning
+    locations whose weight we zero must leave it unchanged."""
+    c = op_golden.case('nonfinite_f32')
+    loc, aw = c['loc'].clone(), c['aw'].clone()
+    loc[0, 0, 0, 0, 0, 0] = float('nan')
+    loc[0, 1, 1, 1, 2, 1] = float('inf')
+    loc[0, 2, 0, 3, 1, 0] = -float('inf')
+    out = O.c_forward(c['value'], c['shapes'], None, loc, aw)
+    assert torch.isfinite(out).all()
+    # expected = clean output minus the contributions of the poisoned samples
+    aw0 = aw.clone()
+    aw0[0, 0, 0, 0, 0] = 0
+    aw0[0, 1, 1, 1, 2] = 0
+    aw0[0, 2, 0, 3, 1] = 0
+    expect = O.grid_sample_port(c['value'], c['shapes'], c['loc'], aw0)
+    assert rel_err(out, expect) < 2e-6
+
+
+def _module_args(c):
+    state = {k[len('state.'):]: v for k, v in c.items() if k.startswith('state.')}
+    cfg = {k[len('cfg.'):]: int(v) for k, v in c.items() if k.startswith('cfg.')}
+    inp = {k[len('in.'):]: v for k, v in c.items() if k.startswith('in.')}
+    return state, cfg, inp
+
+
+def test_encoder_composition(module_golden):
+    for name in ('encoder', 'encoder_box'):
+        state, cfg, inp = _module_args(module_golden.case(name))
+        out = O.encoder_attention_ref(
+            state, cfg, inp['query'], value=inp.get('value'), query_pos=inp.get('query_pos'),
+            key_padding_mask=inp.get('key_padding_mask'),
+            reference_points=inp['reference_points'], spatial_shapes=inp['spatial_shapes'])
+        assert rel_err(out, module_golden.case(name)['out']) < 1e-5
+
+
+def test_pose_composition(module_golden):
+    state, cfg, inp = _module_args(module_golden.case('pose'))
+    out = O.pose_attention_ref(state, cfg, inp['query'], inp['value'], query_pos=inp['query_pos'],
+                               key_padding_mask=inp['key_padding_mask'],
+                               reference_points=inp['reference_points'],
+                               spatial_shapes=inp['spatial_shapes'])
+    assert rel_err(out, module_golden.case('pose')['out']) < 1e-5
+
+
+@pytest.mark.parametrize('T', [3, 5])
+def test_mulframes_pose_composition(module_golden, T):
+    c = module_golden.case('mf_pose%d' % T)
+    state, cfg, inp = _module_args(c)
+    out = O.mulframes_pose_attention_ref(
+        state, cfg, inp['query'], inp['value'], query_pos=inp['query_pos'],
+        key_padding_mask=inp['key_padding_mask'], reference_points=inp['reference_points'],
+        spatial_shapes=inp['spatial_shapes'])
+    assert rel_err(out, c['out']) < 1e-5
+
+
+@pytest.mark.parametrize('T', [3, 5])
+def test_mulframes_joint_composition(module_golden, T):
+    c = module_golden.case('mf_joint%d' % T)
+    state, cfg, inp = _module_args(c)
+    out = O.mulframes_joint_attention_ref(
+        state, cfg, inp['query'], inp['value'], query_pos=inp['query_pos'],
+        key_padding_mask=inp['key_padding_mask'], reference_points=inp['reference_points'],
+        spatial_shapes=inp['spatial_shapes'])
+    assert rel_err(out, c['out']) < 1e-5
+
+
+def test_c_oracle_agrees_with_port_on_random_shapes():
+    """Two independent restatements (scalar C loops vs grid_sample) on shapes
+    not in the fixtures, including ragged level sizes."""
+    g = torch.Generator().manual_seed(77)
+    for shapes, M, D, Q, P in (([(7, 3), (1, 9), (5, 5)], 3, 5, 13, 3),
+                               ([(1, 1)], 1, 1, 1, 1),
+                               ([(13, 21), (25, 42)], 8, 32, 10, 15)):
+        shapes = torch.tensor(shapes)
+        S = int(shapes.prod(1).sum())
+        L = shapes.shape[0]
+        v = torch.randn(2, S, M, D, generator=g, dtype=torch.float64)
+        loc = torch.rand(2, Q, M, L, P, 2, generator=g, dtype=torch.float64) * 1.4 - 0.2
+        aw = torch.rand(2, Q, M, L, P, generator=g, dtype=torch.float64)
+        go = torch.randn(2, Q, M * D, generator=g, dtype=torch.float64)
+        vv, ll, aa = v.clone().requires_grad_(), loc.clone().requires_grad_(), aw.clone().requires_grad_()
+        ref = O.grid_sample_port(vv, shapes, ll, aa)
+        ref.backward(go)
+        assert rel_err(O.c_forward(v, shapes, None, loc, aw), ref) < 1e-13
+        gv, gl, ga = O.c_backward(v, shapes, None, loc, aw, go)
+        assert rel_err(gv, vv.grad) < 1e-13
+        assert rel_err(gl, ll.grad) < 1e-12
+        assert rel_err(ga, aa.grad) < 1e-13
