@@ -1,0 +1,491 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the multi-scale deformable attention hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload encoder_cfg2|pose_cfg3|pose_cfg3_t3|petr_cfg1|stress_cfg5]
+                    [--value-dtype f32|bf16]
+
+A "step" is one forward + backward pass of the op over one clip of synthetic,
+PAVE-Net-shaped input (BASELINE.json configs[1] by default: spatial-encoder
+attention, R-50 features of a 3-frame clip at 800x1333, 8 heads x 4 levels x 4
+points, 66 669 queries).  Metric: queries/s (whole job, all GPUs).
+
+Prints ONE JSON line on stdout (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel (backward): algorithmic bytes / CUDA-event
+                duration against the measured HBM copy peak
+  roofline_fwd / roofline_step   the same for the forward kernel and for the
+                whole step (fwd + grad_value zero-fill + bwd)
+  cpu_baseline  the reference's CPU path (per-level grid_sample + autograd),
+                restated in oracle/msda_oracle.py, timed on this host's cores
+  e2e           the same metric through MultiScaleDeformableAttnFunction with
+                pinned HOST buffers: H2D of the inputs and D2H of output and
+                gradients inside the timed region
+Multi-GPU: clips are independent, so each rank runs its own clips (weak
+scaling) with no collective on the data path; one all-reduce(MAX) of the
+elapsed time at the end.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+R50_LEVELS = [(100, 167), (50, 84), (25, 42), (13, 21)]       # 800x1333, strides 8/16/32/64
+BIG_LEVELS = [(150, 250), (75, 125), (38, 63), (19, 32)]      # 1200x2000
+
+WORKLOADS = {
+    # name: (description, frames-as-batch B, fused frames T, queries, points, levels, kind)
+    'encoder_cfg2': dict(desc='PAVE-Net spatial-encoder MSDA fwd+bwd, R-50 800x1333, 3-frame clip, '
+                              '8 heads x 4 levels x 4 points', B=3, T=1, Q=None, P=4,
+                         levels=R50_LEVELS, kind='encoder'),
+    'pose_cfg3': dict(desc='pose-decoder pose-aware attention fused over T=5 frames, 300 pose queries '
+                           'x 17 keypoints, R-50 800x1333', B=1, T=5, Q=300, P=17,
+                      levels=R50_LEVELS, kind='pose'),
+    'pose_cfg3_t3': dict(desc='pose-decoder pose-aware attention fused over T=3 frames, 300 pose '
+                              'queries x 15 keypoints (PoseTrack config)', B=1, T=3, Q=300, P=15,
+                         levels=R50_LEVELS, kind='pose'),
+    'petr_cfg1': dict(desc='PETR pose attention, 1 frame, 300 queries x 17 keypoints', B=1, T=1,
+                      Q=300, P=17, levels=R50_LEVELS, kind='pose'),
+    'stress_cfg5': dict(desc='encoder stress: 8 frames at 800x1333, 4 levels x 4 points', B=8, T=1,
+                        Q=None, P=4, levels=R50_LEVELS, kind='encoder'),
+}
+M_HEADS, D_HEAD = 8, 32
+
+
+# ---------------------------------------------------------------------------
+# synthetic inputs
+# ---------------------------------------------------------------------------
+def make_problem(wl, seed, device, value_dtype=torch.float32, frames=None):
+    """Seeded synthetic inputs of one step, generated on `device`.
+
+    encoder: queries are the pixels of all levels; locations = reference grid
+    + the module's ring-offset init (multi_scale_deform_attn.py:286-297) + N(0,1)
+    pixels of noise — spatially coherent, like a trained encoder.
+    pose: per-query pose box (centre ~U(0.1,0.9), size ~U(0.05,0.4)), K keypoints
+    uniform in the box + N(0,0.02) offsets, small drift between frames.
+    """
+    cfg = WORKLOADS[wl]
+    g = torch.Generator(device=device).manual_seed(seed)
+    levels = cfg['levels']
+    T, P = cfg['T'], cfg['P']
+    B = frames if frames is not None else cfg['B']
+    L = len(levels)
+    S = sum(h * w for h, w in levels)
+    M, D = M_HEADS, D_HEAD
+    shapes = torch.tensor(levels, dtype=torch.int64, device=device)
+    sizes = shapes[:, 0] * shapes[:, 1]
+    lsi = torch.cat([sizes.new_zeros(1), sizes.cumsum(0)[:-1]])
+
+    def randn(*s):
+        return torch.randn(*s, generator=g, device=device)
+
+    def rand(*s):
+        return torch.rand(*s, generator=g, device=device)
+
+    if cfg['kind'] == 'encoder':
+        Q = S
+        ref = []
+        for h, w in levels:
+            ys = (torch.arange(h, device=device, dtype=torch.float32) + 0.5) / h
+            xs = (torch.arange(w, device=device, dtype=torch.float32) + 0.5) / w
+            yy, xx = torch.meshgrid(ys, xs, indexing='ij')
+            ref.append(torch.stack([xx.reshape(-1), yy.reshape(-1)], -1))
+        ref = torch.cat(ref)                                            # (S, 2)
+        th = torch.arange(M, device=device, dtype=torch.float32) * (2.0 * torch.pi / M)
+        ring = torch.stack([th.cos(), th.sin()], -1)
+        ring = ring / ring.abs().max(-1, keepdim=True)[0]
+        steps = torch.arange(1, P + 1, device=device, dtype=torch.float32)
+        off = ring[:, None, None, :] * steps[None, None, :, None]          # (M,1,P,2)
+        norm = torch.tensor([[w, h] for h, w in levels], dtype=torch.float32, device=device)
+        loc = ref[None, :, None, None, None, :] + (
+            off[None, None] + randn(B, Q, M, L, P, 2)) / norm[None, None, None, :, None, :]
+        Lk = L
+    else:
+        Q = cfg['Q']
+        Lk = T * L
+        centre = rand(B, Q, 1, 1, 1, 2) * 0.8 + 0.1
+        size = rand(B, Q, 1, 1, 1, 2) * 0.35 + 0.05
+        kpt = centre + (rand(B, Q, 1, 1, P, 2) - 0.5) * size                 # shared by levels
+        drift = randn(B, Q, 1, T, 1, 1, 2) * 0.01                             # per frame
+        loc = (kpt[:, :, :, None] + drift).expand(B, Q, 1, T, L, P, 2)
+        loc = loc.reshape(B, Q, 1, Lk, P, 2) + randn(B, Q, M, Lk, P, 2) * 0.02
+        shapes = shapes.repeat(T, 1)
+        lsi = (torch.arange(T, device=device)[:, None] * S + lsi[None, :]).reshape(-1)
+    value = randn(B, T * S, M, D).to(value_dtype)
+    aw = torch.softmax(randn(B, Q, M, Lk * P), -1).view(B, Q, M, Lk, P)
+    grad_out = randn(B, Q, M * D)
+    return dict(value=value.contiguous(), shapes=shapes.contiguous(), lsi=lsi.contiguous(),
+                loc=loc.contiguous(), aw=aw.contiguous(), grad_out=grad_out.contiguous(),
+                dims=dict(B=B, S=T * S, M=M, D=D, L=Lk, Q=Q, P=P))
+
+
+def algorithmic_bytes(dims, value_bytes=4, grad_value_bytes=4):
+    """unique bytes a perfect kernel must move.
+    fwd = V + LOC + W + O;  bwd = V + LOC + W + O(grad_out) + Vg + LOC(grad) + W(grad)
+    with V = min(value bytes, bytes actually sampled)."""
+    B, S, M, D, L, Q, P = (dims[k] for k in 'BSMDLQP')
+    n_s = B * Q * M * L * P
+    V = min(B * S * M * D * value_bytes, n_s * 4 * D * value_bytes)
+    Vg = min(B * S * M * D * grad_value_bytes, n_s * 4 * D * grad_value_bytes)
+    LOC, W, O = 8 * n_s, 4 * n_s, 4 * B * Q * M * D
+    return dict(fwd=V + LOC + W + O, bwd=V + LOC + W + O + Vg + LOC + W)
+
+
+# ---------------------------------------------------------------------------
+# clocks (NVML) sampled during the timed region
+# ---------------------------------------------------------------------------
+class ClockSampler(object):
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:  # noqa: BLE001 - clocks are diagnostics, never fatal
+            self._nv = None
+            self.error = str(exc)
+
+    _REASONS = (('hw_slowdown', 0x8), ('sw_power_cap', 0x4), ('sw_thermal_slowdown', 0x20),
+                ('hw_thermal_slowdown', 0x40), ('hw_power_brake_slowdown', 0x80),
+                ('sync_boost', 0x10), ('applications_clocks_setting', 0x2))
+
+    def _once(self):
+        nv = self._nv
+        self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        try:
+            bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+        except Exception:  # noqa: BLE001
+            bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        for name, bit in self._REASONS:
+            if bits & bit:
+                self.reasons.add(name)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._once()
+            except Exception:  # noqa: BLE001
+                return
+            self._stop.wait(0.005)
+
+    def start(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': [],
+                    'note': getattr(self, 'error', 'no samples')}
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2], 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(s)}
+
+
+# ---------------------------------------------------------------------------
+# CPU baseline: the reference's grid_sample path, restated in oracle/
+# ---------------------------------------------------------------------------
+def cpu_reference_step(prob_cpu):
+    """One fwd+bwd of the reference CPU algorithm on CPU tensors; returns seconds."""
+    from oracle import msda_oracle as O
+    v = prob_cpu['value'].float().requires_grad_()
+    loc = prob_cpu['loc'].clone().requires_grad_()
+    aw = prob_cpu['aw'].clone().requires_grad_()
+    t0 = time.perf_counter()
+    out = O.grid_sample_port(v, prob_cpu['shapes'], loc, aw)
+    out.backward(prob_cpu['grad_out'])
+    return time.perf_counter() - t0
+
+
+def cpu_sample_problem(wl, frames=1, queries=None):
+    """A bounded sample of the workload for the CPU legs: `frames` batch
+    entries and (optionally) the first `queries` queries of each."""
+    prob = make_problem(wl, seed=1234, device='cpu', frames=frames)
+    if queries is not None and queries < prob['dims']['Q']:
+        for k in ('loc', 'aw', 'grad_out'):
+            prob[k] = prob[k][:, :queries].contiguous()
+        prob['dims']['Q'] = queries
+    return prob
+
+
+def measure_cpu_baseline(wl, budget_s=20.0):
+    cfg = WORKLOADS[wl]
+    full_q = sum(h * w for h, w in cfg['levels']) if cfg['kind'] == 'encoder' else cfg['Q']
+    prob = cpu_sample_problem(wl, frames=1, queries=min(full_q, 4096))
+    t = cpu_reference_step(prob)                       # warm-up + calibration
+    per_query = t / prob['dims']['Q']
+    q = int(max(64, min(full_q, budget_s / 4 / max(per_query, 1e-9))))
+    prob = cpu_sample_problem(wl, frames=1, queries=q)
+    cpu_reference_step(prob)
+    best = min(cpu_reference_step(prob) for _ in range(3))
+    return {'value': prob['dims']['Q'] / best, 'unit': 'queries/s',
+            'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '1 batch entry x %d of %d queries of %s, fwd+bwd, fp32, best of 3 after '
+                      '1 warm-up (oracle.grid_sample_port + autograd)' % (q, full_q, wl),
+            'ms_per_sample': best * 1e3}
+
+
+# ---------------------------------------------------------------------------
+def dist_setup(gpus):
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    return world, rank, local
+
+
+def run_reference_arm(args, world, rank):
+    """--impl reference: the reference's CPU implementation of the path (the
+    oracle port; the Python reference itself cannot travel to the GPU box),
+    all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    wl = args.workload
+    cfg = WORKLOADS[wl]
+    full_q = sum(h * w for h, w in cfg['levels']) if cfg['kind'] == 'encoder' else cfg['Q']
+    # size the per-step sample so the whole run stays within ~2 minutes
+    probe = cpu_sample_problem(wl, frames=1, queries=min(full_q, 2048))
+    t = cpu_reference_step(probe)
+    per_query = t / probe['dims']['Q']
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    q = int(max(32, min(full_q, budget / max(per_query, 1e-9))))
+    prob = cpu_sample_problem(wl, frames=1, queries=q)
+    for _ in range(args.warmup):
+        cpu_reference_step(prob)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(prob)
+    dt = time.perf_counter() - t0
+    qps = q * args.steps / dt
+    sample = '1 batch entry x %d of %d queries per step' % (q, full_q)
+    line = {
+        'impl': 'reference', 'metric': 'deform-attn fwd+bwd queries/s', 'value': qps,
+        'unit': 'queries/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': wl, 'description': cfg['desc'], 'sample': sample},
+        'cpu_baseline': {'value': qps, 'unit': 'queries/s', 'cores': torch.get_num_threads(),
+                         'kind': 'port', 'sample': sample},
+        'e2e': {'value': qps, 'unit': 'queries/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def load_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:  # noqa: BLE001
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def load_traffic(kernel_key):
+    """dram bytes per launch from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    try:
+        with open(path) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='encoder_cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--value-dtype', default='f32', choices=['f32', 'bf16'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--sets', type=int, default=4, help='distinct input sets rotated per step')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    world, rank, local = dist_setup(args.gpus)
+    if args.impl == 'reference':
+        run_reference_arm(args, world, rank)
+        return
+
+    import torch.distributed as dist
+    import pavenet_b200
+    from pavenet_b200 import _capi, clip_sharding
+    from pavenet_b200.functional import (MultiScaleDeformableAttnFunction, ms_deform_attn_backward,
+                                         ms_deform_attn_forward)
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (there is no CPU path to time); '
+                         'use --impl reference for the CPU baseline')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    _capi.load()
+
+    wl = args.workload
+    cfg = WORKLOADS[wl]
+    vdt = torch.float32 if args.value_dtype == 'f32' else torch.bfloat16
+    # every rank owns its own clips: weak scaling, `sets` distinct clips per rank
+    probs = [make_problem(wl, seed=1000 * rank + i, device=device, value_dtype=vdt)
+             for i in range(args.sets)]
+    dims = probs[0]['dims']
+    q_per_step = dims['B'] * dims['Q']
+    gv_dtype = torch.float32
+    bufs = [dict(grad_value=torch.empty(p['value'].shape, dtype=gv_dtype, device=device),
+                 grad_loc=torch.empty_like(p['loc']), grad_aw=torch.empty_like(p['aw']))
+            for p in probs]
+    footprint = sum(t.numel() * t.element_size() for p in probs for t in p.values()
+                    if isinstance(t, torch.Tensor))
+    footprint += sum(t.numel() * t.element_size() for b in bufs for t in b.values())
+
+    def step(i, ev=None):
+        p, b = probs[i % args.sets], bufs[i % args.sets]
+        if ev:
+            ev[0].record()
+        out = ms_deform_attn_forward(p['value'], p['shapes'], p['lsi'], p['loc'], p['aw'], 64)
+        if ev:
+            ev[1].record()
+        b['grad_value'].zero_()
+        if ev:
+            ev[2].record()
+        ms_deform_attn_backward(p['value'], p['shapes'], p['lsi'], p['loc'], p['aw'],
+                                p['grad_out'], b['grad_value'], b['grad_loc'], b['grad_aw'], 64)
+        if ev:
+            ev[3].record()
+        return out
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    launches0 = _capi.launch_count()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        step(i, evs[i])
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clock_info = clocks.stop()
+    launches = _capi.launch_count() - launches0
+
+    elapsed_ms = t_start.elapsed_time(t_end)
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    zero_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    bwd_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
+    elapsed_max = clip_sharding.max_over_ranks(elapsed_ms, device)
+    total_q = clip_sharding.sum_over_ranks(q_per_step * args.steps, device)
+    value = total_q / (elapsed_max * 1e-3)
+
+    # ---- end to end through the public op with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        p = probs[0]
+        host = {k: torch.empty(p[k].shape, dtype=p[k].dtype).pin_memory()
+                for k in ('value', 'loc', 'aw', 'grad_out')}
+        for k in host:
+            host[k].copy_(p[k])
+        out_h = torch.empty((dims['B'], dims['Q'], dims['M'] * dims['D'])).pin_memory()
+        gv_h = torch.empty(p['value'].shape, dtype=p['value'].dtype).pin_memory()
+        gl_h = torch.empty(p['loc'].shape).pin_memory()
+        ga_h = torch.empty(p['aw'].shape).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in host.values())
+        d2h = sum(t.numel() * t.element_size() for t in (out_h, gv_h, gl_h, ga_h))
+
+        def e2e_step():
+            v = host['value'].to(device, non_blocking=True).requires_grad_()
+            loc = host['loc'].to(device, non_blocking=True).requires_grad_()
+            aw = host['aw'].to(device, non_blocking=True).requires_grad_()
+            go = host['grad_out'].to(device, non_blocking=True)
+            out = MultiScaleDeformableAttnFunction.apply(v, p['shapes'], p['lsi'], loc, aw, 64)
+            out.backward(go)
+            out_h.copy_(out.detach(), non_blocking=True)
+            gv_h.copy_(v.grad, non_blocking=True)
+            gl_h.copy_(loc.grad, non_blocking=True)
+            ga_h.copy_(aw.grad, non_blocking=True)
+
+        n_e2e = max(5, min(args.steps, 30))
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = clip_sharding.max_over_ranks(e0.elapsed_time(e1), device)
+        tq = clip_sharding.sum_over_ranks(q_per_step * n_e2e, device)
+        e2e = {'value': tq / (ms * 1e-3), 'unit': 'queries/s', 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': d2h, 'ms_per_step': ms / n_e2e, 'steps': n_e2e,
+               'api': 'MultiScaleDeformableAttnFunction.apply + backward, pinned host tensors'}
+
+    if rank == 0:
+        peak, peak_src = load_peak()
+        vb = 4 if vdt == torch.float32 else 2
+        ab = algorithmic_bytes(dims, value_bytes=vb, grad_value_bytes=4)
+
+        def roof(nbytes, ms, key):
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            return {'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s',
+                    'frac': gbs / peak, 'traffic': load_traffic(key), 'kernel': key,
+                    'algorithmic_bytes': nbytes, 'kernel_ms': ms, 'peak_source': peak_src,
+                    'frac_of_8TBs_nominal': gbs / 8000.0}
+
+        kname = _capi.kernel_name(dims['D'], 0, 0 if vdt == torch.float32 else 2)
+        line = {
+            'metric': 'deform-attn fwd+bwd queries/s', 'value': value, 'unit': 'queries/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': elapsed_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32' if vdt == torch.float32 else 'f32 (bf16 value storage)',
+            'data': 'synthetic',
+            'config': {'workload': wl, 'description': cfg['desc'], 'dims': dims,
+                       'queries_per_step': q_per_step, 'kernel': kname,
+                       'l2_policy': 'inputs larger than L2: %d distinct clips rotated per step, '
+                                    '%.2f GB footprint per GPU' % (args.sets, footprint / 1e9),
+                       'parallelism': 'clip-sharded x%d, no data-path collective' % world},
+            'roofline': roof(ab['bwd'], bwd_ms, 'msda_bwd_rows_kernel'),
+            'roofline_fwd': roof(ab['fwd'], fwd_ms, 'msda_fwd_rows_kernel'),
+            'roofline_step': roof(ab['fwd'] + ab['bwd'], fwd_ms + zero_ms + bwd_ms, 'step'),
+            'kernel_ms': {'fwd': fwd_ms, 'grad_value_zero_fill': zero_ms, 'bwd': bwd_ms},
+            'clocks': clock_info, 'gpu_launches': int(launches), 'e2e': e2e,
+        }
+        if not args.no_cpu_baseline:
+            line['cpu_baseline'] = measure_cpu_baseline(wl)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,21 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, smoke, micro-benchmark, bench, ncu launch list.
+# Usage (under gpurun): bash tools/gpu_check.sh [tag]
+TAG=${1:-r01}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.csv 2>&1
+lscpu | head -20 > $OUT/cpu.txt 2>&1
+echo "== pytest gpu" ; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee $OUT/pytest_gpu.log
+echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee $OUT/smoke.log
+echo "== microbench" ; timeout 120 ./tools/microbench_red 2>&1 | tee $OUT/microbench_red.log
+echo "== bench" ; timeout 600 python bench.py --steps 100 --warmup 10 2>$OUT/bench.err | tee $OUT/bench.json
+tail -5 $OUT/bench.err
+for wl in pose_cfg3 pose_cfg3_t3 petr_cfg1 stress_cfg5; do
+  timeout 300 python bench.py --steps 100 --warmup 10 --workload $wl --no-cpu-baseline --no-e2e 2>>$OUT/bench.err | tee $OUT/bench_$wl.json
+done
+timeout 300 python bench.py --steps 100 --warmup 10 --value-dtype bf16 --no-cpu-baseline --no-e2e 2>>$OUT/bench.err | tee $OUT/bench_bf16.json
+echo "== ncu launches"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_bench.log 2>&1
+tail -3 $OUT/ncu_bench.log
+echo done
