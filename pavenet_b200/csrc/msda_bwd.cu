@@ -93,15 +93,23 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   const int warp = threadIdx.x >> 5;
   const int gl = lane & (G - 1);
   const int grp = lane / G;
-  const int64_t n_units = static_cast<int64_t>(d.B) * d.Q * d.M;
-  const int64_t gid = (static_cast<int64_t>(blockIdx.x) * kRowsThreads + threadIdx.x) / G;
-  int64_t unit = gid / nsplit;
-  const int split = static_cast<int>(gid % nsplit);
-  const bool live = unit < n_units;
-  if (!live) unit = n_units - 1;
 
-  const int m = static_cast<int>(unit % d.M);
-  const int64_t b = unit / d.M / d.Q;
+  // same block -> (batch entry, query chunk, head) mapping as the forward
+  constexpr int GPB = kRowsThreads / G;   // row groups per block
+  const int qpb = GPB / nsplit;           // queries per block (nsplit divides GPB)
+  const int n_chunks = (d.Q + qpb - 1) / qpb;
+  int blk = blockIdx.x;
+  const int m = blk % d.M;
+  blk /= d.M;
+  const int chunk = blk % n_chunks;
+  const int64_t b = blk / n_chunks;
+  const int gib = threadIdx.x / G;
+  const int split = gib % nsplit;
+  int q_idx = chunk * qpb + gib / nsplit;
+  const bool live = q_idx < d.Q;
+  if (!live) q_idx = d.Q - 1;
+  const int64_t unit = (b * d.Q + q_idx) * d.M + m;
+
   const int64_t boff = b * d.S * MD + m * D + gl * VEC;
   const VT* vbase = value + boff;
   GT* gvbase = grad_value + boff;
@@ -131,7 +139,7 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     float Wf = 0.f, Hf = 0.f;
     {
       SampleRec r;
-      r.off00 = 0; r.meta = 0; r.lh = 0.f; r.lw = 0.f; r.a = 0.f;
+      r.off00 = 0; r.meta = 0; r.lh = 0.f; r.lw = 0.f; r.a = 0.f; r.rs = 0;
       if (s < s_end) {
         const float2 xy = ld_stream_f2(loc_u + 2 * s);
         r.a = ld_stream_f(aw_u + s);
@@ -139,26 +147,27 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
         const LevelInfo lv = s_lvl[l];
         Wf = static_cast<float>(lv.W);
         Hf = static_cast<float>(lv.H);
+        r.rs = lv.row_stride;
         make_sample(xy.x, xy.y, r.a, lv, l, MD, r.off00, r.meta, r.lh, r.lw);
       }
       *reinterpret_cast<int4*>(&rec[lane]) =
           make_int4(r.off00, r.meta, __float_as_int(r.lh), __float_as_int(r.lw));
-      rec[lane].a = r.a;
+      *reinterpret_cast<int2*>(&rec[lane].a) = make_int2(__float_as_int(r.a), r.rs);
     }
     __syncwarp();
 
     float pw[G], px[G], py[G];
 #pragma unroll
     for (int j = 0; j < G; ++j) {
-      pw[j] = 0.f; px[j] = 0.f; py[j] = 0.f;
       const SampleRec* rj = &rec[grp * G + j];
       const int4 q = *reinterpret_cast<const int4*>(rj);
       const int meta = q.y;
-      if (meta & 15) {
-        const float a = rj->a;
+      {
+        const int2 ar = *reinterpret_cast<const int2*>(&rj->a);
+      const float a = __int_as_float(ar.x);  // 0 for samples outside the map
         const float lh = __int_as_float(q.z), lw = __int_as_float(q.w);
         const float hh = 1.f - lh, hw = 1.f - lw;
-        const int rs = s_lvl[meta >> 4].row_stride;
+        const int rs = ar.y;
         const VT* p = vbase + q.x;
         GT* gp = gvbase + q.x;
         float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
@@ -322,8 +331,11 @@ static cudaError_t launch_bwd_rows(const void* value, const int64_t* shapes, con
                                    float* gloc, float* gaw, const Dims& d, int nsplit,
                                    cudaStream_t st) {
   constexpr int G = D / Vec16<VT>::VEC;
-  const int64_t threads = static_cast<int64_t>(d.B) * d.Q * d.M * nsplit * G;
-  const int64_t blocks = (threads + kRowsThreads - 1) / kRowsThreads;
+  constexpr int GPB = kRowsThreads / G;
+  if (nsplit > GPB) nsplit = GPB;   // (a power of two, so it divides GPB)
+  const int qpb = GPB / nsplit;
+  const int64_t blocks = static_cast<int64_t>(d.B) * ((d.Q + qpb - 1) / qpb) * d.M;
+  if (blocks >= (int64_t(1) << 31)) return cudaErrorInvalidConfiguration;
   msda_bwd_rows_kernel<D, VT, GT><<<static_cast<unsigned>(blocks), kRowsThreads, 0, st>>>(
       static_cast<const VT*>(value), shapes, lsi, loc, aw, go, static_cast<GT*>(gv), gloc, gaw, d,
       nsplit);
@@ -332,12 +344,16 @@ static cudaError_t launch_bwd_rows(const void* value, const int64_t* shapes, con
 }
 
 static int choose_bwd_split(const Dims& d, int G, int sm_count) {
-  if (tuning().bwd_split > 0) return tuning().bwd_split;
+  if (tuning().bwd_split > 0) {
+    int s = 1;
+    while (s * 2 <= tuning().bwd_split && s < 8) s *= 2;  // power of two
+    return s;
+  }
   const int64_t units = static_cast<int64_t>(d.B) * d.Q * d.M;
   const int64_t want_groups = static_cast<int64_t>(sm_count) * 64 * (32 / G);
   const int LP = d.L * d.P;
   int split = 1;
-  while (split < 64 && units * split < want_groups && LP / (split * 2) >= G) split *= 2;
+  while (split < 8 && units * split < want_groups && LP / (split * 2) >= G) split *= 2;
   return split;
 }
 

@@ -89,12 +89,13 @@ struct __align__(16) SampleRec {
   int meta;    // bits 0..3 corner validity (v1,v2,v3,v4), bits 4.. level index
   float lh;    // h - h0
   float lw;    // w - w0
-  float a;     // attention weight
-  int pad0, pad1, pad2;
+  float a;     // attention weight (0 when the sample is outside the map)
+  int rs;      // row stride of the sample's level, W*M*D elements
+  int pad0, pad1;
 };
 
 // Corner order matches the reference: v1=(h0,w0) v2=(h0,w1) v3=(h1,w0) v4=(h1,w1).
-__device__ __forceinline__ void make_sample(float x, float y, float a, const LevelInfo& lv,
+__device__ __forceinline__ void make_sample(float x, float y, float& a, const LevelInfo& lv,
                                             int level, int MD, int& off00, int& meta,
                                             float& lh, float& lw) {
   const float h_im = y * static_cast<float>(lv.H) - 0.5f;
@@ -110,8 +111,9 @@ __device__ __forceinline__ void make_sample(float x, float y, float a, const Lev
     const int c0 = w0 >= 0, c1 = w0 + 1 <= lv.W - 1;
     meta = (r0 & c0) | ((r0 & c1) << 1) | ((r1 & c0) << 2) | ((r1 & c1) << 3) | (level << 4);
     off00 = (lv.start + h0 * lv.W + w0) * MD;
+  } else {
+    a = 0.f;  // out-of-range samples contribute nothing, whatever their weight (even NaN)
   }
-  (void)a;
 }
 
 }  // namespace msda

@@ -104,15 +104,25 @@ msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   const int warp = threadIdx.x >> 5;
   const int gl = lane & (G - 1);        // lane within the row group
   const int grp = lane / G;             // group within the warp
-  const int64_t n_units = static_cast<int64_t>(d.B) * d.Q * d.M;
-  const int64_t gid = (static_cast<int64_t>(blockIdx.x) * kRowsThreads + threadIdx.x) / G;
-  int64_t unit = gid / SPLIT;
-  const int split = static_cast<int>(gid % SPLIT);
-  const bool live = unit < n_units;
-  if (!live) unit = n_units - 1;  // keep the warp converged; result discarded
 
-  const int m = static_cast<int>(unit % d.M);
-  const int64_t b = unit / d.M / d.Q;
+  // Block -> (batch entry b, chunk of consecutive queries, head m).  All rows
+  // of a block belong to ONE head and to neighbouring queries, so when
+  // neighbouring queries look at neighbouring pixels (the encoder) their
+  // bilinear corners are the same 128-byte rows and hit in L1.
+  constexpr int QPB = kRowsThreads / G / SPLIT;  // queries per block
+  const int n_chunks = (d.Q + QPB - 1) / QPB;
+  int blk = blockIdx.x;
+  const int m = blk % d.M;
+  blk /= d.M;
+  const int chunk = blk % n_chunks;
+  const int64_t b = blk / n_chunks;
+  const int gib = threadIdx.x / G;      // group within the block
+  const int split = gib % SPLIT;
+  int q_idx = chunk * QPB + gib / SPLIT;
+  const bool live = q_idx < d.Q;
+  if (!live) q_idx = d.Q - 1;           // keep the warp converged; result discarded
+  const int64_t unit = (b * d.Q + q_idx) * d.M + m;
+
   const VT* vbase = value + b * d.S * MD + m * D + gl * VEC;
   const int LP = d.L * d.P;
   const float* loc_u = loc + unit * LP * 2;
@@ -133,16 +143,18 @@ msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     {
       const int s = s0 + gl;
       SampleRec r;
-      r.off00 = 0; r.meta = 0; r.lh = 0.f; r.lw = 0.f; r.a = 0.f;
+      r.off00 = 0; r.meta = 0; r.lh = 0.f; r.lw = 0.f; r.a = 0.f; r.rs = 0;
       if (s < s_end) {
         const float2 xy = ld_stream_f2(loc_u + 2 * s);
         r.a = ld_stream_f(aw_u + s);
         const int l = s / d.P;
-        make_sample(xy.x, xy.y, r.a, s_lvl[l], l, MD, r.off00, r.meta, r.lh, r.lw);
+        const LevelInfo lv = s_lvl[l];
+        r.rs = lv.row_stride;
+        make_sample(xy.x, xy.y, r.a, lv, l, MD, r.off00, r.meta, r.lh, r.lw);
       }
       *reinterpret_cast<int4*>(&rec[lane]) =
           make_int4(r.off00, r.meta, __float_as_int(r.lh), __float_as_int(r.lw));
-      rec[lane].a = r.a;
+      *reinterpret_cast<int2*>(&rec[lane].a) = make_int2(__float_as_int(r.a), r.rs);
     }
     __syncwarp();
     // --- the whole group gathers each sample of the chunk ---
@@ -151,25 +163,25 @@ msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
       const SampleRec* rj = &rec[grp * G + j];
       const int4 q = *reinterpret_cast<const int4*>(rj);
       const int meta = q.y;
-      if (meta & 15) {
-        const float a = rj->a;
-        const float lh = __int_as_float(q.z), lw = __int_as_float(q.w);
-        const float hh = 1.f - lh, hw = 1.f - lw;
-        const int rs = s_lvl[meta >> 4].row_stride;
-        const VT* p = vbase + q.x;
-        float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+      const int2 ar = *reinterpret_cast<const int2*>(&rj->a);
+      const float a = __int_as_float(ar.x);  // 0 for samples outside the map
+      const float lh = __int_as_float(q.z), lw = __int_as_float(q.w);
+      const float hh = 1.f - lh, hw = 1.f - lw;
+      const int rs = ar.y;
+      const VT* p = vbase + q.x;
+      float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
 #pragma unroll
-        for (int c = 0; c < VEC; ++c) v1[c] = v2[c] = v3[c] = v4[c] = 0.f;
-        if (meta & 1) Vec16<VT>::load(p, v1);
-        if (meta & 2) Vec16<VT>::load(p + MD, v2);
-        if (meta & 4) Vec16<VT>::load(p + rs, v3);
-        if (meta & 8) Vec16<VT>::load(p + rs + MD, v4);
-        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+      for (int c = 0; c < VEC; ++c) v1[c] = v2[c] = v3[c] = v4[c] = 0.f;
+      // predicated loads, no branch: the loads of several samples overlap
+      if (meta & 1) Vec16<VT>::load(p, v1);
+      if (meta & 2) Vec16<VT>::load(p + MD, v2);
+      if (meta & 4) Vec16<VT>::load(p + rs, v3);
+      if (meta & 8) Vec16<VT>::load(p + rs + MD, v4);
+      const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
 #pragma unroll
-        for (int c = 0; c < VEC; ++c) {
-          const float val = w1 * v1[c] + w2 * v2[c] + w3 * v3[c] + w4 * v4[c];
-          acc[c] += val * a;
-        }
+      for (int c = 0; c < VEC; ++c) {
+        const float val = w1 * v1[c] + w2 * v2[c] + w3 * v3[c] + w4 * v4[c];
+        acc[c] += val * a;
       }
     }
     __syncwarp();
@@ -197,9 +209,9 @@ static cudaError_t launch_rows_split(const void* value, const int64_t* shapes, c
                                      const float* loc, const float* aw, float* out, const Dims& d,
                                      cudaStream_t st) {
   constexpr int G = D / Vec16<VT>::VEC;
-  const int64_t groups = static_cast<int64_t>(d.B) * d.Q * d.M * SPLIT;
-  const int64_t threads = groups * G;
-  const int64_t blocks = (threads + kRowsThreads - 1) / kRowsThreads;
+  constexpr int QPB = kRowsThreads / G / SPLIT;
+  const int64_t blocks = static_cast<int64_t>(d.B) * ((d.Q + QPB - 1) / QPB) * d.M;
+  if (blocks >= (int64_t(1) << 31)) return cudaErrorInvalidConfiguration;
   msda_fwd_rows_kernel<D, VT, SPLIT><<<static_cast<unsigned>(blocks), kRowsThreads, 0, st>>>(
       static_cast<const VT*>(value), shapes, lsi, loc, aw, out, d);
   note_launches(1);

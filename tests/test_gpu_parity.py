@@ -295,7 +295,7 @@ def test_full_size_encoder_properties(fn):
     assert rel_err(out2, out * 2 + ones) < 1e-5
     assert rel_err(fn(v, s, i, l, a * 0.5, 64), out * 0.5) < 1e-6
     # (2) constant value, all samples inside the map: output = sum of weights = 1
-    centre = (l.clamp(0.02, 0.98))
+    centre = l.clamp(0.04, 0.96)   # every corner inside even the 13-row level
     const = fn(torch.ones_like(v), s, i, centre, a, 64)
     assert (const - 1).abs().max() < 1e-5
     # (3) a slice of queries against the CPU oracle

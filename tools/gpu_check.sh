@@ -16,6 +16,12 @@ for wl in pose_cfg3 pose_cfg3_t3 petr_cfg1 stress_cfg5; do
 done
 timeout 300 python bench.py --steps 100 --warmup 10 --value-dtype bf16 --no-cpu-baseline --no-e2e 2>>$OUT/bench.err | tee $OUT/bench_bf16.json
 echo "== ncu launches"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_bench.log 2>&1
-tail -3 $OUT/ncu_bench.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:msda|FillFunctor<float>' -c 40 --csv --log-file $OUT/launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_bench.log 2>&1
+tail -2 $OUT/ncu_bench.log | cut -c1-300
+if [ -n "$NCU_FULL" ]; then
+  echo "== ncu full"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:msda -s 6 -c 2 -f -o $OUT/prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_full.log 2>&1
+  tail -2 $OUT/ncu_full.log | cut -c1-300
+  ls -la $OUT/*.ncu-rep
+fi
 echo done
