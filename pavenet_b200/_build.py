@@ -15,7 +15,8 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 LIB_DIR = os.path.join(_HERE, 'lib')
-LIB_PATH = os.path.join(LIB_DIR, 'libpavenet_msda.so')
+# PAVENET_MSDA_LIB selects an alternative build of the same ABI (kernel-tuning experiments)
+LIB_PATH = os.environ.get('PAVENET_MSDA_LIB') or os.path.join(LIB_DIR, 'libpavenet_msda.so')
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), 'include')
 
 SOURCES = ['msda_fwd.cu', 'msda_bwd.cu', 'msda_capi.cu']
@@ -52,7 +53,7 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS
+    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get('PAVENET_MSDA_NVCC_EXTRA', '').split()
     if verbose:
         cmd += ['-Xptxas', '-v']
     tmp = LIB_PATH + '.tmp%d' % os.getpid()

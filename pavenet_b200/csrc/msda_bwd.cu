@@ -17,6 +17,8 @@
 // over the G lanes of the group (7 shuffles per 8 samples per quantity)
 // instead of a shared-memory pass with thread 0 summing serially
 // (ms_deform_attn_cuda_kernel.cuh:319-336).
+#include <type_traits>
+
 #include "msda_kernels.h"
 
 namespace msda {
@@ -35,6 +37,23 @@ __device__ __forceinline__ void red_add_row(float* p, const float (&v)[8]) {
                "f"(v[5]), "f"(v[6]), "f"(v[7])
                : "memory");
 }
+// fp32 gradient rows under bf16 value storage: a lane's 8 value channels are 32
+// bytes of fp32 gradient.  Reducing them as [8*gl, 8*gl+8) would touch half of
+// each 32-byte sector twice; instead the G lanes cover the row as two
+// contiguous halves, lane gl taking channels [4*gl, 4*gl+4) and
+// [D/2 + 4*gl, D/2 + 4*gl + 4): every reduction fills whole sectors.
+__device__ __forceinline__ void red_add_halves(float* row, int gl, int half_d, const float (&v)[8]) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + 4 * gl), "f"(v[0]),
+               "f"(v[1]), "f"(v[2]), "f"(v[3])
+               : "memory");
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + half_d + 4 * gl),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void red_add_halves(float*, int, int, const float (&)[4]) {}
+__device__ __forceinline__ void red_add_halves(__nv_bfloat16*, int, int, const float (&)[4]) {}
+__device__ __forceinline__ void red_add_halves(__nv_bfloat16*, int, int, const float (&)[8]) {}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&t);
@@ -83,7 +102,7 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   static_assert(D % VEC == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0, "bad D");
 
   __shared__ LevelInfo s_lvl[kMaxSmemLevels];
-  __shared__ SampleRec s_rec[kRowsWarps][32];
+  __shared__ int4 s_board[kRowsWarps][G * (2 * (32 / G) + 1)];
 
   const int MD = d.M * D;
   for (int l = threadIdx.x; l < d.L; l += blockDim.x) s_lvl[l] = load_level(shapes, lsi, l, MD);
@@ -110,9 +129,10 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   if (!live) q_idx = d.Q - 1;
   const int64_t unit = (b * d.Q + q_idx) * d.M + m;
 
+  constexpr bool kHalves = std::is_same<GT, float>::value && VEC == 8;
   const int64_t boff = b * d.S * MD + m * D + gl * VEC;
   const VT* vbase = value + boff;
-  GT* gvbase = grad_value + boff;
+  GT* gvbase = grad_value + boff - (kHalves ? gl * VEC : 0);  // kHalves: row start, lanes add their own slots
   const int LP = d.L * d.P;
   const float* loc_u = loc + unit * LP * 2;
   const float* aw_u = aw + unit * LP;
@@ -129,11 +149,37 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     }
   }
 
+  // grad_out channels this lane scatters (== g unless the row is covered in halves)
+  float gs[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) gs[c] = g[c];
+  if (kHalves) {
+    const float* gp = grad_out + unit * D;
+    const float4 lo = __ldcs(reinterpret_cast<const float4*>(gp + 4 * gl));
+    const float4 hi = __ldcs(reinterpret_cast<const float4*>(gp + D / 2 + 4 * gl));
+    gs[0] = lo.x; gs[1] = lo.y; gs[2] = lo.z; gs[3] = lo.w;
+    gs[VEC - 4] = hi.x; gs[VEC - 3] = hi.y; gs[VEC - 2] = hi.z; gs[VEC - 1] = hi.w;
+  }
+
   const int per = ((LP + nsplit - 1) / nsplit + G - 1) / G * G;
   const int s_begin = split * per;
   const int s_end = live ? min(LP, s_begin + per) : 0;  // dead groups touch nothing
 
-  SampleRec* rec = s_rec[warp];
+  // per-warp record board, same conflict-free layout as the forward kernel
+  constexpr int NG = 32 / G;
+  int4* board = s_board[warp];
+  auto unit_of = [](int j, int grp_, int half) { return j * (2 * NG + 1) + 2 * grp_ + half; };
+  const FastDivP level_of(d.P);
+
+  float2 nxt_xy = make_float2(0.f, 0.f);
+  float nxt_a = 0.f;
+  {
+    const int s = s_begin + gl;
+    if (s < s_end) {
+      nxt_xy = ld_stream_f2(loc_u + 2 * s);
+      nxt_a = ld_stream_f(aw_u + s);
+    }
+  }
   for (int s0 = s_begin; s0 < s_begin + per; s0 += G) {
     const int s = s0 + gl;
     float Wf = 0.f, Hf = 0.f;
@@ -141,29 +187,32 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
       SampleRec r;
       r.off00 = 0; r.meta = 0; r.lh = 0.f; r.lw = 0.f; r.a = 0.f; r.rs = 0;
       if (s < s_end) {
-        const float2 xy = ld_stream_f2(loc_u + 2 * s);
-        r.a = ld_stream_f(aw_u + s);
-        const int l = s / d.P;
+        r.a = nxt_a;
+        const int l = level_of(s);
         const LevelInfo lv = s_lvl[l];
         Wf = static_cast<float>(lv.W);
         Hf = static_cast<float>(lv.H);
         r.rs = lv.row_stride;
-        make_sample(xy.x, xy.y, r.a, lv, l, MD, r.off00, r.meta, r.lh, r.lw);
+        make_sample(nxt_xy.x, nxt_xy.y, r.a, lv, l, MD, r.off00, r.meta, r.lh, r.lw);
       }
-      *reinterpret_cast<int4*>(&rec[lane]) =
+      board[unit_of(gl, grp, 0)] =
           make_int4(r.off00, r.meta, __float_as_int(r.lh), __float_as_int(r.lw));
-      *reinterpret_cast<int2*>(&rec[lane].a) = make_int2(__float_as_int(r.a), r.rs);
+      *reinterpret_cast<int2*>(&board[unit_of(gl, grp, 1)]) = make_int2(__float_as_int(r.a), r.rs);
+      const int sn = s + G;
+      if (sn < s_end) {
+        nxt_xy = ld_stream_f2(loc_u + 2 * sn);
+        nxt_a = ld_stream_f(aw_u + sn);
+      }
     }
     __syncwarp();
 
     float pw[G], px[G], py[G];
 #pragma unroll
     for (int j = 0; j < G; ++j) {
-      const SampleRec* rj = &rec[grp * G + j];
-      const int4 q = *reinterpret_cast<const int4*>(rj);
+      const int4 q = board[unit_of(j, grp, 0)];
       const int meta = q.y;
       {
-        const int2 ar = *reinterpret_cast<const int2*>(&rj->a);
+        const int2 ar = *reinterpret_cast<const int2*>(&board[unit_of(j, grp, 1)]);
       const float a = __int_as_float(ar.x);  // 0 for samples outside the map
         const float lh = __int_as_float(q.z), lw = __int_as_float(q.w);
         const float hh = 1.f - lh, hw = 1.f - lw;
@@ -192,26 +241,17 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
         }
         pw[j] = sw; px[j] = sx; py[j] = sy;
         float t[VEC];
-        if (meta & 1) {
-#pragma unroll
-          for (int c = 0; c < VEC; ++c) t[c] = w1 * tg[c];
-          red_add_row(gp, t);
-        }
-        if (meta & 2) {
-#pragma unroll
-          for (int c = 0; c < VEC; ++c) t[c] = w2 * tg[c];
-          red_add_row(gp + MD, t);
-        }
-        if (meta & 4) {
-#pragma unroll
-          for (int c = 0; c < VEC; ++c) t[c] = w3 * tg[c];
-          red_add_row(gp + rs, t);
-        }
-        if (meta & 8) {
-#pragma unroll
-          for (int c = 0; c < VEC; ++c) t[c] = w4 * tg[c];
-          red_add_row(gp + rs + MD, t);
-        }
+#define MSDA_SCATTER(BIT, WK, PTR)                                   \
+  if (meta & BIT) {                                                  \
+    _Pragma("unroll") for (int c = 0; c < VEC; ++c) t[c] = (WK) * a * gs[c]; \
+    if (kHalves) red_add_halves(PTR, gl, D / 2, t);                  \
+    else red_add_row(PTR, t);                                        \
+  }
+        MSDA_SCATTER(1, w1, gp)
+        MSDA_SCATTER(2, w2, gp + MD)
+        MSDA_SCATTER(4, w3, gp + rs)
+        MSDA_SCATTER(8, w4, gp + rs + MD)
+#undef MSDA_SCATTER
       }
     }
     // lane gl receives the channel-summed gradients of sample s0 + gl
@@ -346,14 +386,14 @@ static cudaError_t launch_bwd_rows(const void* value, const int64_t* shapes, con
 static int choose_bwd_split(const Dims& d, int G, int sm_count) {
   if (tuning().bwd_split > 0) {
     int s = 1;
-    while (s * 2 <= tuning().bwd_split && s < 8) s *= 2;  // power of two
+    while (s * 2 <= tuning().bwd_split && s < 32) s *= 2;  // power of two
     return s;
   }
   const int64_t units = static_cast<int64_t>(d.B) * d.Q * d.M;
   const int64_t want_groups = static_cast<int64_t>(sm_count) * 64 * (32 / G);
   const int LP = d.L * d.P;
   int split = 1;
-  while (split < 8 && units * split < want_groups && LP / (split * 2) >= G) split *= 2;
+  while (split < 32 && units * split < want_groups && LP / (split * 2) >= G) split *= 2;
   return split;
 }
 

@@ -45,6 +45,17 @@ __device__ __forceinline__ LevelInfo load_level(const int64_t* __restrict__ shap
   return li;
 }
 
+// s / P for 0 <= s < L*P < 2^24 without an integer division per sample:
+// magic = floor(2^32 / P) + 1 is exact for s * P < 2^32.
+struct FastDivP {
+  uint32_t magic;
+  int P;
+  __device__ __forceinline__ explicit FastDivP(int p) : magic(0xFFFFFFFFu / p + 1u), P(p) {}
+  __device__ __forceinline__ int operator()(int s) const {
+    return P == 1 ? s : static_cast<int>(__umulhi(static_cast<uint32_t>(s), magic));
+  }
+};
+
 // ---- 16-byte row-segment loads -------------------------------------------
 // A "row" is the D channels of one head at one pixel.  Each lane owns VEC
 // consecutive channels = one 16-byte load.
@@ -73,6 +84,32 @@ struct Vec16<__nv_bfloat16> {
     v[6] = __uint_as_float(t.w << 16); v[7] = __uint_as_float(t.w & 0xffff0000u);
   }
 };
+
+// Predicated 16-byte row-segment load from (uniform base + 32-bit byte offset).
+// When `pred` is false nothing is loaded and v keeps its previous contents.
+__device__ __forceinline__ void ldg16_pred(const char* base, uint32_t byte_off, int pred,
+                                           float (&v)[4]) {
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+      "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3])
+      : "l"(base + byte_off), "r"(0), "r"(pred));
+}
+__device__ __forceinline__ void ldg16_pred(const char* base, uint32_t byte_off, int pred,
+                                           float (&v)[8]) {
+  // 8 bf16 -> 8 floats; the packed words persist in v's bit patterns only after
+  // conversion, so a skipped load must leave v untouched: convert under the predicate
+  uint32_t x = 0, y = 0, z = 0, w = 0;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "+r"(x), "+r"(y), "+r"(z), "+r"(w)
+      : "l"(base + byte_off), "r"(pred));
+  if (pred) {
+    v[0] = __uint_as_float(x << 16); v[1] = __uint_as_float(x & 0xffff0000u);
+    v[2] = __uint_as_float(y << 16); v[3] = __uint_as_float(y & 0xffff0000u);
+    v[4] = __uint_as_float(z << 16); v[5] = __uint_as_float(z & 0xffff0000u);
+    v[6] = __uint_as_float(w << 16); v[7] = __uint_as_float(w & 0xffff0000u);
+  }
+}
 
 // Streaming (read-once) loads for locations / weights / grad_output: keep them
 // from displacing value rows in L1.
@@ -114,6 +151,52 @@ __device__ __forceinline__ void make_sample(float x, float y, float& a, const Le
   } else {
     a = 0.f;  // out-of-range samples contribute nothing, whatever their weight (even NaN)
   }
+}
+
+// ---- forward record: weights and strides resolved by the owning lane ------
+// The cell is re-anchored so that all four loads are in bounds: a corner that
+// falls outside the map is replaced by a duplicate of a valid one (stride 0)
+// carrying weight 0, and the attention weight is folded into the four corner
+// weights.  The G lanes then run 4 unconditional 16-byte loads and 4 FMAs per
+// channel - no validity tests, no zero fills, no weight arithmetic per lane.
+struct __align__(16) FwdRec {
+  int off;    // BYTE offset of the anchor corner (head 0, channel 0) inside the batch entry
+  int rsx;    // bits 0..30 row stride in BYTES (0 if the second row is a duplicate);
+              // bit 31 set if the second column is one pixel to the right (else duplicate).
+              // kDeadRec: the sample is outside the map, skip its loads.
+  float w1, w2;  // anchor row:   (col a, col b)
+  float w3, w4;  // second row:   (col a, col b)
+  int pad0, pad1;  // 32-byte records: 16-byte aligned vector access, conflict-free when adjacent
+};
+constexpr int kDeadRec = 0x7fffffff;
+
+template <int ELT_BYTES>
+__device__ __forceinline__ FwdRec make_fwd_rec(float x, float y, float a, const LevelInfo& lv,
+                                               int MD) {
+  FwdRec r;
+  r.off = 0; r.rsx = kDeadRec; r.w1 = r.w2 = r.w3 = r.w4 = 0.f;
+  const float h_im = y * static_cast<float>(lv.H) - 0.5f;
+  const float w_im = x * static_cast<float>(lv.W) - 0.5f;
+  if (h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(lv.H) &&
+      w_im < static_cast<float>(lv.W)) {
+    const float hf = floorf(h_im), wf = floorf(w_im);
+    int h0 = static_cast<int>(hf), w0 = static_cast<int>(wf);
+    const float lh = h_im - hf, lw = w_im - wf;
+    // rows: (ra, rb) are the weights of the anchor row and of the row below it
+    float ra = 1.f - lh, rb = lh;
+    int rs = lv.row_stride;
+    if (h0 < 0) { h0 = 0; ra = lh; rb = 0.f; rs = 0; }            // only row 0 (the lower corner) exists
+    else if (h0 + 1 > lv.H - 1) { rb = 0.f; rs = 0; }             // only row h0 exists
+    float ca = 1.f - lw, cb = lw;
+    int right = 1;
+    if (w0 < 0) { w0 = 0; ca = lw; cb = 0.f; right = 0; }
+    else if (w0 + 1 > lv.W - 1) { cb = 0.f; right = 0; }
+    r.off = (lv.start + h0 * lv.W + w0) * MD * ELT_BYTES;
+    r.rsx = (rs * ELT_BYTES) | (right ? static_cast<int>(0x80000000u) : 0);
+    ra *= a; rb *= a;
+    r.w1 = ra * ca; r.w2 = ra * cb; r.w3 = rb * ca; r.w4 = rb * cb;
+  }
+  return r;
 }
 
 }  // namespace msda
