@@ -53,6 +53,7 @@
 #ifndef PAVENET_MSDA_H_
 #define PAVENET_MSDA_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -126,6 +127,15 @@ typedef struct msda_workspace msda_workspace;
 
 int msda_workspace_create(msda_workspace **out_ws);
 void msda_workspace_destroy(msda_workspace *ws);
+/* Upload bytes per pipeline piece of the staged calls (default 12 MiB). */
+int msda_workspace_set_piece_bytes(msda_workspace *ws, size_t bytes);
+
+/* Page-locked host memory for callers without their own CUDA binding.  With
+ * pinned buffers the staged calls below overlap the upload of the next piece,
+ * the kernels of the current one and the download of the previous one (the
+ * link is full duplex); with pageable memory they still work, serialised. */
+void *msda_host_alloc(size_t bytes);
+void msda_host_free(void *ptr);
 
 int msda_forward_host(msda_workspace *ws, const void *h_value,
                       const int64_t *h_spatial_shapes,
@@ -135,8 +145,10 @@ int msda_forward_host(msda_workspace *ws, const void *h_value,
                       int num_heads, int channels, int num_levels,
                       int num_query, int num_point, int dtype, int value_dtype);
 
-/* Forward + backward in one staged call: inputs and grad_output go up once,
- * output and the three gradients come back.  `h_output` may be NULL. */
+/* Forward + backward in one staged, pipelined call: inputs and grad_output go
+ * up once, output and the three gradients come back; work is cut into
+ * (batch entry, query chunk) pieces that flow through three streams.
+ * `h_output` may be NULL (backward only).  grad_value is returned in `dtype`. */
 int msda_forward_backward_host(
     msda_workspace *ws, const void *h_value, const int64_t *h_spatial_shapes,
     const int64_t *h_level_start_index, const void *h_sampling_loc,

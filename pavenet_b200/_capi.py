@@ -16,7 +16,9 @@ MSDA_OK = 0
 EXPORTED_SYMBOLS = (
     'msda_abi_version', 'msda_last_error', 'msda_launch_count',
     'msda_kernel_name', 'msda_forward', 'msda_backward',
-    'msda_workspace_create', 'msda_workspace_destroy', 'msda_forward_host',
+    'msda_workspace_create', 'msda_workspace_destroy', 'msda_workspace_set_piece_bytes',
+    'msda_host_alloc',
+    'msda_host_free', 'msda_forward_host',
     'msda_forward_backward_host',
 )
 
@@ -49,6 +51,12 @@ def _declare(lib):
     lib.msda_workspace_create.argtypes = [ctypes.POINTER(c_void_p)]
     lib.msda_workspace_destroy.restype = None
     lib.msda_workspace_destroy.argtypes = [c_void_p]
+    lib.msda_workspace_set_piece_bytes.restype = c_int
+    lib.msda_workspace_set_piece_bytes.argtypes = [c_void_p, ctypes.c_size_t]
+    lib.msda_host_alloc.restype = c_void_p
+    lib.msda_host_alloc.argtypes = [ctypes.c_size_t]
+    lib.msda_host_free.restype = None
+    lib.msda_host_free.argtypes = [c_void_p]
     lib.msda_forward_host.restype = c_int
     lib.msda_forward_host.argtypes = (
         [c_void_p] + [c_void_p] * 6 + [c_int] * 7 + [c_int, c_int])

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "msda_kernels.h"
 
@@ -193,20 +194,33 @@ int msda_backward(const void* d_value, const int64_t* d_spatial_shapes,
 
 // ---------------------------------------------------------------------------
 // host-buffer entry points
+//
+// The staged call is pipelined: work is cut into (batch entry, query chunk)
+// pieces; piece k+1 is copied host->device on one stream while piece k runs
+// forward + backward on a second and piece k-1's results return on a third.
+// PCIe is full duplex, so with pinned host memory the call costs about
+// max(bytes up, bytes down) / link bandwidth instead of their sum plus the
+// kernels.
 // ---------------------------------------------------------------------------
 struct msda_workspace {
-  cudaStream_t stream = nullptr;
+  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
   void* buf = nullptr;   // one grow-only device arena
   size_t cap = 0;
+  std::vector<cudaEvent_t> events;  // grow-only pool, reused across calls
+  size_t next_event = 0;
+  size_t piece_bytes = size_t(12) << 20;  // upload bytes per pipeline piece
 };
 
 int msda_workspace_create(msda_workspace** out_ws) {
   if (!out_ws) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_workspace_create: NULL out pointer");
   msda_workspace* ws = new msda_workspace();
-  const cudaError_t e = cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking);
-  if (e != cudaSuccess) {
-    delete ws;
-    return fail(MSDA_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  cudaStream_t* st[3] = {&ws->s_in, &ws->s_cmp, &ws->s_out};
+  for (auto* p : st) {
+    const cudaError_t e = cudaStreamCreateWithFlags(p, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      msda_workspace_destroy(ws);
+      return fail(MSDA_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
   }
   *out_ws = ws;
   return MSDA_OK;
@@ -214,9 +228,32 @@ int msda_workspace_create(msda_workspace** out_ws) {
 
 void msda_workspace_destroy(msda_workspace* ws) {
   if (!ws) return;
+  for (cudaEvent_t e : ws->events) cudaEventDestroy(e);
   if (ws->buf) cudaFree(ws->buf);
-  if (ws->stream) cudaStreamDestroy(ws->stream);
+  if (ws->s_in) cudaStreamDestroy(ws->s_in);
+  if (ws->s_cmp) cudaStreamDestroy(ws->s_cmp);
+  if (ws->s_out) cudaStreamDestroy(ws->s_out);
   delete ws;
+}
+
+int msda_workspace_set_piece_bytes(msda_workspace* ws, size_t bytes) {
+  if (!ws || bytes == 0)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_workspace_set_piece_bytes: NULL workspace or 0 bytes");
+  ws->piece_bytes = bytes;
+  return MSDA_OK;
+}
+
+void* msda_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    fail(MSDA_ERR_CUDA, "cudaHostAlloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+
+void msda_host_free(void* p) {
+  if (p) cudaFreeHost(p);
 }
 
 namespace {
@@ -242,11 +279,36 @@ int ws_reserve(msda_workspace* ws, size_t bytes) {
   return MSDA_OK;
 }
 
+int ws_event(msda_workspace* ws, cudaEvent_t* out) {
+  if (ws->next_event == ws->events.size()) {
+    cudaEvent_t e;
+    const cudaError_t rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (rc != cudaSuccess) return fail(MSDA_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(rc));
+    ws->events.push_back(e);
+  }
+  *out = ws->events[ws->next_event++];
+  return MSDA_OK;
+}
+
 #define MSDA_CU(expr)                                                                     \
   do {                                                                                    \
     const cudaError_t e_ = (expr);                                                        \
     if (e_ != cudaSuccess) return fail(MSDA_ERR_CUDA, #expr ": %s", cudaGetErrorString(e_)); \
   } while (0)
+#define MSDA_RC(expr)          \
+  do {                         \
+    const int rc_ = (expr);    \
+    if (rc_) return rc_;       \
+  } while (0)
+
+// queries per pipeline piece: pieces of >= ~8 MiB keep the link efficient
+int pick_chunk(int num_query, size_t bytes_per_query, size_t target) {
+  int64_t q = static_cast<int64_t>(target / (bytes_per_query ? bytes_per_query : 1));
+  if (q < 1) q = 1;
+  if (q > num_query) q = num_query;
+  const int pieces = static_cast<int>((num_query + q - 1) / q);
+  return (num_query + pieces - 1) / pieces;  // even pieces
+}
 }  // namespace
 
 int msda_forward_backward_host(msda_workspace* ws, const void* h_value,
@@ -262,57 +324,91 @@ int msda_forward_backward_host(msda_workspace* ws, const void* h_value,
       (do_bwd && (!h_grad_value || !h_grad_sampling_loc || !h_grad_attn_weight)))
     return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_*_host: NULL pointer argument");
   Dims d;
-  int rc = check_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, &d);
-  if (rc) return rc;
-  rc = check_dtypes(dtype, value_dtype, do_bwd ? dtype : -1);
-  if (rc) return rc;
+  MSDA_RC(check_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, &d));
+  MSDA_RC(check_dtypes(dtype, value_dtype, do_bwd ? dtype : -1));
   const size_t es = dtype_size(dtype), vs = dtype_size(value_dtype);
-  const size_t n_val = static_cast<size_t>(batch) * spatial_size * num_heads * channels;
-  const size_t n_smp = static_cast<size_t>(batch) * num_query * num_heads * num_levels * num_point;
-  const size_t n_out = static_cast<size_t>(batch) * num_query * num_heads * channels;
-  const size_t b_val = n_val * vs, b_loc = n_smp * 2 * es, b_aw = n_smp * es, b_out = n_out * es;
+  // per batch entry
+  const size_t n_val = static_cast<size_t>(spatial_size) * num_heads * channels;
+  const size_t smp_q = static_cast<size_t>(num_heads) * num_levels * num_point;  // samples per query
+  const size_t out_q = static_cast<size_t>(num_heads) * channels;                // outputs per query
+  const size_t b_val = n_val * vs, b_gval = n_val * es;  // grad_value is accumulated and returned in `dtype`
+  const size_t b_loc = smp_q * 2 * es * num_query, b_aw = smp_q * es * num_query;
+  const size_t b_out = out_q * es * num_query;
   const size_t b_shp = static_cast<size_t>(num_levels) * 2 * 8, b_lsi = static_cast<size_t>(num_levels) * 8;
-  // grad_value is accumulated in `dtype` on the device and returned in `dtype`
-  const size_t b_gval = n_val * es;
-  size_t need = pad256(b_val) + pad256(b_loc) + pad256(b_aw) + pad256(b_out) + pad256(b_shp) + pad256(b_lsi);
-  if (do_bwd) need += pad256(b_out) + pad256(b_gval) + pad256(b_loc) + pad256(b_aw);
-  rc = ws_reserve(ws, need);
-  if (rc) return rc;
+  size_t need = pad256(b_shp) + pad256(b_lsi) +
+                batch * (pad256(b_val) + pad256(b_loc) + pad256(b_aw) + pad256(b_out));
+  if (do_bwd) need += batch * (pad256(b_out) + pad256(b_gval) + pad256(b_loc) + pad256(b_aw));
+  MSDA_RC(ws_reserve(ws, need));
+  ws->next_event = 0;
   Arena ar{static_cast<char*>(ws->buf)};
-  void* d_val = ar.take(b_val);
-  void* d_loc = ar.take(b_loc);
-  void* d_aw = ar.take(b_aw);
-  void* d_out = ar.take(b_out);
   int64_t* d_shp = static_cast<int64_t*>(ar.take(b_shp));
   int64_t* d_lsi = static_cast<int64_t*>(ar.take(b_lsi));
-  cudaStream_t st = ws->stream;
-  MSDA_CU(cudaMemcpyAsync(d_shp, h_spatial_shapes, b_shp, cudaMemcpyHostToDevice, st));
-  MSDA_CU(cudaMemcpyAsync(d_lsi, h_level_start_index, b_lsi, cudaMemcpyHostToDevice, st));
-  MSDA_CU(cudaMemcpyAsync(d_val, h_value, b_val, cudaMemcpyHostToDevice, st));
-  MSDA_CU(cudaMemcpyAsync(d_loc, h_sampling_loc, b_loc, cudaMemcpyHostToDevice, st));
-  MSDA_CU(cudaMemcpyAsync(d_aw, h_attn_weight, b_aw, cudaMemcpyHostToDevice, st));
-  if (h_output) {
-    rc = msda_forward(d_val, d_shp, d_lsi, d_loc, d_aw, d_out, batch, spatial_size, num_heads,
-                      channels, num_levels, num_query, num_point, dtype, value_dtype, st);
-    if (rc) return rc;
-    MSDA_CU(cudaMemcpyAsync(h_output, d_out, b_out, cudaMemcpyDeviceToHost, st));
+  MSDA_CU(cudaMemcpyAsync(d_shp, h_spatial_shapes, b_shp, cudaMemcpyHostToDevice, ws->s_in));
+  MSDA_CU(cudaMemcpyAsync(d_lsi, h_level_start_index, b_lsi, cudaMemcpyHostToDevice, ws->s_in));
+
+  const size_t up_q = (smp_q * 3 + (do_bwd ? out_q : 0)) * es;
+  const int chunk = pick_chunk(num_query, up_q, ws->piece_bytes);
+  auto hoff = [](const void* p, size_t bytes) { return static_cast<const char*>(p) + bytes; };
+  auto hoffw = [](void* p, size_t bytes) { return static_cast<char*>(p) + bytes; };
+
+  for (int b = 0; b < batch; ++b) {
+    char* d_val = static_cast<char*>(ar.take(b_val));
+    char* d_loc = static_cast<char*>(ar.take(b_loc));
+    char* d_aw = static_cast<char*>(ar.take(b_aw));
+    char* d_out = static_cast<char*>(ar.take(b_out));
+    char *d_go = nullptr, *d_gval = nullptr, *d_gloc = nullptr, *d_gaw = nullptr;
+    if (do_bwd) {
+      d_go = static_cast<char*>(ar.take(b_out));
+      d_gval = static_cast<char*>(ar.take(b_gval));
+      d_gloc = static_cast<char*>(ar.take(b_loc));
+      d_gaw = static_cast<char*>(ar.take(b_aw));
+      MSDA_CU(cudaMemsetAsync(d_gval, 0, b_gval, ws->s_cmp));
+    }
+    MSDA_CU(cudaMemcpyAsync(d_val, hoff(h_value, b * b_val), b_val, cudaMemcpyHostToDevice, ws->s_in));
+    cudaEvent_t ev_done = nullptr;
+    for (int q0 = 0; q0 < num_query; q0 += chunk) {
+      const int nq = (num_query - q0 < chunk) ? num_query - q0 : chunk;
+      const size_t o_loc = smp_q * 2 * es * q0, o_aw = smp_q * es * q0, o_out = out_q * es * q0;
+      const size_t n_loc = smp_q * 2 * es * nq, n_aw = smp_q * es * nq, n_out = out_q * es * nq;
+      MSDA_CU(cudaMemcpyAsync(d_loc + o_loc, hoff(h_sampling_loc, b * b_loc + o_loc), n_loc,
+                              cudaMemcpyHostToDevice, ws->s_in));
+      MSDA_CU(cudaMemcpyAsync(d_aw + o_aw, hoff(h_attn_weight, b * b_aw + o_aw), n_aw,
+                              cudaMemcpyHostToDevice, ws->s_in));
+      if (do_bwd)
+        MSDA_CU(cudaMemcpyAsync(d_go + o_out, hoff(h_grad_output, b * b_out + o_out), n_out,
+                                cudaMemcpyHostToDevice, ws->s_in));
+      cudaEvent_t ev_in;
+      MSDA_RC(ws_event(ws, &ev_in));
+      MSDA_CU(cudaEventRecord(ev_in, ws->s_in));
+      MSDA_CU(cudaStreamWaitEvent(ws->s_cmp, ev_in, 0));
+      if (h_output)
+        MSDA_RC(msda_forward(d_val, d_shp, d_lsi, d_loc + o_loc, d_aw + o_aw, d_out + o_out, 1,
+                             spatial_size, num_heads, channels, num_levels, nq, num_point, dtype,
+                             value_dtype, ws->s_cmp));
+      if (do_bwd)
+        MSDA_RC(msda_backward(d_val, d_shp, d_lsi, d_loc + o_loc, d_aw + o_aw, d_go + o_out, d_gval,
+                              d_gloc + o_loc, d_gaw + o_aw, 1, spatial_size, num_heads, channels,
+                              num_levels, nq, num_point, dtype, value_dtype, dtype, ws->s_cmp));
+      MSDA_RC(ws_event(ws, &ev_done));
+      MSDA_CU(cudaEventRecord(ev_done, ws->s_cmp));
+      MSDA_CU(cudaStreamWaitEvent(ws->s_out, ev_done, 0));
+      if (h_output)
+        MSDA_CU(cudaMemcpyAsync(hoffw(h_output, b * b_out + o_out), d_out + o_out, n_out,
+                                cudaMemcpyDeviceToHost, ws->s_out));
+      if (do_bwd) {
+        MSDA_CU(cudaMemcpyAsync(hoffw(h_grad_sampling_loc, b * b_loc + o_loc), d_gloc + o_loc, n_loc,
+                                cudaMemcpyDeviceToHost, ws->s_out));
+        MSDA_CU(cudaMemcpyAsync(hoffw(h_grad_attn_weight, b * b_aw + o_aw), d_gaw + o_aw, n_aw,
+                                cudaMemcpyDeviceToHost, ws->s_out));
+      }
+    }
+    if (do_bwd)  // all pieces of this batch entry have been scattered (s_out waited on the last one)
+      MSDA_CU(cudaMemcpyAsync(hoffw(h_grad_value, b * b_gval), d_gval, b_gval, cudaMemcpyDeviceToHost,
+                              ws->s_out));
   }
-  if (do_bwd) {
-    void* d_go = ar.take(b_out);
-    void* d_gval = ar.take(b_gval);
-    void* d_gloc = ar.take(b_loc);
-    void* d_gaw = ar.take(b_aw);
-    MSDA_CU(cudaMemcpyAsync(d_go, h_grad_output, b_out, cudaMemcpyHostToDevice, st));
-    MSDA_CU(cudaMemsetAsync(d_gval, 0, b_gval, st));
-    rc = msda_backward(d_val, d_shp, d_lsi, d_loc, d_aw, d_go, d_gval, d_gloc, d_gaw, batch,
-                       spatial_size, num_heads, channels, num_levels, num_query, num_point, dtype,
-                       value_dtype, dtype, st);
-    if (rc) return rc;
-    MSDA_CU(cudaMemcpyAsync(h_grad_value, d_gval, b_gval, cudaMemcpyDeviceToHost, st));
-    MSDA_CU(cudaMemcpyAsync(h_grad_sampling_loc, d_gloc, b_loc, cudaMemcpyDeviceToHost, st));
-    MSDA_CU(cudaMemcpyAsync(h_grad_attn_weight, d_gaw, b_aw, cudaMemcpyDeviceToHost, st));
-  }
-  MSDA_CU(cudaStreamSynchronize(st));
+  MSDA_CU(cudaStreamSynchronize(ws->s_out));
+  MSDA_CU(cudaStreamSynchronize(ws->s_cmp));
+  MSDA_CU(cudaStreamSynchronize(ws->s_in));
   return MSDA_OK;
 }
 

@@ -18,6 +18,7 @@ from . import _capi
 __all__ = [
     'MultiScaleDeformableAttnFunction', 'ext_module', 'ms_deform_attn_forward',
     'ms_deform_attn_backward', 'fuse_frames_as_levels', 'BF16_GRAD_VALUE_ATOMICS',
+    'HostWorkspace',
 ]
 
 #: When value is stored in bf16, accumulate grad_value in an fp32 scratch
@@ -233,3 +234,96 @@ def fuse_frames_as_levels(spatial_shapes, level_start_index, num_frames, num_key
                               dtype=level_start_index.dtype) * num_keys
     starts = (frame_base[:, None] + level_start_index[None, :]).reshape(-1)
     return shapes.contiguous(), starts.contiguous()
+
+
+class HostWorkspace(object):
+    """Host-buffer front-end of the C ABI (`msda_forward_host`,
+    `msda_forward_backward_host`): CPU tensors in, CPU tensors out.
+
+    The staged call is pipelined inside the library (upload of the next piece,
+    kernels of the current one and download of the previous one overlap on
+    three streams), so pass PINNED tensors (`tensor.pin_memory()`) to get the
+    overlap; pageable tensors work but serialise.  This is the entry point a
+    caller without device-memory management binds (INTEGRATION.md section 4);
+    the autograd `MultiScaleDeformableAttnFunction` is the one PyTorch uses.
+    """
+
+    def __init__(self):
+        import ctypes
+        self._lib = _capi.load()
+        handle = ctypes.c_void_p()
+        _capi.check(self._lib.msda_workspace_create(ctypes.byref(handle)), 'msda_workspace_create')
+        self._ws = handle
+
+    def set_piece_bytes(self, nbytes):
+        """Upload bytes per pipeline piece (default 12 MiB)."""
+        _capi.check(self._lib.msda_workspace_set_piece_bytes(self._ws, int(nbytes)),
+                    'msda_workspace_set_piece_bytes')
+
+    def close(self):
+        if getattr(self, '_ws', None):
+            self._lib.msda_workspace_destroy(self._ws)
+            self._ws = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+    @staticmethod
+    def _check_host(value, shapes, lsi, loc, aw):
+        for name, t in (('value', value), ('spatial_shapes', shapes), ('level_start_index', lsi),
+                        ('sampling_locations', loc), ('attention_weights', aw)):
+            if t.is_cuda:
+                raise RuntimeError('%s must be a CPU tensor for the host-buffer entry points' % name)
+            if not t.is_contiguous():
+                raise RuntimeError('%s tensor has to be contiguous' % name)
+        if shapes.dtype != torch.int64 or lsi.dtype != torch.int64:
+            raise RuntimeError('spatial_shapes and level_start_index must be int64 tensors')
+        B, S, M, D = value.shape
+        _, Q, _, L, P, _ = loc.shape
+        if min(B, S, M, D, L, Q, P) <= 0:
+            raise RuntimeError('host-buffer entry points need non-empty tensors')
+        return B, S, M, D, L, Q, P
+
+    def forward(self, value, spatial_shapes, level_start_index, sampling_locations,
+                attention_weights, out=None):
+        B, S, M, D, L, Q, P = self._check_host(value, spatial_shapes, level_start_index,
+                                               sampling_locations, attention_weights)
+        if out is None:
+            out = torch.empty((B, Q, M * D), dtype=sampling_locations.dtype)
+        status = self._lib.msda_forward_host(
+            self._ws, value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_locations.data_ptr(), attention_weights.data_ptr(), out.data_ptr(),
+            B, S, M, D, L, Q, P, _DTYPE_CODE[sampling_locations.dtype], _DTYPE_CODE[value.dtype])
+        _capi.check(status, 'msda_forward_host')
+        return out
+
+    def forward_backward(self, value, spatial_shapes, level_start_index, sampling_locations,
+                         attention_weights, grad_output, out=None, grad_value=None,
+                         grad_sampling_loc=None, grad_attn_weight=None):
+        """Returns (out, grad_value, grad_sampling_loc, grad_attn_weight); the
+        optional arguments are preallocated (pinned) result buffers."""
+        B, S, M, D, L, Q, P = self._check_host(value, spatial_shapes, level_start_index,
+                                               sampling_locations, attention_weights)
+        dt = sampling_locations.dtype
+        if out is None:
+            out = torch.empty((B, Q, M * D), dtype=dt)
+        if grad_value is None:
+            grad_value = torch.empty(value.shape, dtype=dt)
+        if grad_sampling_loc is None:
+            grad_sampling_loc = torch.empty_like(sampling_locations)
+        if grad_attn_weight is None:
+            grad_attn_weight = torch.empty_like(attention_weights)
+        if grad_value.dtype != dt:
+            raise RuntimeError('grad_value is returned in %s' % dt)
+        grad_output = grad_output.contiguous()
+        status = self._lib.msda_forward_backward_host(
+            self._ws, value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_locations.data_ptr(), attention_weights.data_ptr(), grad_output.data_ptr(),
+            out.data_ptr(), grad_value.data_ptr(), grad_sampling_loc.data_ptr(),
+            grad_attn_weight.data_ptr(), B, S, M, D, L, Q, P, _DTYPE_CODE[dt],
+            _DTYPE_CODE[value.dtype])
+        _capi.check(status, 'msda_forward_backward_host')
+        return out, grad_value, grad_sampling_loc, grad_attn_weight

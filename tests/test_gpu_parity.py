@@ -457,6 +457,29 @@ def test_module_gradients_flow_and_match_composition_oracle(module_golden):
         assert rel_err(params[k].grad, st[k].grad) < BWD_TOL_F32, k
 
 
+@pytest.mark.parametrize('pinned', [True, False])
+def test_host_buffer_entry_points(pinned):
+    """msda_forward_host / msda_forward_backward_host (pipelined over batch
+    entries and query chunks) against the CPU oracle."""
+    import pavenet_b200
+    value, shapes_t, loc, aw, go = _random_problem(21, 3, 4000, 8, 32, 4, MID_LEVELS)
+    lsi = O.level_start_index(shapes_t)
+    if pinned:
+        value, loc, aw, go = (t.pin_memory() for t in (value, loc, aw, go))
+    ws = pavenet_b200.HostWorkspace()
+    ws.set_piece_bytes(1 << 20)          # force several query chunks per batch entry
+    out_f = ws.forward(value, shapes_t, lsi, loc, aw)
+    out, gv, gl, ga = ws.forward_backward(value, shapes_t, lsi, loc, aw, go)
+    ws.close()
+    ref = O.c_forward(value, shapes_t, lsi, loc, aw)
+    rgv, rgl, rga = O.c_backward(value, shapes_t, lsi, loc, aw, go)
+    assert not out.is_cuda
+    assert rel_err(out_f, ref) < FWD_TOL_F32 and rel_err(out, ref) < FWD_TOL_F32
+    assert rel_err(gv, rgv) < BWD_TOL_F32
+    assert rel_err(gl, rgl) < BWD_TOL_F32
+    assert rel_err(ga, rga) < BWD_TOL_F32
+
+
 def test_loaded_library_is_in_tree():
     import pavenet_b200
     lib = pavenet_b200._capi.load()
