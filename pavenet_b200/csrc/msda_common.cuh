@@ -163,18 +163,23 @@ struct __align__(16) FwdRec {
   int off;    // BYTE offset of the anchor corner (head 0, channel 0) inside the batch entry
   int rsx;    // bits 0..30 row stride in BYTES (0 if the second row is a duplicate);
               // bit 31 set if the second column is one pixel to the right (else duplicate).
-              // kDeadRec: the sample is outside the map, skip its loads.
+              // off == kDeadOff: the sample is outside the map (weights 0, loads go to g_zero_row).
   float w1, w2;  // anchor row:   (col a, col b)
   float w3, w4;  // second row:   (col a, col b)
   int pad0, pad1;  // 32-byte records: 16-byte aligned vector access, conflict-free when adjacent
 };
-constexpr int kDeadRec = 0x7fffffff;
+constexpr int kDeadOff = -1;  // FwdRec::off of a sample outside the map (byte offsets are < 2^31)
+
+// 256 bytes of zeros: where the four loads of an out-of-map sample are pointed
+// (all weights are zero too), so the gather needs no predicates and the
+// compiler is free to keep the loads of several samples in flight.
+__device__ __align__(16) const float g_zero_row[64] = {};
 
 template <int ELT_BYTES>
 __device__ __forceinline__ FwdRec make_fwd_rec(float x, float y, float a, const LevelInfo& lv,
                                                int MD) {
   FwdRec r;
-  r.off = 0; r.rsx = kDeadRec; r.w1 = r.w2 = r.w3 = r.w4 = 0.f;
+  r.off = kDeadOff; r.rsx = 0; r.w1 = r.w2 = r.w3 = r.w4 = 0.f;
   const float h_im = y * static_cast<float>(lv.H) - 0.5f;
   const float w_im = x * static_cast<float>(lv.W) - 0.5f;
   if (h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(lv.H) &&

@@ -82,22 +82,28 @@ msda_fwd_generic_kernel(const VT* __restrict__ value, const int64_t* __restrict_
 // --------------------------------------------------------------------------
 constexpr int kRowsThreads = 256;
 constexpr int kRowsWarps = kRowsThreads / 32;
-#ifndef MSDA_FWD_MIN_BLOCKS
-#define MSDA_FWD_MIN_BLOCKS 4
-#endif
+// Resident blocks per SM the compiler must allow: 4 (<= 64 registers) for the
+// large-Q shapes, which are bound by the L1 data pipe and want warps; 3 (<= 80
+// registers, more gathers in flight per lane) for the split small-Q shapes,
+// which are latency bound (measured on B200: pose cfg3 58 -> 48 us).
+constexpr int fwd_min_blocks(int split) { return split > 1 ? 3 : 4; }
 
 template <int D, typename VT, int SPLIT>
-__global__ void __launch_bounds__(kRowsThreads, MSDA_FWD_MIN_BLOCKS)
+__global__ void __launch_bounds__(kRowsThreads, fwd_min_blocks(SPLIT))
 msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                      const float* __restrict__ aw, float* __restrict__ out, Dims d) {
   constexpr int VEC = Vec16<VT>::VEC;
   constexpr int G = D / VEC;  // lanes per row
   static_assert(D % VEC == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0, "bad D");
-  static_assert(G * SPLIT <= 32, "row splits must stay inside one warp");
+  constexpr int NGW = 32 / G;                            // row groups per warp
+  constexpr int WSPLIT = SPLIT < NGW ? SPLIT : NGW;      // splits combined by shuffles inside a warp
+  constexpr int XSPLIT = SPLIT / WSPLIT;                 // ... and across warps through shared memory
+  static_assert(SPLIT * G <= kRowsThreads && (SPLIT & (SPLIT - 1)) == 0, "bad SPLIT");
 
   __shared__ LevelInfo s_lvl[kMaxSmemLevels];
   __shared__ int4 s_board[kRowsWarps][G * (2 * (32 / G) + 1)];
+  __shared__ float s_part[XSPLIT > 1 ? kRowsWarps : 1][D];   // per-warp partial rows (XSPLIT > 1)
 
   const int MD = d.M * D;
   for (int l = threadIdx.x; l < d.L; l += blockDim.x) s_lvl[l] = load_level(shapes, lsi, l, MD);
@@ -140,11 +146,8 @@ msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   const int s_end = min(LP, s_begin + per);
 
   float acc[VEC];
-  // corner registers persist across samples: a skipped (out-of-map) sample
-  // leaves them untouched and multiplies them by zero weights
-  float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
 #pragma unroll
-  for (int c = 0; c < VEC; ++c) acc[c] = v1[c] = v2[c] = v3[c] = v4[c] = 0.f;
+  for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
 
   // Per-warp record board: slot (j, grp) holds the record of sample j of row
   // group grp as two 16-byte halves; half h lives at 16-byte unit
@@ -173,7 +176,7 @@ msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     {
       const int s = s0 + gl;
       FwdRec r;
-      r.off = 0; r.rsx = kDeadRec; r.w1 = r.w2 = r.w3 = r.w4 = 0.f;
+      r.off = kDeadOff; r.rsx = 0; r.w1 = r.w2 = r.w3 = r.w4 = 0.f;
       if (s < s_end) r = make_fwd_rec<sizeof(VT)>(nxt_xy.x, nxt_xy.y, nxt_a, s_lvl[level_of(s)], MD);
       board[unit_of(gl, grp, 0)] =
           make_int4(r.off, r.rsx, __float_as_int(r.w1), __float_as_int(r.w2));
@@ -191,14 +194,17 @@ msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
       // (broadcasting the record with 6 shuffles instead was measured: 0.241 vs 0.234 ms)
       const int4 q = board[unit_of(j, grp, 0)];
       const float2 w34 = *reinterpret_cast<const float2*>(&board[unit_of(j, grp, 1)]);
-      const int alive = q.y != kDeadRec;
+      const bool alive = q.x != kDeadOff;
       const uint32_t rs = q.y & 0x7fffffff;
       const uint32_t xs = (q.y >> 31) & MDb;  // one pixel to the right, or 0 for a duplicate
-      const uint32_t o1 = static_cast<uint32_t>(q.x) + lane_b;
-      ldg16_pred(vrow, o1, alive, v1);
-      ldg16_pred(vrow, o1 + xs, alive, v2);
-      ldg16_pred(vrow, o1 + rs, alive, v3);
-      ldg16_pred(vrow, o1 + rs + xs, alive, v4);
+      // out-of-map samples read the zero row (their strides are 0, their weights 0)
+      const char* src = alive ? vrow : reinterpret_cast<const char*>(g_zero_row);
+      const uint32_t o1 = (alive ? static_cast<uint32_t>(q.x) : 0u) + lane_b;
+      float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+      Vec16<VT>::load(reinterpret_cast<const VT*>(src + o1), v1);
+      Vec16<VT>::load(reinterpret_cast<const VT*>(src + (o1 + xs)), v2);
+      Vec16<VT>::load(reinterpret_cast<const VT*>(src + (o1 + rs)), v3);
+      Vec16<VT>::load(reinterpret_cast<const VT*>(src + (o1 + rs + xs)), v4);
       const float w1 = __int_as_float(q.z), w2 = __int_as_float(q.w);
 #pragma unroll
       for (int c = 0; c < VEC; ++c) {
@@ -211,11 +217,26 @@ msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     __syncwarp();
   }
 
-  // --- combine the SPLIT partial rows (adjacent groups of the same warp) ---
+  // --- combine the SPLIT partial rows: adjacent groups of a warp by shuffles ... ---
 #pragma unroll
-  for (int off = G; off < G * SPLIT; off <<= 1) {
+  for (int off = G; off < G * WSPLIT; off <<= 1) {
 #pragma unroll
     for (int c = 0; c < VEC; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
+  }
+  // --- ... and, when a row is spread over XSPLIT warps, those through shared memory ---
+  if (XSPLIT > 1) {
+    if (grp == 0) {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) s_part[warp][gl * VEC + c] = acc[c];
+    }
+    __syncthreads();
+    if (grp == 0 && (warp % XSPLIT) == 0) {
+#pragma unroll
+      for (int x = 1; x < XSPLIT; ++x) {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) acc[c] += s_part[warp + x][gl * VEC + c];
+      }
+    }
   }
   if (live && split == 0) {
     float* o = out + unit * D + gl * VEC;
@@ -247,10 +268,16 @@ static cudaError_t launch_rows(const void* value, const int64_t* shapes, const i
                                const float* loc, const float* aw, float* out, const Dims& d,
                                int split, cudaStream_t st) {
   constexpr int G = D / Vec16<VT>::VEC;
-  constexpr int MAXS = 32 / G;
-  if (split >= 8 && MAXS >= 8) return launch_rows_split<D, VT, (MAXS >= 8 ? 8 : 1)>(value, shapes, lsi, loc, aw, out, d, st);
-  if (split >= 4 && MAXS >= 4) return launch_rows_split<D, VT, (MAXS >= 4 ? 4 : 1)>(value, shapes, lsi, loc, aw, out, d, st);
-  if (split >= 2 && MAXS >= 2) return launch_rows_split<D, VT, (MAXS >= 2 ? 2 : 1)>(value, shapes, lsi, loc, aw, out, d, st);
+  constexpr int MAXS = (kRowsThreads / G) < 32 ? (kRowsThreads / G) : 32;  // up to a whole block per row
+#define MSDA_TRY_SPLIT(S)                                                                          \
+  if (split >= S && MAXS >= S)                                                                     \
+    return launch_rows_split<D, VT, (MAXS >= S ? S : 1)>(value, shapes, lsi, loc, aw, out, d, st);
+  MSDA_TRY_SPLIT(32)
+  MSDA_TRY_SPLIT(16)
+  MSDA_TRY_SPLIT(8)
+  MSDA_TRY_SPLIT(4)
+  MSDA_TRY_SPLIT(2)
+#undef MSDA_TRY_SPLIT
   return launch_rows_split<D, VT, 1>(value, shapes, lsi, loc, aw, out, d, st);
 }
 
@@ -259,10 +286,11 @@ static cudaError_t launch_rows(const void* value, const int64_t* shapes, const i
 int choose_split(const Dims& d, int G, int sm_count) {
   if (tuning().fwd_split > 0) return tuning().fwd_split;
   const int64_t units = static_cast<int64_t>(d.B) * d.Q * d.M;
-  const int64_t want_groups = static_cast<int64_t>(sm_count) * (2048 / 32) * (32 / G);  // one full wave of resident warps
+  // aim for ~48 resident warps per SM, but keep at least two chunks of G samples per group
+  const int64_t want_groups = static_cast<int64_t>(sm_count) * 48 * (32 / G);
   const int LP = d.L * d.P;
   int split = 1;
-  while (split < 8 && units * split < want_groups && LP / (split * 2) >= 2 * G) split *= 2;
+  while (split < 32 && units * split < want_groups && LP / (split * 2) >= 2 * G) split *= 2;
   return split;
 }
 
