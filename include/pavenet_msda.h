@@ -116,6 +116,43 @@ int msda_backward(const void *d_value, const int64_t *d_spatial_shapes,
                   int value_dtype, int grad_value_dtype, void *stream);
 
 /*
+ * Fused variants (no counterpart in the reference: they absorb the elementwise
+ * chain its modules run around the op, multi_scale_deform_attn.py:373-393,
+ * opera/models/utils/transformer.py:390-412).  Inputs are the RAW projections:
+ *   d_offsets    (B,Q,M,L,P,2)  sampling_offsets Linear output
+ *   d_logits     (B,Q,M,L*P)    attention_weights Linear output (pre-softmax)
+ *   d_ref_points (B,Q,L,R,2)    reference points, R = ref_points_per_level = 1 or P
+ *   d_scale      (B,Q,L,2)      offset scale, or NULL for 1/(W_l, H_l)
+ * and the kernels compute  loc = ref + off * scale  and  w = softmax(logits)
+ * over L*P themselves.  fp32 only; channels must be 32 (MSDA_ERR_UNSUPPORTED
+ * otherwise — callers then fall back to msda_forward / msda_backward).
+ * d_softmax_stats (B,Q,M,2) is written by the forward (row max, 1/sum) and
+ * read by the backward.  The backward accumulates into the zero-initialised
+ * d_grad_value and overwrites d_grad_offsets / d_grad_logits (softmax and
+ * scale already differentiated through); d_grad_loc, if not NULL, receives
+ * d/d(loc) for callers that need reference-point gradients.
+ */
+int msda_fused_forward(const void *d_value, const int64_t *d_spatial_shapes,
+                       const int64_t *d_level_start_index, const float *d_offsets,
+                       const float *d_logits, const float *d_ref_points,
+                       const float *d_scale, float *d_output,
+                       float *d_softmax_stats, int batch, int spatial_size,
+                       int num_heads, int channels, int num_levels,
+                       int num_query, int num_point, int ref_points_per_level,
+                       int value_dtype, void *stream);
+
+int msda_fused_backward(const void *d_value, const int64_t *d_spatial_shapes,
+                        const int64_t *d_level_start_index,
+                        const float *d_offsets, const float *d_logits,
+                        const float *d_ref_points, const float *d_scale,
+                        const float *d_softmax_stats, const float *d_grad_output,
+                        float *d_grad_value, float *d_grad_offsets,
+                        float *d_grad_logits, float *d_grad_loc, int batch,
+                        int spatial_size, int num_heads, int channels,
+                        int num_levels, int num_query, int num_point,
+                        int ref_points_per_level, int value_dtype, void *stream);
+
+/*
  * Host-buffer convenience entry points (what a cgo / JNI / ctypes caller
  * without its own device memory management binds).  All pointers are HOST
  * pointers (pinned memory gives asynchronous copies; pageable memory works

@@ -15,7 +15,8 @@ There is no CPU path: ops raise if the CUDA library is missing or a tensor is
 not on a CUDA device.
 """
 from . import _capi
-from .functional import (HostWorkspace, MultiScaleDeformableAttnFunction, ext_module,
+from .functional import (FusedMultiScaleDeformableAttnFunction, HostWorkspace,
+                         MultiScaleDeformableAttnFunction, ext_module, fused_supported,
                          fuse_frames_as_levels, ms_deform_attn_backward,
                          ms_deform_attn_forward)
 from .modules import (MulFramesMultiScaleDeformableAttentionNumFrames3,
@@ -31,6 +32,7 @@ __version__ = '0.1.0'
 __all__ = [
     'MultiScaleDeformableAttnFunction', 'ext_module', 'ms_deform_attn_forward',
     'ms_deform_attn_backward', 'fuse_frames_as_levels', 'HostWorkspace',
+    'FusedMultiScaleDeformableAttnFunction', 'fused_supported',
     'MultiScaleDeformableAttention', 'MultiScaleDeformablePoseAttention',
     'MulFramesMultiScaleDeformablePoseAttentionNumFrames3',
     'MulFramesMultiScaleDeformablePoseAttentionNumFrames5',

@@ -90,22 +90,99 @@ __device__ __forceinline__ float group_transpose_reduce(float (&p)[G], int gl) {
 constexpr int kRowsThreads = 256;
 constexpr int kRowsWarps = kRowsThreads / 32;
 
-template <int D, typename VT, typename GT>
+// ---- where the per-sample gradients go -------------------------------------
+// PlainIO: the reference op's outputs, grad_sampling_loc and grad_attn_weight.
+// FusedIO: gradients of the raw projections — grad_offsets = grad_loc * scale
+// and, after a row-wide reduction, the softmax backward
+//   grad_logit_s = w_s * (gw_s - sum_t w_t gw_t)
+// (what autograd would compute through softmax and the location transform,
+// multi_scale_deform_attn.py:375-393), optionally grad_loc for callers that
+// need reference-point gradients.
+struct PlainIO {
+  PlainSource src;
+  float* grad_loc;
+  float* grad_aw;
+  static constexpr bool kFused = false;
+  __device__ __forceinline__ void bind(int64_t unit, int LP, int M, int64_t bq) {
+    src.bind(unit, LP, M, bq);
+    grad_loc += unit * LP * 2;
+    grad_aw += unit * LP;
+  }
+  __device__ __forceinline__ void store(int s, int, float gw, float gx, float gy, float, float,
+                                        float) {
+    __stcs(grad_aw + s, gw);
+    __stcs(reinterpret_cast<float2*>(grad_loc + 2 * s), make_float2(gx, gy));
+  }
+};
+
+struct FusedIO {
+  FusedSource src;
+  float* grad_off;    // (B,Q,M,L,P,2)
+  float* grad_logit;  // (B,Q,M,L*P)
+  float* grad_loc;    // optional (B,Q,M,L,P,2), NULL if reference points need no gradient
+  float dot;          // this lane's share of sum_t w_t gw_t
+  static constexpr bool kFused = true;
+  __device__ __forceinline__ void bind(int64_t unit, int LP, int M, int64_t bq) {
+    src.bind(unit, LP, M, bq);
+    grad_off += unit * LP * 2;
+    grad_logit += unit * LP;
+    if (grad_loc) grad_loc += unit * LP * 2;
+    dot = 0.f;
+  }
+  // gw: d/d(attention weight); (gx, gy): d/d(location); w: the sample's softmax weight
+  __device__ __forceinline__ void store(int s, int l, float gw, float gx, float gy, float w,
+                                        float Wf, float Hf) {
+    float2 go;
+    if (src.scale) {
+      const float2 sc = __ldg(reinterpret_cast<const float2*>(src.scale) + l);
+      go = make_float2(gx * sc.x, gy * sc.y);
+    } else {
+      go = make_float2(gx / Wf, gy / Hf);
+    }
+    __stcs(reinterpret_cast<float2*>(grad_off + 2 * s), go);
+    if (grad_loc) __stcs(reinterpret_cast<float2*>(grad_loc + 2 * s), make_float2(gx, gy));
+    grad_logit[s] = gw;  // parked here until the row's dot product is known
+    dot += w * gw;
+  }
+};
+
+template <int G>
+__device__ __forceinline__ void finish_softmax_backward(PlainIO&, float*, int, int, int, int) {}
+
+// Turns the parked gw_s into grad_logit_s = w_s (gw_s - dot).  The row may be
+// split over several groups of the block: their partial dots meet in shared
+// memory.  Every thread of the block must call this (it has a barrier).
+template <int G>
+__device__ __forceinline__ void finish_softmax_backward(FusedIO& io, float* s_dot, int row_in_block,
+                                                        int s_begin, int s_end, int gl) {
+  float dot = io.dot;
+#pragma unroll
+  for (int o = G / 2; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  if (gl == 0 && s_end > s_begin) atomicAdd(&s_dot[row_in_block], dot);
+  __syncthreads();
+  dot = s_dot[row_in_block];
+  for (int s = s_begin + gl; s < s_end; s += G) {
+    const float w = expf(__ldg(io.src.logit + s) - io.src.mx) * io.src.inv;
+    io.grad_logit[s] = w * (io.grad_logit[s] - dot);   // own earlier write: same thread
+  }
+}
+
+template <int D, typename VT, typename GT, class IO>
 __global__ void __launch_bounds__(kRowsThreads)
 msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
-                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
-                     const float* __restrict__ aw, const float* __restrict__ grad_out,
-                     GT* __restrict__ grad_value, float* __restrict__ grad_loc,
-                     float* __restrict__ grad_aw, Dims d, int nsplit) {
+                     const int64_t* __restrict__ lsi, IO io, const float* __restrict__ grad_out,
+                     GT* __restrict__ grad_value, Dims d, int nsplit) {
   constexpr int VEC = Vec16<VT>::VEC;
   constexpr int G = D / VEC;
   static_assert(D % VEC == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0, "bad D");
 
   __shared__ LevelInfo s_lvl[kMaxSmemLevels];
   __shared__ int4 s_board[kRowsWarps][G * (2 * (32 / G) + 1)];
+  __shared__ float s_dot[IO::kFused ? kRowsThreads / G : 1];  // fused: per-row sum_t w_t gw_t
 
   const int MD = d.M * D;
   for (int l = threadIdx.x; l < d.L; l += blockDim.x) s_lvl[l] = load_level(shapes, lsi, l, MD);
+  if (IO::kFused && threadIdx.x < kRowsThreads / G) s_dot[threadIdx.x] = 0.f;
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -134,10 +211,8 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   const VT* vbase = value + boff;
   GT* gvbase = grad_value + boff - (kHalves ? gl * VEC : 0);  // kHalves: row start, lanes add their own slots
   const int LP = d.L * d.P;
-  const float* loc_u = loc + unit * LP * 2;
-  const float* aw_u = aw + unit * LP;
-  float* gloc_u = grad_loc + unit * LP * 2;
-  float* gaw_u = grad_aw + unit * LP;
+  io.bind(unit, LP, d.M, b * d.Q + q_idx);
+  io.src.template prepass<G>(LP, gl, false);   // fused: row max and 1/sum saved by the forward
 
   float g[VEC];
   {
@@ -171,38 +246,36 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   auto unit_of = [](int j, int grp_, int half) { return j * (2 * NG + 1) + 2 * grp_ + half; };
   const FastDivP level_of(d.P);
 
-  float2 nxt_xy = make_float2(0.f, 0.f);
-  float nxt_a = 0.f;
+  RawSample nxt;
+  nxt.x = nxt.y = nxt.w = 0.f;
   {
     const int s = s_begin + gl;
-    if (s < s_end) {
-      nxt_xy = ld_stream_f2(loc_u + 2 * s);
-      nxt_a = ld_stream_f(aw_u + s);
-    }
+    if (s < s_end) nxt = io.src.load(s);
   }
   for (int s0 = s_begin; s0 < s_begin + per; s0 += G) {
     const int s = s0 + gl;
-    float Wf = 0.f, Hf = 0.f;
+    float Wf = 0.f, Hf = 0.f, w_true = 0.f;
+    int lvl = 0;
     {
       SampleRec r;
       r.off00 = 0; r.meta = 0; r.lh = 0.f; r.lw = 0.f; r.a = 0.f; r.rs = 0;
       if (s < s_end) {
-        r.a = nxt_a;
-        const int l = level_of(s);
-        const LevelInfo lv = s_lvl[l];
+        lvl = level_of(s);
+        const LevelInfo lv = s_lvl[lvl];
+        RawSample cur = nxt;
+        io.src.finish(cur, s, lvl, lv);
+        w_true = cur.w;
+        r.a = cur.w;
         Wf = static_cast<float>(lv.W);
         Hf = static_cast<float>(lv.H);
         r.rs = lv.row_stride;
-        make_sample(nxt_xy.x, nxt_xy.y, r.a, lv, l, MD, r.off00, r.meta, r.lh, r.lw);
+        make_sample(cur.x, cur.y, r.a, lv, lvl, MD, r.off00, r.meta, r.lh, r.lw);
       }
       board[unit_of(gl, grp, 0)] =
           make_int4(r.off00, r.meta, __float_as_int(r.lh), __float_as_int(r.lw));
       *reinterpret_cast<int2*>(&board[unit_of(gl, grp, 1)]) = make_int2(__float_as_int(r.a), r.rs);
       const int sn = s + G;
-      if (sn < s_end) {
-        nxt_xy = ld_stream_f2(loc_u + 2 * sn);
-        nxt_a = ld_stream_f(aw_u + sn);
-      }
+      if (sn < s_end) nxt = io.src.load(sn);
     }
     __syncwarp();
 
@@ -258,12 +331,10 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     const float tw = group_transpose_reduce<G>(pw, gl);
     const float tx = group_transpose_reduce<G>(px, gl);
     const float ty = group_transpose_reduce<G>(py, gl);
-    if (s < s_end) {
-      __stcs(gaw_u + s, tw);
-      __stcs(reinterpret_cast<float2*>(gloc_u + 2 * s), make_float2(Wf * tx, Hf * ty));
-    }
+    if (s < s_end) io.store(s, lvl, tw, Wf * tx, Hf * ty, w_true, Wf, Hf);
     __syncwarp();
   }
+  finish_softmax_backward<G>(io, s_dot, gib / nsplit, s_begin, s_end, gl);
 }
 
 // --------------------------------------------------------------------------
@@ -365,20 +436,18 @@ msda_bwd_generic_kernel(const VT* __restrict__ value, const int64_t* __restrict_
 // --------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------
-template <int D, typename VT, typename GT>
+template <int D, typename VT, typename GT, class IO>
 static cudaError_t launch_bwd_rows(const void* value, const int64_t* shapes, const int64_t* lsi,
-                                   const float* loc, const float* aw, const float* go, void* gv,
-                                   float* gloc, float* gaw, const Dims& d, int nsplit,
-                                   cudaStream_t st) {
+                                   const IO& io, const float* go, void* gv, const Dims& d,
+                                   int nsplit, cudaStream_t st) {
   constexpr int G = D / Vec16<VT>::VEC;
   constexpr int GPB = kRowsThreads / G;
   if (nsplit > GPB) nsplit = GPB;   // (a power of two, so it divides GPB)
   const int qpb = GPB / nsplit;
   const int64_t blocks = static_cast<int64_t>(d.B) * ((d.Q + qpb - 1) / qpb) * d.M;
   if (blocks >= (int64_t(1) << 31)) return cudaErrorInvalidConfiguration;
-  msda_bwd_rows_kernel<D, VT, GT><<<static_cast<unsigned>(blocks), kRowsThreads, 0, st>>>(
-      static_cast<const VT*>(value), shapes, lsi, loc, aw, go, static_cast<GT*>(gv), gloc, gaw, d,
-      nsplit);
+  msda_bwd_rows_kernel<D, VT, GT, IO><<<static_cast<unsigned>(blocks), kRowsThreads, 0, st>>>(
+      static_cast<const VT*>(value), shapes, lsi, io, go, static_cast<GT*>(gv), d, nsplit);
   note_launches(1);
   return cudaGetLastError();
 }
@@ -405,25 +474,23 @@ cudaError_t launch_backward(const void* value, const int64_t* shapes, const int6
   if (dtype == MSDA_F32 && !force_generic && d.L <= kMaxSmemLevels &&
       rows_supported(d.D, value_dtype) &&
       (grad_value_dtype == MSDA_F32 || (grad_value_dtype == MSDA_BF16 && value_dtype == MSDA_BF16))) {
-    const float* locf = static_cast<const float*>(loc);
-    const float* awf = static_cast<const float*>(aw);
+    PlainIO io;
+    io.src.loc = static_cast<const float*>(loc);
+    io.src.aw = static_cast<const float*>(aw);
+    io.grad_loc = static_cast<float*>(grad_loc);
+    io.grad_aw = static_cast<float*>(grad_aw);
     const float* gof = static_cast<const float*>(grad_out);
-    float* glocf = static_cast<float*>(grad_loc);
-    float* gawf = static_cast<float*>(grad_aw);
 #define MSDA_BWD_CASE(DD)                                                                         \
   case DD:                                                                                        \
     if (value_dtype == MSDA_F32) {                                                                \
-      return launch_bwd_rows<DD, float, float>(value, shapes, lsi, locf, awf, gof, grad_value,    \
-                                               glocf, gawf, d,                                    \
-                                               choose_bwd_split(d, DD / 4, sm_count), st);        \
+      return launch_bwd_rows<DD, float, float, PlainIO>(                                          \
+          value, shapes, lsi, io, gof, grad_value, d, choose_bwd_split(d, DD / 4, sm_count), st); \
     } else if (grad_value_dtype == MSDA_F32) {                                                    \
-      return launch_bwd_rows<DD, __nv_bfloat16, float>(value, shapes, lsi, locf, awf, gof,        \
-                                                       grad_value, glocf, gawf, d,                \
-                                                       choose_bwd_split(d, DD / 8, sm_count), st); \
+      return launch_bwd_rows<DD, __nv_bfloat16, float, PlainIO>(                                  \
+          value, shapes, lsi, io, gof, grad_value, d, choose_bwd_split(d, DD / 8, sm_count), st); \
     } else {                                                                                      \
-      return launch_bwd_rows<DD, __nv_bfloat16, __nv_bfloat16>(                                   \
-          value, shapes, lsi, locf, awf, gof, grad_value, glocf, gawf, d,                         \
-          choose_bwd_split(d, DD / 8, sm_count), st);                                             \
+      return launch_bwd_rows<DD, __nv_bfloat16, __nv_bfloat16, PlainIO>(                          \
+          value, shapes, lsi, io, gof, grad_value, d, choose_bwd_split(d, DD / 8, sm_count), st); \
     }
     switch (d.D) {
       MSDA_BWD_CASE(16)
@@ -454,6 +521,28 @@ cudaError_t launch_backward(const void* value, const int64_t* shapes, const int6
 #undef MSDA_GEN
   note_launches(1);
   return cudaGetLastError();
+}
+
+// fused epilogue: D = 32, fp32 gradients, fp32 or bf16 value
+cudaError_t launch_backward_fused(const void* value, const int64_t* shapes, const int64_t* lsi,
+                                  const FusedSource& src, const float* grad_out, float* grad_value,
+                                  float* grad_off, float* grad_logit, float* grad_loc,
+                                  const Dims& d, int value_dtype, int sm_count, cudaStream_t st) {
+  if (d.D != 32 || d.L > kMaxSmemLevels) return cudaErrorNotSupported;
+  FusedIO io;
+  io.src = src;
+  io.src.stats_ready = 1;
+  io.grad_off = grad_off;
+  io.grad_logit = grad_logit;
+  io.grad_loc = grad_loc;
+  io.dot = 0.f;
+  if (value_dtype == MSDA_F32)
+    return launch_bwd_rows<32, float, float, FusedIO>(value, shapes, lsi, io, grad_out, grad_value,
+                                                      d, choose_bwd_split(d, 8, sm_count), st);
+  if (value_dtype == MSDA_BF16)
+    return launch_bwd_rows<32, __nv_bfloat16, float, FusedIO>(
+        value, shapes, lsi, io, grad_out, grad_value, d, choose_bwd_split(d, 4, sm_count), st);
+  return cudaErrorNotSupported;
 }
 
 }  // namespace msda

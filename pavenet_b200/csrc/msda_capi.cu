@@ -193,6 +193,92 @@ int msda_backward(const void* d_value, const int64_t* d_spatial_shapes,
 }
 
 // ---------------------------------------------------------------------------
+// fused entry points: softmax and the reference-point transform inside the kernels
+// ---------------------------------------------------------------------------
+static int fused_source(FusedSource* src, const float* off, const float* logit, const float* ref,
+                        const float* scale, float* stats, int ref_per_level, int num_point) {
+  if (ref_per_level != 1 && ref_per_level != num_point)
+    return fail(MSDA_ERR_INVALID_ARGUMENT,
+                "ref_points_per_level must be 1 or num_point (%d), got %d", num_point, ref_per_level);
+  src->off = off; src->logit = logit; src->ref = ref; src->scale = scale; src->stats = stats;
+  src->R = ref_per_level; src->P = num_point; src->stats_ready = 0; src->mx = 0.f; src->inv = 0.f;
+  return MSDA_OK;
+}
+
+int msda_fused_forward(const void* d_value, const int64_t* d_spatial_shapes,
+                       const int64_t* d_level_start_index, const float* d_offsets,
+                       const float* d_logits, const float* d_ref_points, const float* d_scale,
+                       float* d_output, float* d_softmax_stats, int batch, int spatial_size,
+                       int num_heads, int channels, int num_levels, int num_query, int num_point,
+                       int ref_points_per_level, int value_dtype, void* stream) {
+  if (!d_value || !d_spatial_shapes || !d_level_start_index || !d_offsets || !d_logits ||
+      !d_ref_points || !d_output || !d_softmax_stats)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_fused_forward: NULL pointer argument");
+  Dims d;
+  int rc = check_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, &d);
+  if (rc) return rc;
+  rc = check_dtypes(MSDA_F32, value_dtype, -1);
+  if (rc) return rc;
+  if (misaligned16(d_value) || misaligned16(d_output) || misaligned16(d_offsets))
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_fused_forward needs 16-byte aligned buffers");
+  FusedSource src;
+  rc = fused_source(&src, d_offsets, d_logits, d_ref_points, d_scale, d_softmax_stats,
+                    ref_points_per_level, num_point);
+  if (rc) return rc;
+  int sms = 0;
+  rc = current_sm_count(&sms);
+  if (rc) return rc;
+  const cudaError_t e = launch_forward_fused(d_value, d_spatial_shapes, d_level_start_index, src,
+                                             d_output, d, value_dtype, sms,
+                                             static_cast<cudaStream_t>(stream));
+  if (e == cudaErrorNotSupported)
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_fused_forward: only channels == 32 and <= %d levels",
+                kMaxSmemLevels);
+  if (e != cudaSuccess)
+    return fail(MSDA_ERR_CUDA, "msda_fused_forward launch failed: %s", cudaGetErrorString(e));
+  return MSDA_OK;
+}
+
+int msda_fused_backward(const void* d_value, const int64_t* d_spatial_shapes,
+                        const int64_t* d_level_start_index, const float* d_offsets,
+                        const float* d_logits, const float* d_ref_points, const float* d_scale,
+                        const float* d_softmax_stats, const float* d_grad_output,
+                        float* d_grad_value, float* d_grad_offsets, float* d_grad_logits,
+                        float* d_grad_loc, int batch, int spatial_size, int num_heads,
+                        int channels, int num_levels, int num_query, int num_point,
+                        int ref_points_per_level, int value_dtype, void* stream) {
+  if (!d_value || !d_spatial_shapes || !d_level_start_index || !d_offsets || !d_logits ||
+      !d_ref_points || !d_softmax_stats || !d_grad_output || !d_grad_value || !d_grad_offsets ||
+      !d_grad_logits)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_fused_backward: NULL pointer argument");
+  Dims d;
+  int rc = check_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, &d);
+  if (rc) return rc;
+  rc = check_dtypes(MSDA_F32, value_dtype, MSDA_F32);
+  if (rc) return rc;
+  if (misaligned16(d_value) || misaligned16(d_grad_output) || misaligned16(d_grad_value) ||
+      misaligned16(d_offsets) || misaligned16(d_grad_offsets))
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_fused_backward needs 16-byte aligned buffers");
+  FusedSource src;
+  rc = fused_source(&src, d_offsets, d_logits, d_ref_points, d_scale,
+                    const_cast<float*>(d_softmax_stats), ref_points_per_level, num_point);
+  if (rc) return rc;
+  int sms = 0;
+  rc = current_sm_count(&sms);
+  if (rc) return rc;
+  const cudaError_t e = launch_backward_fused(
+      d_value, d_spatial_shapes, d_level_start_index, src, d_grad_output, d_grad_value,
+      d_grad_offsets, d_grad_logits, d_grad_loc, d, value_dtype, sms,
+      static_cast<cudaStream_t>(stream));
+  if (e == cudaErrorNotSupported)
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_fused_backward: only channels == 32 and <= %d levels",
+                kMaxSmemLevels);
+  if (e != cudaSuccess)
+    return fail(MSDA_ERR_CUDA, "msda_fused_backward launch failed: %s", cudaGetErrorString(e));
+  return MSDA_OK;
+}
+
+// ---------------------------------------------------------------------------
 // host-buffer entry points
 //
 // The staged call is pipelined: work is cut into (batch entry, query chunk)

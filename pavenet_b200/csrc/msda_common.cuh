@@ -118,6 +118,100 @@ __device__ __forceinline__ float2 ld_stream_f2(const float* p) {
 }
 __device__ __forceinline__ float ld_stream_f(const float* p) { return __ldcs(p); }
 
+// ---- where a sample's (x, y, weight) comes from ----------------------------
+// PlainSource: the reference op's inputs — materialised sampling_locations and
+// attention_weights.  FusedSource: the raw projections the modules compute
+// (offsets, attention logits) plus reference points; the location transform
+//   loc = ref[b,q,l,(p)] + off * scale[b,q,l]      (scale == NULL: off / (W_l, H_l))
+// and the softmax over the L*P logits of a row happen in the kernel, so the
+// two largest intermediates of the modules are never written or re-read
+// (multi_scale_deform_attn.py:373-393; transformer.py:390-412).
+struct RawSample {
+  float x, y, w;   // location (or offset) and weight (or logit), as loaded
+};
+
+struct PlainSource {
+  const float* loc;
+  const float* aw;
+  __device__ __forceinline__ void bind(int64_t unit, int LP, int, int64_t) {
+    loc += unit * LP * 2;
+    aw += unit * LP;
+  }
+  template <int G>
+  __device__ __forceinline__ void prepass(int, int, bool) {}
+  __device__ __forceinline__ RawSample load(int s) const {
+    const float2 xy = ld_stream_f2(loc + 2 * s);
+    RawSample r;
+    r.x = xy.x; r.y = xy.y; r.w = ld_stream_f(aw + s);
+    return r;
+  }
+  __device__ __forceinline__ void finish(RawSample& r, int, int, const LevelInfo&) const {}
+};
+
+struct FusedSource {
+  const float* off;      // (B,Q,M,L,P,2)
+  const float* logit;    // (B,Q,M,L*P)
+  const float* ref;      // (B,Q,L,R,2)
+  const float* scale;    // (B,Q,L,2) or NULL
+  float* stats;          // (B,Q,M,2): row max and 1/sum(exp) — written by the forward, read by the backward
+  int R;                 // reference points per level: 1 or P
+  int P;
+  int stats_ready;       // backward: read stats instead of recomputing them
+  float mx, inv;
+  __device__ __forceinline__ void bind(int64_t unit, int LP, int M, int64_t bq) {
+    off += unit * LP * 2;
+    logit += unit * LP;
+    stats += unit * 2;
+    const int L = LP / P;
+    ref += bq * L * R * 2;
+    if (scale) scale += bq * L * 2;
+    (void)M;
+  }
+  // max and sum over the row's logits, by the G lanes of the group
+  template <int G>
+  __device__ __forceinline__ void prepass(int LP, int gl, bool writer) {
+    if (stats_ready) {
+      mx = stats[0];
+      inv = stats[1];
+      return;
+    }
+    float m_ = -INFINITY;
+    for (int s = gl; s < LP; s += G) m_ = fmaxf(m_, __ldg(logit + s));
+#pragma unroll
+    for (int o = G / 2; o >= 1; o >>= 1) m_ = fmaxf(m_, __shfl_xor_sync(0xffffffffu, m_, o));
+    float sum = 0.f;
+    for (int s = gl; s < LP; s += G) sum += expf(__ldg(logit + s) - m_);
+#pragma unroll
+    for (int o = G / 2; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mx = m_;
+    inv = 1.f / sum;
+    if (writer && gl == 0) {
+      stats[0] = mx;
+      stats[1] = inv;
+    }
+  }
+  __device__ __forceinline__ RawSample load(int s) const {
+    const float2 xy = ld_stream_f2(off + 2 * s);
+    RawSample r;
+    r.x = xy.x; r.y = xy.y; r.w = __ldg(logit + s);
+    return r;
+  }
+  // offsets -> location, logit -> softmax weight
+  __device__ __forceinline__ void finish(RawSample& r, int s, int l, const LevelInfo& lv) const {
+    const int p = s - l * P;
+    const float2 rp = __ldg(reinterpret_cast<const float2*>(ref) + (l * R + (R == 1 ? 0 : p)));
+    if (scale) {
+      const float2 sc = __ldg(reinterpret_cast<const float2*>(scale) + l);
+      r.x = rp.x + r.x * sc.x;
+      r.y = rp.y + r.y * sc.y;
+    } else {
+      r.x = rp.x + r.x / static_cast<float>(lv.W);
+      r.y = rp.y + r.y / static_cast<float>(lv.H);
+    }
+    r.w = expf(r.w - mx) * inv;
+  }
+};
+
 // ---- sample record -------------------------------------------------------
 // What the lane that "owns" a sample computes once and the G lanes of the
 // row group consume.  32 bytes in shared memory.

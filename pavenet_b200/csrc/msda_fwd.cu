@@ -88,11 +88,10 @@ constexpr int kRowsWarps = kRowsThreads / 32;
 // which are latency bound (measured on B200: pose cfg3 58 -> 48 us).
 constexpr int fwd_min_blocks(int split) { return split > 1 ? 3 : 4; }
 
-template <int D, typename VT, int SPLIT>
+template <int D, typename VT, int SPLIT, class SRC>
 __global__ void __launch_bounds__(kRowsThreads, fwd_min_blocks(SPLIT))
 msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
-                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
-                     const float* __restrict__ aw, float* __restrict__ out, Dims d) {
+                     const int64_t* __restrict__ lsi, SRC src, float* __restrict__ out, Dims d) {
   constexpr int VEC = Vec16<VT>::VEC;
   constexpr int G = D / VEC;  // lanes per row
   static_assert(D % VEC == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0, "bad D");
@@ -137,8 +136,8 @@ msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   const uint32_t lane_b = gl * 16;
   const uint32_t MDb = MD * sizeof(VT);
   const int LP = d.L * d.P;
-  const float* loc_u = loc + unit * LP * 2;
-  const float* aw_u = aw + unit * LP;
+  src.bind(unit, LP, d.M, b * d.Q + q_idx);
+  src.template prepass<G>(LP, gl, live && split == 0);  // fused: softmax max / sum of the row
 
   // sample range of this split, in chunks of G
   const int per = ((LP + SPLIT - 1) / SPLIT + G - 1) / G * G;
@@ -162,14 +161,11 @@ msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
 
   // locations / weights of the chunk after the current one are fetched while
   // the current chunk is being gathered (they come from DRAM)
-  float2 nxt_xy = make_float2(0.f, 0.f);
-  float nxt_a = 0.f;
+  RawSample nxt;
+  nxt.x = nxt.y = nxt.w = 0.f;
   {
     const int s = s_begin + gl;
-    if (s < s_end) {
-      nxt_xy = ld_stream_f2(loc_u + 2 * s);
-      nxt_a = ld_stream_f(aw_u + s);
-    }
+    if (s < s_end) nxt = src.load(s);
   }
   for (int s0 = s_begin; s0 < s_begin + per; s0 += G) {
     // --- one lane per sample resolves the geometry and the four weights ---
@@ -177,15 +173,18 @@ msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
       const int s = s0 + gl;
       FwdRec r;
       r.off = kDeadOff; r.rsx = 0; r.w1 = r.w2 = r.w3 = r.w4 = 0.f;
-      if (s < s_end) r = make_fwd_rec<sizeof(VT)>(nxt_xy.x, nxt_xy.y, nxt_a, s_lvl[level_of(s)], MD);
+      if (s < s_end) {
+        const int l = level_of(s);
+        const LevelInfo lv = s_lvl[l];
+        RawSample cur = nxt;
+        src.finish(cur, s, l, lv);
+        r = make_fwd_rec<sizeof(VT)>(cur.x, cur.y, cur.w, lv, MD);
+      }
       board[unit_of(gl, grp, 0)] =
           make_int4(r.off, r.rsx, __float_as_int(r.w1), __float_as_int(r.w2));
       *reinterpret_cast<float2*>(&board[unit_of(gl, grp, 1)]) = make_float2(r.w3, r.w4);
       const int sn = s + G;
-      if (sn < s_end) {
-        nxt_xy = ld_stream_f2(loc_u + 2 * sn);
-        nxt_a = ld_stream_f(aw_u + sn);
-      }
+      if (sn < s_end) nxt = src.load(sn);
     }
     __syncwarp();
     // --- the whole group gathers each sample of the chunk ---
@@ -249,36 +248,35 @@ msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
 // --------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------
-template <int D, typename VT, int SPLIT>
+template <int D, typename VT, int SPLIT, class SRC>
 static cudaError_t launch_rows_split(const void* value, const int64_t* shapes, const int64_t* lsi,
-                                     const float* loc, const float* aw, float* out, const Dims& d,
-                                     cudaStream_t st) {
+                                     const SRC& src, float* out, const Dims& d, cudaStream_t st) {
   constexpr int G = D / Vec16<VT>::VEC;
   constexpr int QPB = kRowsThreads / G / SPLIT;
   const int64_t blocks = static_cast<int64_t>(d.B) * ((d.Q + QPB - 1) / QPB) * d.M;
   if (blocks >= (int64_t(1) << 31)) return cudaErrorInvalidConfiguration;
-  msda_fwd_rows_kernel<D, VT, SPLIT><<<static_cast<unsigned>(blocks), kRowsThreads, 0, st>>>(
-      static_cast<const VT*>(value), shapes, lsi, loc, aw, out, d);
+  msda_fwd_rows_kernel<D, VT, SPLIT, SRC><<<static_cast<unsigned>(blocks), kRowsThreads, 0, st>>>(
+      static_cast<const VT*>(value), shapes, lsi, src, out, d);
   note_launches(1);
   return cudaGetLastError();
 }
 
-template <int D, typename VT>
+template <int D, typename VT, class SRC>
 static cudaError_t launch_rows(const void* value, const int64_t* shapes, const int64_t* lsi,
-                               const float* loc, const float* aw, float* out, const Dims& d,
-                               int split, cudaStream_t st) {
+                               const SRC& src, float* out, const Dims& d, int split,
+                               cudaStream_t st) {
   constexpr int G = D / Vec16<VT>::VEC;
   constexpr int MAXS = (kRowsThreads / G) < 32 ? (kRowsThreads / G) : 32;  // up to a whole block per row
 #define MSDA_TRY_SPLIT(S)                                                                          \
   if (split >= S && MAXS >= S)                                                                     \
-    return launch_rows_split<D, VT, (MAXS >= S ? S : 1)>(value, shapes, lsi, loc, aw, out, d, st);
+    return launch_rows_split<D, VT, (MAXS >= S ? S : 1), SRC>(value, shapes, lsi, src, out, d, st);
   MSDA_TRY_SPLIT(32)
   MSDA_TRY_SPLIT(16)
   MSDA_TRY_SPLIT(8)
   MSDA_TRY_SPLIT(4)
   MSDA_TRY_SPLIT(2)
 #undef MSDA_TRY_SPLIT
-  return launch_rows_split<D, VT, 1>(value, shapes, lsi, loc, aw, out, d, st);
+  return launch_rows_split<D, VT, 1, SRC>(value, shapes, lsi, src, out, d, st);
 }
 
 // How many groups should share one row: enough that the grid covers the
@@ -304,17 +302,18 @@ cudaError_t launch_forward(const void* value, const int64_t* shapes, const int64
                            int value_dtype, int sm_count, int force_generic, cudaStream_t st) {
   if (dtype == MSDA_F32 && !force_generic && d.L <= kMaxSmemLevels &&
       rows_supported(d.D, value_dtype)) {
-    const float* locf = static_cast<const float*>(loc);
-    const float* awf = static_cast<const float*>(aw);
+    PlainSource src;
+    src.loc = static_cast<const float*>(loc);
+    src.aw = static_cast<const float*>(aw);
     float* outf = static_cast<float*>(out);
 #define MSDA_ROWS_CASE(DD)                                                                   \
   case DD:                                                                                   \
     if (value_dtype == MSDA_F32) {                                                           \
       const int split = choose_split(d, DD / 4, sm_count);                                   \
-      return launch_rows<DD, float>(value, shapes, lsi, locf, awf, outf, d, split, st);      \
+      return launch_rows<DD, float, PlainSource>(value, shapes, lsi, src, outf, d, split, st); \
     } else {                                                                                 \
       const int split = choose_split(d, DD / 8, sm_count);                                   \
-      return launch_rows<DD, __nv_bfloat16>(value, shapes, lsi, locf, awf, outf, d, split, st); \
+      return launch_rows<DD, __nv_bfloat16, PlainSource>(value, shapes, lsi, src, outf, d, split, st); \
     }
     switch (d.D) {
       MSDA_ROWS_CASE(16)
@@ -345,6 +344,20 @@ cudaError_t launch_forward(const void* value, const int64_t* shapes, const int64
   }
   note_launches(1);
   return cudaGetLastError();
+}
+
+// fused prologue: D = 32 only (PAVE-Net's head size), fp32 or bf16 value
+cudaError_t launch_forward_fused(const void* value, const int64_t* shapes, const int64_t* lsi,
+                                 const FusedSource& src, float* out, const Dims& d, int value_dtype,
+                                 int sm_count, cudaStream_t st) {
+  if (d.D != 32 || d.L > kMaxSmemLevels) return cudaErrorNotSupported;
+  if (value_dtype == MSDA_F32)
+    return launch_rows<32, float, FusedSource>(value, shapes, lsi, src, out, d,
+                                               choose_split(d, 8, sm_count), st);
+  if (value_dtype == MSDA_BF16)
+    return launch_rows<32, __nv_bfloat16, FusedSource>(value, shapes, lsi, src, out, d,
+                                                       choose_split(d, 4, sm_count), st);
+  return cudaErrorNotSupported;
 }
 
 }  // namespace msda

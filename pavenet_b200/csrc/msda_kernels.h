@@ -31,6 +31,15 @@ cudaError_t launch_backward(const void* value, const int64_t* shapes, const int6
                             int dtype, int value_dtype, int grad_value_dtype, int sm_count,
                             int force_generic, cudaStream_t st);
 
+cudaError_t launch_forward_fused(const void* value, const int64_t* shapes, const int64_t* lsi,
+                                 const FusedSource& src, float* out, const Dims& d, int value_dtype,
+                                 int sm_count, cudaStream_t st);
+
+cudaError_t launch_backward_fused(const void* value, const int64_t* shapes, const int64_t* lsi,
+                                  const FusedSource& src, const float* grad_out, float* grad_value,
+                                  float* grad_off, float* grad_logit, float* grad_loc,
+                                  const Dims& d, int value_dtype, int sm_count, cudaStream_t st);
+
 // number of kernel launches the last launch_* call on this thread enqueued
 int last_launches();
 void note_launches(int n);

@@ -18,7 +18,7 @@ from . import _capi
 __all__ = [
     'MultiScaleDeformableAttnFunction', 'ext_module', 'ms_deform_attn_forward',
     'ms_deform_attn_backward', 'fuse_frames_as_levels', 'BF16_GRAD_VALUE_ATOMICS',
-    'HostWorkspace',
+    'HostWorkspace', 'FusedMultiScaleDeformableAttnFunction', 'fused_supported',
 ]
 
 #: When value is stored in bf16, accumulate grad_value in an fp32 scratch
@@ -327,3 +327,106 @@ class HostWorkspace(object):
             _DTYPE_CODE[value.dtype])
         _capi.check(status, 'msda_forward_backward_host')
         return out, grad_value, grad_sampling_loc, grad_attn_weight
+
+
+# ---------------------------------------------------------------------------
+# fused prologue / epilogue
+# ---------------------------------------------------------------------------
+def fused_supported(value, offsets):
+    """True when `FusedMultiScaleDeformableAttnFunction` has a kernel for these
+    tensors (CUDA, fp32 projections, fp32/bf16 value, 32 channels per head)."""
+    return (value.is_cuda and offsets.is_cuda and value.dim() == 4 and value.shape[-1] == 32
+            and offsets.dtype == torch.float32
+            and value.dtype in (torch.float32, torch.bfloat16)
+            and offsets.dim() == 6 and 0 < offsets.shape[3] <= 64
+            and min(value.shape) > 0 and min(offsets.shape) > 0)
+
+
+class FusedMultiScaleDeformableAttnFunction(Function):
+    """The op with the modules' elementwise chain folded in.
+
+    Replaces, in one forward and one backward launch,
+        weights   = softmax(logits over L*P)
+        locations = ref_points + offsets * scale        (scale None: / (W_l, H_l))
+        out       = MultiScaleDeformableAttnFunction(value, ..., locations, weights)
+    (multi_scale_deform_attn.py:373-401; transformer.py:390-420) so that
+    `sampling_locations` / `attention_weights` and their gradients are never
+    written to or re-read from HBM.
+
+    Args:
+        value (bs, num_keys, heads, 32), fp32 or bf16
+        spatial_shapes (L, 2) int64, level_start_index (L,) int64, on the GPU
+        offsets (bs, Q, heads, L, P, 2) fp32 — raw `sampling_offsets` output
+        logits (bs, Q, heads, L*P) fp32 — raw `attention_weights` output
+        ref_points (bs, Q, L, R, 2) fp32, R = 1 (one reference per level) or P (one per point)
+        scale (bs, Q, L, 2) fp32 or None
+    Returns (bs, Q, heads*32).
+    """
+
+    @staticmethod
+    def forward(ctx, value, spatial_shapes, level_start_index, offsets, logits, ref_points, scale):
+        B, S, M, D = value.shape
+        _, Q, _, L, P, _ = offsets.shape
+        R = ref_points.shape[3]
+        if not fused_supported(value, offsets):
+            raise RuntimeError('fused deformable attention: unsupported tensors '
+                               '(need CUDA, fp32 projections, 32 channels per head)')
+        if tuple(logits.shape) != (B, Q, M, L * P) or tuple(ref_points.shape) != (B, Q, L, R, 2) \
+                or R not in (1, P) or (scale is not None and tuple(scale.shape) != (B, Q, L, 2)):
+            raise RuntimeError('fused deformable attention: inconsistent shapes value %s offsets %s '
+                               'logits %s ref_points %s' % (tuple(value.shape), tuple(offsets.shape),
+                                                            tuple(logits.shape), tuple(ref_points.shape)))
+        value, offsets, logits = value.contiguous(), offsets.contiguous(), logits.contiguous()
+        ref_points = ref_points.contiguous().float()
+        scale = None if scale is None else scale.contiguous().float()
+        lib = _capi.load()
+        with torch.cuda.device(value.device):
+            out = torch.empty((B, Q, M * D), dtype=torch.float32, device=value.device)
+            stats = torch.empty((B, Q, M, 2), dtype=torch.float32, device=value.device)
+            status = lib.msda_fused_forward(
+                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                offsets.data_ptr(), logits.data_ptr(), ref_points.data_ptr(),
+                None if scale is None else scale.data_ptr(), out.data_ptr(), stats.data_ptr(),
+                B, S, M, D, L, Q, P, R, _DTYPE_CODE[value.dtype],
+                torch.cuda.current_stream().cuda_stream)
+        _capi.check(status, 'msda_fused_forward')
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, offsets, logits,
+                              ref_points, scale, stats)
+        ctx.has_scale = scale is not None
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, spatial_shapes, level_start_index, offsets, logits, ref_points, scale, stats = \
+            ctx.saved_tensors
+        B, S, M, D = value.shape
+        _, Q, _, L, P, _ = offsets.shape
+        R = ref_points.shape[3]
+        need_ref = ctx.needs_input_grad[5]
+        need_scale = ctx.has_scale and ctx.needs_input_grad[6]
+        lib = _capi.load()
+        with torch.cuda.device(value.device):
+            grad_value = torch.zeros(value.shape, dtype=torch.float32, device=value.device)
+            grad_offsets = torch.empty_like(offsets)
+            grad_logits = torch.empty_like(logits)
+            grad_loc = torch.empty_like(offsets) if (need_ref or need_scale) else None
+            status = lib.msda_fused_backward(
+                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                offsets.data_ptr(), logits.data_ptr(), ref_points.data_ptr(),
+                None if scale is None else scale.data_ptr(), stats.data_ptr(),
+                grad_output.contiguous().data_ptr(), grad_value.data_ptr(),
+                grad_offsets.data_ptr(), grad_logits.data_ptr(),
+                None if grad_loc is None else grad_loc.data_ptr(),
+                B, S, M, D, L, Q, P, R, _DTYPE_CODE[value.dtype],
+                torch.cuda.current_stream().cuda_stream)
+        _capi.check(status, 'msda_fused_backward')
+        if grad_value.dtype != value.dtype:
+            grad_value = grad_value.to(value.dtype)
+        grad_ref = grad_scale = None
+        if need_ref:
+            # loc = ref[b,q,l,(p)] + ...: sum over heads (and over points when R == 1)
+            grad_ref = grad_loc.sum(dim=2) if R == P else grad_loc.sum(dim=(2, 4)).unsqueeze(3)
+        if need_scale:
+            grad_scale = (grad_loc * offsets).sum(dim=(2, 4))
+        return grad_value, None, None, grad_offsets, grad_logits, grad_ref, grad_scale

@@ -32,7 +32,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .functional import MultiScaleDeformableAttnFunction, fuse_frames_as_levels
+from .functional import (FusedMultiScaleDeformableAttnFunction, MultiScaleDeformableAttnFunction,
+                         fuse_frames_as_levels, fused_supported)
 from .registry import ATTENTION, OPERA_ATTENTION
 
 __all__ = [
@@ -84,8 +85,22 @@ def _run_op(value, spatial_shapes, level_start_index, loc, weights, im2col_step)
         weights.contiguous(), im2col_step)
 
 
+def _run_fused(value, spatial_shapes, level_start_index, offsets, logits, ref_points, scale):
+    """softmax + location transform + sampling in one kernel (forward and backward)."""
+    return FusedMultiScaleDeformableAttnFunction.apply(
+        value, spatial_shapes, level_start_index, offsets, logits, ref_points, scale)
+
+
 class _DeformAttnBase(nn.Module):
     """Shared constructor logic (argument checks are the reference's)."""
+
+    #: fold softmax and the reference-point transform into the sampling kernels
+    #: when the shapes allow it (CUDA, fp32 projections, 32 channels per head);
+    #: False reproduces the reference's op-by-op composition
+    fuse_prologue = True
+
+    def _can_fuse(self, value, offsets):
+        return self.fuse_prologue and fused_supported(value, offsets)
 
     def __init__(self, embed_dims, num_heads, num_levels, num_points, im2col_step, dropout,
                  batch_first, norm_cfg, init_cfg, value_dtype):
@@ -175,6 +190,21 @@ class MultiScaleDeformableAttention(_DeformAttnBase):
             bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
         attention_weights = self.attention_weights(query).view(
             bs, num_query, self.num_heads, self.num_levels * self.num_points)
+        if reference_points.shape[-1] not in (2, 4):
+            raise ValueError(f'Last dim of reference_points must be 2 or 4, '
+                             f'but get {reference_points.shape[-1]} instead.')
+        if self._can_fuse(value, sampling_offsets):
+            if reference_points.shape[-1] == 2:
+                ref, scale = reference_points.unsqueeze(3), None        # off / (W_l, H_l) in-kernel
+            else:
+                ref = reference_points[..., :2].unsqueeze(3)
+                scale = reference_points[..., 2:] * (0.5 / self.num_points)
+            output = _run_fused(value, spatial_shapes, level_start_index, sampling_offsets,
+                                attention_weights, ref, scale)
+            output = self.output_proj(output)
+            if not self.batch_first:
+                output = output.permute(1, 0, 2)
+            return self.dropout(output) + identity
         attention_weights = attention_weights.softmax(-1).view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points)
         if reference_points.shape[-1] == 2:
@@ -253,15 +283,20 @@ class MultiScaleDeformablePoseAttention(_DeformAttnBase):
             bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
         attention_weights = self.attention_weights(query).view(
             bs, num_query, self.num_heads, self.num_levels * self.num_points)
-        attention_weights = attention_weights.softmax(-1).view(
-            bs, num_query, self.num_heads, self.num_levels, self.num_points)
         if reference_points.shape[-1] != self.num_points * 2:
             raise ValueError(f'Last dim of reference_points must be 2K, '
                              f'but get {reference_points.shape[-1]} instead.')
-        kpts = reference_points.reshape(bs, num_query, self.num_levels, -1, 2).unsqueeze(2)
-        sampling_locations = kpts + sampling_offsets * _pose_box_wh(kpts) * 0.5
-        output = _run_op(value, spatial_shapes, level_start_index, sampling_locations,
-                         attention_weights, self.im2col_step)
+        kpts = reference_points.reshape(bs, num_query, self.num_levels, -1, 2)
+        if self._can_fuse(value, sampling_offsets):
+            output = _run_fused(value, spatial_shapes, level_start_index, sampling_offsets,
+                                attention_weights, kpts, _pose_box_wh(kpts).squeeze(3) * 0.5)
+        else:
+            attention_weights = attention_weights.softmax(-1).view(
+                bs, num_query, self.num_heads, self.num_levels, self.num_points)
+            kpts = kpts.unsqueeze(2)
+            sampling_locations = kpts + sampling_offsets * _pose_box_wh(kpts) * 0.5
+            output = _run_op(value, spatial_shapes, level_start_index, sampling_locations,
+                             attention_weights, self.im2col_step)
         # the reference permutes unconditionally here (transformer.py:425)
         output = self.output_proj(output).permute(1, 0, 2)
         return self.dropout(output) + inp_residual
@@ -359,15 +394,20 @@ class _MulFramesPoseAttention(_MulFramesBase):
                 bs, num_query, M, T * L, P, 2)
             logits = self._stacked_linear(query, 'attention_weights', L * P).view(
                 bs, num_query, M, T * L * P)
-            weights = logits.softmax(-1).view(bs, num_query, M, T * L, P)
-            kpts_f = kpts.permute(0, 2, 1, 3, 4, 5).reshape(bs, num_query, 1, T * L, P, 2)
-            wh_f = wh.permute(0, 2, 1, 3, 4, 5).reshape(bs, num_query, 1, T * L, 1, 2)
-            locations = kpts_f + offsets * wh_f * 0.5
+            kpts_f = kpts.permute(0, 2, 1, 3, 4, 5).reshape(bs, num_query, T * L, P, 2)
+            wh_f = wh.permute(0, 2, 1, 3, 4, 5).reshape(bs, num_query, T * L, 2)
             shapes_f, starts_f = fuse_frames_as_levels(spatial_shapes, level_start_index, T,
                                                        num_key)
             # frames of clip b are rows b*T .. b*T+T-1: a free reinterpretation
             value_f = value.reshape(bs, T * num_key, M, -1)
-            output = _run_op(value_f, shapes_f, starts_f, locations, weights, self.im2col_step)
+            if self._can_fuse(value_f, offsets):
+                output = _run_fused(value_f, shapes_f, starts_f, offsets, logits, kpts_f,
+                                    wh_f * 0.5)
+            else:
+                weights = logits.softmax(-1).view(bs, num_query, M, T * L, P)
+                locations = kpts_f.unsqueeze(2) + offsets * wh_f[:, :, None, :, None, :] * 0.5
+                output = _run_op(value_f, shapes_f, starts_f, locations, weights,
+                                 self.im2col_step)
         else:
             outs, logits = [], []
             for t, pre in enumerate(self._prefixes):
@@ -476,19 +516,30 @@ class _MulFramesJointAttention(_MulFramesBase):
                 bs, num_query, M, T * L, P, 2)
             logits = self._stacked_linear(query, 'attention_weights', L * P).view(
                 bs, num_query, M, T * L * P)
-            weights = logits.softmax(-1).view(bs, num_query, M, T * L, P)
-            if ref_dim == 2:
-                ref_f = ref.permute(1, 2, 0, 3, 4).reshape(bs, num_query, 1, T * L, 1, 2)
-                locations = ref_f + offsets / normalizer.repeat(T, 1)[None, None, None, :, None, :]
-            else:
-                ref_f = ref.repeat(1, 1, T, 1)[:, :, None, :, None, :]
-                locations = ref_f[..., :2] + offsets / P * ref_f[..., 2:] * 0.5
             shapes_f, starts_f = fuse_frames_as_levels(spatial_shapes, level_start_index, T,
                                                        num_value)
             # frames are interleaved along dim 2 here, so this is one copy
             # (the reference makes T `.contiguous()` copies of the same bytes)
             value_f = value.permute(0, 2, 1, 3).reshape(bs, T * num_value, M, -1)
-            output = _run_op(value_f, shapes_f, starts_f, locations, weights, self.im2col_step)
+            if ref_dim == 2:
+                ref_f = ref.permute(1, 2, 0, 3, 4).reshape(bs, num_query, T * L, 1, 2)
+                scale_f = None
+            else:
+                boxes = ref.repeat(1, 1, T, 1)
+                ref_f = boxes[..., :2].unsqueeze(3)
+                scale_f = boxes[..., 2:] * (0.5 / P)
+            if self._can_fuse(value_f, offsets):
+                output = _run_fused(value_f, shapes_f, starts_f, offsets, logits, ref_f, scale_f)
+            else:
+                weights = logits.softmax(-1).view(bs, num_query, M, T * L, P)
+                if ref_dim == 2:
+                    locations = ref_f.unsqueeze(2) \
+                        + offsets / normalizer.repeat(T, 1)[None, None, None, :, None, :]
+                else:
+                    locations = ref_f.unsqueeze(2) \
+                        + offsets / P * boxes[:, :, None, :, None, 2:] * 0.5
+                output = _run_op(value_f, shapes_f, starts_f, locations, weights,
+                                 self.im2col_step)
         else:
             outs, logits = [], []
             for t, pre in enumerate(self._prefixes):

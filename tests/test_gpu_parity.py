@@ -457,6 +457,162 @@ def test_module_gradients_flow_and_match_composition_oracle(module_golden):
         assert rel_err(params[k].grad, st[k].grad) < BWD_TOL_F32, k
 
 
+# --------------------------------------------------------------------------
+# fused prologue / epilogue (softmax + location transform inside the kernels)
+# --------------------------------------------------------------------------
+def _fused_problem(seed, B, Q, P, shapes, R, with_scale, value_dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    shapes_t = torch.tensor(shapes, dtype=torch.long)
+    L, M, D = len(shapes), 8, 32
+    S = int(shapes_t.prod(1).sum())
+    value = torch.randn(B, S, M, D, generator=g).to(value_dtype)
+    offsets = torch.randn(B, Q, M, L, P, 2, generator=g) * (0.5 if with_scale else 3.0)
+    logits = torch.randn(B, Q, M, L * P, generator=g) * 2
+    ref = torch.rand(B, Q, L, R, 2, generator=g) * 0.9 + 0.05
+    scale = torch.rand(B, Q, L, 2, generator=g) * 0.3 + 0.02 if with_scale else None
+    go = torch.randn(B, Q, M * D, generator=g)
+    return value, shapes_t, offsets, logits, ref, scale, go
+
+
+def _unfused_reference(value, shapes_t, offsets, logits, ref, scale):
+    """The chain the fused op replaces, in plain torch on the CPU + the oracle op
+    (differentiable through grid_sample_port)."""
+    B, Q, M, L, P, _ = offsets.shape
+    w = logits.softmax(-1).view(B, Q, M, L, P)
+    if scale is None:
+        norm = torch.stack([shapes_t[:, 1], shapes_t[:, 0]], -1).to(offsets.dtype)
+        loc = ref[:, :, None] + offsets / norm[None, None, None, :, None, :]
+    else:
+        loc = ref[:, :, None] + offsets * scale[:, :, None, :, None, :]
+    return O.grid_sample_port(value.float(), shapes_t, loc, w)
+
+
+@pytest.mark.parametrize('Q,P,shapes,R,with_scale', [
+    (333, 4, MID_LEVELS, 1, False),        # encoder: off / (W, H)
+    (200, 4, MID_LEVELS, 1, True),         # reference boxes
+    (300, 15, MID_LEVELS * 3, 15, True),   # fused 3-frame pose decoder: ref per keypoint, wh scale
+    (40, 17, MID_LEVELS * 5, 17, True),    # 5 frames: 20 levels, row split over several groups
+    (3, 1, [(2, 3)], 1, False),
+])
+def test_fused_function_matches_unfused_chain(Q, P, shapes, R, with_scale):
+    import pavenet_b200
+    fused = pavenet_b200.FusedMultiScaleDeformableAttnFunction.apply
+    value, shapes_t, offsets, logits, ref, scale, go = _fused_problem(Q, 2, Q, P, shapes, R, with_scale)
+    lsi = O.level_start_index(shapes_t)
+    leaves = [t.clone().requires_grad_() for t in (value, offsets, logits, ref)]
+    sc = None if scale is None else scale.clone().requires_grad_()
+    ref_out = _unfused_reference(leaves[0], shapes_t, leaves[1], leaves[2], leaves[3], sc)
+    ref_out.backward(go)
+    cu = [t.cuda().requires_grad_() for t in (value, offsets, logits, ref)]
+    sc_cu = None if scale is None else scale.cuda().requires_grad_()
+    out = fused(cu[0], shapes_t.cuda(), lsi.cuda(), cu[1], cu[2], cu[3], sc_cu)
+    out.backward(go.cuda())
+    assert rel_err(out, ref_out) < FWD_TOL_F32
+    for a, b, name in zip(cu, leaves, ('value', 'offsets', 'logits', 'ref_points')):
+        assert rel_err(a.grad, b.grad) < BWD_TOL_F32, name
+    if scale is not None:
+        assert rel_err(sc_cu.grad, sc.grad) < BWD_TOL_F32
+
+
+def test_fused_function_bf16_value():
+    import pavenet_b200
+    fused = pavenet_b200.FusedMultiScaleDeformableAttnFunction.apply
+    value, shapes_t, offsets, logits, ref, scale, go = _fused_problem(
+        5, 1, 256, 4, MID_LEVELS, 1, False, value_dtype=torch.bfloat16)
+    lsi = O.level_start_index(shapes_t)
+    v = value.cuda().requires_grad_()
+    o = offsets.cuda().requires_grad_()
+    out = fused(v, shapes_t.cuda(), lsi.cuda(), o, logits.cuda(), ref.cuda(), None)
+    out.backward(go.cuda())
+    vr = value.float().requires_grad_()
+    orf = offsets.clone().requires_grad_()
+    ref_out = _unfused_reference(vr, shapes_t, orf, logits, ref, None)
+    ref_out.backward(go)
+    assert rel_err(out, ref_out) < 2e-5            # same rounded value on both sides
+    assert v.grad.dtype == torch.bfloat16 and rel_err(v.grad.float(), vr.grad) < 4e-3
+    assert rel_err(o.grad, orf.grad) < BWD_TOL_F32
+
+
+def _full_size_module(cls_name, **kw):
+    import pavenet_b200
+    torch.manual_seed(0)
+    mod = getattr(pavenet_b200, cls_name)(dropout=0.0, **kw).cuda()
+    with torch.no_grad():
+        for name, p in mod.named_parameters():
+            if 'sampling_offsets' in name or 'attention_weights' in name:
+                p.add_(torch.randn_like(p) * 0.05)
+    return mod
+
+
+@pytest.mark.parametrize('case', ['encoder', 'encoder_box', 'pose', 'mf_pose3', 'mf_pose5',
+                                  'mf_joint3', 'mf_joint5'])
+def test_modules_fused_prologue_equals_op_by_op(case):
+    """embed_dims 256 / 8 heads (32 channels per head, the PAVE-Net geometry):
+    every module class with the fused kernels against the same module running
+    the reference's op-by-op composition (fuse_prologue=False), outputs and all
+    parameter / input gradients."""
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    shapes = torch.tensor(MID_LEVELS)
+    lsi = O.level_start_index(shapes).cuda()
+    S = int(shapes.prod(1).sum())
+    L, C = 4, 256
+
+    def rnd(*s):
+        return torch.randn(*s, generator=g).cuda()
+
+    if case.startswith('encoder'):
+        mod = _full_size_module('MultiScaleDeformableAttention')
+        B = 2
+        ref = torch.rand(B, S, L, 4 if case == 'encoder_box' else 2, generator=g).cuda()
+        args = (rnd(S, B, C),)
+        kwargs = dict(query_pos=rnd(S, B, C), reference_points=ref)
+    elif case == 'pose':
+        mod = _full_size_module('MultiScaleDeformablePoseAttention', num_points=17)
+        B, Q = 2, 50
+        args = (rnd(Q, B, C), None, rnd(S, B, C))
+        kwargs = dict(query_pos=rnd(Q, B, C),
+                      reference_points=torch.rand(B, Q, L, 34, generator=g).cuda().requires_grad_())
+    elif case.startswith('mf_pose'):
+        T = int(case[-1])
+        mod = _full_size_module('MulFramesMultiScaleDeformablePoseAttentionNumFrames%d' % T,
+                                num_points=15)
+        Bc, Q = 2, 30
+        args = (rnd(Q, Bc, C), None, rnd(S, Bc * T, C))
+        kwargs = dict(query_pos=rnd(Q, Bc, C),
+                      key_padding_mask=(torch.rand(Bc * T, S, generator=g) < 0.1).cuda(),
+                      reference_points=torch.rand(Bc, T * Q, L, 30, generator=g).cuda().requires_grad_())
+    else:
+        T = int(case[-1])
+        mod = _full_size_module('MulFramesMultiScaleDeformableAttentionNumFrames%d' % T)
+        G, Q = 3, 15
+        args = (rnd(Q, G, C), None, rnd(S, G, T, C))
+        kwargs = dict(query_pos=rnd(Q, G, C),
+                      reference_points=torch.rand(T * G, Q, L, 2, generator=g).cuda())
+    kwargs.update(spatial_shapes=shapes.cuda(), level_start_index=lsi)
+
+    results = []
+    for fuse in (True, False):
+        mod.fuse_prologue = fuse
+        mod.zero_grad()
+        ins = [a.clone().requires_grad_() if isinstance(a, torch.Tensor) else a for a in args]
+        rp = kwargs['reference_points']
+        if rp.requires_grad:
+            rp.grad = None
+        out = mod(*ins, **kwargs)
+        out.square().sum().backward()
+        grads = {n: p.grad.clone() for n, p in mod.named_parameters()}
+        grads['query'] = ins[0].grad.clone()
+        if len(ins) > 2:
+            grads['value_in'] = ins[2].grad.clone()
+        if rp.requires_grad:
+            grads['reference_points'] = rp.grad.clone()
+        results.append((out.detach(), grads))
+    (out_f, g_f), (out_u, g_u) = results
+    assert rel_err(out_f, out_u) < 1e-5
+    for name in g_u:
+        assert rel_err(g_f[name], g_u[name]) < 2e-4, name
+
+
 @pytest.mark.parametrize('pinned', [True, False])
 def test_host_buffer_entry_points(pinned):
     """msda_forward_host / msda_forward_backward_host (pipelined over batch
