@@ -17,9 +17,11 @@ Prints ONE JSON line on stdout (rank 0).  Keys beyond the base contract:
                 whole step (fwd + grad_value zero-fill + bwd)
   cpu_baseline  the reference's CPU path (per-level grid_sample + autograd),
                 restated in oracle/msda_oracle.py, timed on this host's cores
-  e2e           the same metric through MultiScaleDeformableAttnFunction with
-                pinned HOST buffers: H2D of the inputs and D2H of output and
-                gradients inside the timed region
+  e2e           the same metric through the C-ABI host-buffer call
+                (msda_forward_backward_host) with pinned HOST buffers: H2D of
+                the inputs and D2H of output and all gradients inside the timed
+                region, pipelined inside the library
+  e2e_autograd  the same copies issued serially around the autograd Function
 Multi-GPU: clips are independent, so each rank runs its own clips (weak
 scaling) with no collective on the data path; one all-reduce(MAX) of the
 elapsed time at the end.
@@ -295,12 +297,13 @@ def load_peak():
         return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
-def load_traffic(kernel_key):
-    """dram bytes per launch from the committed ncu capture, if any."""
+def load_traffic(workload, kernel_key):
+    """dram bytes per launch of this workload's kernel from the committed
+    `ncu --set full` capture (profiles/traffic.json), or None."""
     path = os.path.join(ROOT, 'profiles', 'traffic.json')
     try:
         with open(path) as f:
-            return json.load(f).get(kernel_key)
+            return json.load(f).get(workload, {}).get(kernel_key)
     except Exception:  # noqa: BLE001
         return None
 
@@ -316,6 +319,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--sets', type=int, default=4, help='distinct input sets rotated per step')
+    ap.add_argument('--piece-mb', type=float, default=0, help='e2e: upload MiB per pipeline piece (0 = library default)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -447,6 +451,8 @@ def main():
 
         # (1) the C-ABI host-buffer call a non-PyTorch caller binds (pipelined inside the library)
         hws = pavenet_b200.HostWorkspace()
+        if args.piece_mb > 0:
+            hws.set_piece_bytes(int(args.piece_mb * (1 << 20)))
 
         def e2e_capi():
             hws.forward_backward(host['value'], shapes_h, lsi_h, host['loc'], host['aw'],
@@ -480,12 +486,13 @@ def main():
     if rank == 0:
         peak, peak_src = load_peak()
         vb = 4 if vdt == torch.float32 else 2
+        traffic_wl = wl if vdt == torch.float32 else wl + '_bf16'
         ab = algorithmic_bytes(dims, value_bytes=vb, grad_value_bytes=4)
 
         def roof(nbytes, ms, key):
             gbs = nbytes / (ms * 1e-3) / 1e9
             return {'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s',
-                    'frac': gbs / peak, 'traffic': load_traffic(key), 'kernel': key,
+                    'frac': gbs / peak, 'traffic': load_traffic(traffic_wl, key), 'kernel': key,
                     'algorithmic_bytes': nbytes, 'kernel_ms': ms, 'peak_source': peak_src,
                     'frac_of_8TBs_nominal': gbs / 8000.0}
 

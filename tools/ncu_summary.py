@@ -49,5 +49,33 @@ def main(path):
         print('%-78s %16.3f %s' % ('traffic = dram read + write', rd + wr, u))
 
 
+def traffic(path, out_json, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, keyed by kernel
+    family, merged into `out_json` (what bench.py reports as roofline.traffic)."""
+    import json
+    import os
+    raw = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], stdout=subprocess.PIPE,
+                         stderr=subprocess.DEVNULL, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    db = json.load(open(out_json)) if os.path.exists(out_json) else {}
+    entry = db.setdefault(workload, {})
+    for d in data:
+        name = d[hdr.index('Kernel Name')]
+        key = 'msda_bwd_rows_kernel' if 'msda_bwd' in name else 'msda_fwd_rows_kernel'
+        tot = 0.0
+        for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            i = hdr.index(m)
+            tot += float(d[i]) * scale[units[i]]
+        entry[key] = tot
+    entry['source'] = os.path.basename(path)
+    json.dump(db, open(out_json, 'w'), indent=1, sort_keys=True)
+    print(json.dumps(db[workload]))
+
+
 if __name__ == '__main__':
-    main(sys.argv[1])
+    if len(sys.argv) >= 5 and sys.argv[1] == '--traffic':
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        main(sys.argv[1])
