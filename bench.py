@@ -201,6 +201,17 @@ class ClockSampler(object):
 # ---------------------------------------------------------------------------
 # CPU baseline: the reference's grid_sample path, restated in oracle/
 # ---------------------------------------------------------------------------
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every
+    core this process may run on."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_reference_step(prob_cpu):
     """One fwd+bwd of the reference CPU algorithm on CPU tensors; returns seconds."""
     from oracle import msda_oracle as O
@@ -225,6 +236,7 @@ def cpu_sample_problem(wl, frames=1, queries=None):
 
 
 def measure_cpu_baseline(wl, budget_s=20.0):
+    use_all_host_threads()
     cfg = WORKLOADS[wl]
     full_q = sum(h * w for h, w in cfg['levels']) if cfg['kind'] == 'encoder' else cfg['Q']
     prob = cpu_sample_problem(wl, frames=1, queries=min(full_q, 4096))
@@ -255,6 +267,7 @@ def run_reference_arm(args, world, rank):
     all host threads, rank 0 only."""
     if rank != 0:
         return
+    use_all_host_threads()
     wl = args.workload
     cfg = WORKLOADS[wl]
     full_q = sum(h * w for h, w in cfg['levels']) if cfg['kind'] == 'encoder' else cfg['Q']
@@ -515,7 +528,7 @@ def main():
             'clocks': clock_info, 'gpu_launches': int(launches), 'e2e': e2e,
             'e2e_autograd': e2e_autograd,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N = 1 only
             line['cpu_baseline'] = measure_cpu_baseline(wl)
         print(json.dumps(line), flush=True)
     if world > 1:
