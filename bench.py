@@ -332,6 +332,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--sets', type=int, default=4, help='distinct input sets rotated per step')
+    ap.add_argument('--fused', action='store_true', help='time the fused-prologue kernels (offsets/logits in, softmax + location transform in-kernel) on the same problem')
     ap.add_argument('--piece-mb', type=float, default=0, help='e2e: upload MiB per pipeline piece (0 = library default)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -364,6 +365,18 @@ def main():
              for i in range(args.sets)]
     dims = probs[0]['dims']
     q_per_step = dims['B'] * dims['Q']
+    if args.fused:
+        # the same samples expressed as the modules' raw projections:
+        # loc = ref + off / (W_l, H_l) with ref = 0.5, aw = softmax(logits)
+        lib = _capi.load()
+        norm = torch.stack([probs[0]['shapes'][:, 1], probs[0]['shapes'][:, 0]], -1).float()
+        for p in probs:
+            B_, Q_, M_, L_, P_ = p['aw'].shape
+            p['ref'] = torch.full((B_, Q_, L_, 1, 2), 0.5, device=device)
+            p['off'] = ((p['loc'] - 0.5) * norm[None, None, None, :, None, :]).contiguous()
+            p['logit'] = p['aw'].clamp_min(1e-30).log().reshape(B_, Q_, M_, L_ * P_).contiguous()
+            p['stats'] = torch.empty((B_, Q_, M_, 2), device=device)
+            p['out'] = torch.empty((B_, Q_, M_ * dims['D']), device=device)
     gv_dtype = torch.float32
     bufs = [dict(grad_value=torch.empty(p['value'].shape, dtype=gv_dtype, device=device),
                  grad_loc=torch.empty_like(p['loc']), grad_aw=torch.empty_like(p['aw']))
@@ -372,18 +385,38 @@ def main():
                     if isinstance(t, torch.Tensor))
     footprint += sum(t.numel() * t.element_size() for b in bufs for t in b.values())
 
+    vcode = 0 if vdt == torch.float32 else 2
+
     def step(i, ev=None):
         p, b = probs[i % args.sets], bufs[i % args.sets]
+        stream = torch.cuda.current_stream().cuda_stream
         if ev:
             ev[0].record()
-        out = ms_deform_attn_forward(p['value'], p['shapes'], p['lsi'], p['loc'], p['aw'], 64)
+        if args.fused:
+            _capi.check(lib.msda_fused_forward(
+                p['value'].data_ptr(), p['shapes'].data_ptr(), p['lsi'].data_ptr(),
+                p['off'].data_ptr(), p['logit'].data_ptr(), p['ref'].data_ptr(), None,
+                p['out'].data_ptr(), p['stats'].data_ptr(), dims['B'], dims['S'], dims['M'],
+                dims['D'], dims['L'], dims['Q'], dims['P'], 1, vcode, stream), 'msda_fused_forward')
+            out = p['out']
+        else:
+            out = ms_deform_attn_forward(p['value'], p['shapes'], p['lsi'], p['loc'], p['aw'], 64)
         if ev:
             ev[1].record()
         b['grad_value'].zero_()
         if ev:
             ev[2].record()
-        ms_deform_attn_backward(p['value'], p['shapes'], p['lsi'], p['loc'], p['aw'],
-                                p['grad_out'], b['grad_value'], b['grad_loc'], b['grad_aw'], 64)
+        if args.fused:
+            _capi.check(lib.msda_fused_backward(
+                p['value'].data_ptr(), p['shapes'].data_ptr(), p['lsi'].data_ptr(),
+                p['off'].data_ptr(), p['logit'].data_ptr(), p['ref'].data_ptr(), None,
+                p['stats'].data_ptr(), p['grad_out'].data_ptr(), b['grad_value'].data_ptr(),
+                b['grad_loc'].data_ptr(), b['grad_aw'].data_ptr(), None, dims['B'], dims['S'],
+                dims['M'], dims['D'], dims['L'], dims['Q'], dims['P'], 1, vcode, stream),
+                'msda_fused_backward')
+        else:
+            ms_deform_attn_backward(p['value'], p['shapes'], p['lsi'], p['loc'], p['aw'],
+                                    p['grad_out'], b['grad_value'], b['grad_loc'], b['grad_aw'], 64)
         if ev:
             ev[3].record()
         return out
@@ -517,7 +550,7 @@ def main():
             'vs_baseline': None, 'dtype': 'f32' if vdt == torch.float32 else 'f32 (bf16 value storage)',
             'data': 'synthetic',
             'config': {'workload': wl, 'description': cfg['desc'], 'dims': dims,
-                       'queries_per_step': q_per_step, 'kernel': kname,
+                       'queries_per_step': q_per_step, 'kernel': kname + (' + fused prologue' if args.fused else ''),
                        'l2_policy': 'inputs larger than L2: %d distinct clips rotated per step, '
                                     '%.2f GB footprint per GPU' % (args.sets, footprint / 1e9),
                        'parallelism': 'clip-sharded x%d, no data-path collective' % world},

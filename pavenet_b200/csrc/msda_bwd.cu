@@ -108,10 +108,11 @@ struct PlainIO {
     grad_loc += unit * LP * 2;
     grad_aw += unit * LP;
   }
-  __device__ __forceinline__ void store(int s, int, float gw, float gx, float gy, float, float,
-                                        float) {
+  // gw: d/d(attention weight); (tx, ty): d/d(pixel coordinate), so d/d(location) = (W tx, H ty)
+  __device__ __forceinline__ void store(int s, int, int, float gw, float tx, float ty, float,
+                                        float Wf, float Hf) {
     __stcs(grad_aw + s, gw);
-    __stcs(reinterpret_cast<float2*>(grad_loc + 2 * s), make_float2(gx, gy));
+    __stcs(reinterpret_cast<float2*>(grad_loc + 2 * s), make_float2(Wf * tx, Hf * ty));
   }
 };
 
@@ -121,6 +122,10 @@ struct FusedIO {
   float* grad_logit;  // (B,Q,M,L*P)
   float* grad_loc;    // optional (B,Q,M,L,P,2), NULL if reference points need no gradient
   float dot;          // this lane's share of sum_t w_t gw_t
+  // (w_s, gw_s) of the first kCache samples this lane owns stay in registers until the
+  // row's dot product is known; later ones are parked in grad_logit and re-read
+  static constexpr int kCache = 2;
+  float wc[kCache], gc[kCache];
   static constexpr bool kFused = true;
   __device__ __forceinline__ void bind(int64_t unit, int LP, int M, int64_t bq) {
     src.bind(unit, LP, M, bq);
@@ -128,47 +133,61 @@ struct FusedIO {
     grad_logit += unit * LP;
     if (grad_loc) grad_loc += unit * LP * 2;
     dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < kCache; ++k) wc[k] = gc[k] = 0.f;
   }
-  // gw: d/d(attention weight); (gx, gy): d/d(location); w: the sample's softmax weight
-  __device__ __forceinline__ void store(int s, int l, float gw, float gx, float gy, float w,
+  // ci: index of the chunk within this group's sample range
+  __device__ __forceinline__ void store(int s, int l, int ci, float gw, float tx, float ty, float w,
                                         float Wf, float Hf) {
     float2 go;
     if (src.scale) {
       const float2 sc = __ldg(reinterpret_cast<const float2*>(src.scale) + l);
-      go = make_float2(gx * sc.x, gy * sc.y);
+      go = make_float2(Wf * tx * sc.x, Hf * ty * sc.y);
     } else {
-      go = make_float2(gx / Wf, gy / Hf);
+      go = make_float2(tx, ty);   // d loc / d off = 1 / (W, H) cancels the pixel scale
     }
     __stcs(reinterpret_cast<float2*>(grad_off + 2 * s), go);
-    if (grad_loc) __stcs(reinterpret_cast<float2*>(grad_loc + 2 * s), make_float2(gx, gy));
-    grad_logit[s] = gw;  // parked here until the row's dot product is known
+    if (grad_loc) __stcs(reinterpret_cast<float2*>(grad_loc + 2 * s), make_float2(Wf * tx, Hf * ty));
+#pragma unroll
+    for (int k = 0; k < kCache; ++k) {
+      wc[k] = (ci == k) ? w : wc[k];
+      gc[k] = (ci == k) ? gw : gc[k];
+    }
+    if (ci >= kCache) grad_logit[s] = gw;  // parked until the row's dot product is known
     dot += w * gw;
   }
 };
 
 template <int G>
-__device__ __forceinline__ void finish_softmax_backward(PlainIO&, float*, int, int, int, int) {}
+__device__ __forceinline__ void finish_softmax_backward(PlainIO&, float*, int, int, int, int, int) {}
 
-// Turns the parked gw_s into grad_logit_s = w_s (gw_s - dot).  The row may be
-// split over several groups of the block: their partial dots meet in shared
-// memory.  Every thread of the block must call this (it has a barrier).
+// grad_logit_s = w_s (gw_s - dot), dot = sum_t w_t gw_t over the row.  A row
+// split over several groups of the block (nsplit > 1) adds its partial dots in
+// shared memory; every thread of the block must then reach the barrier.
 template <int G>
 __device__ __forceinline__ void finish_softmax_backward(FusedIO& io, float* s_dot, int row_in_block,
-                                                        int s_begin, int s_end, int gl) {
+                                                        int s_begin, int s_end, int gl, int nsplit) {
   float dot = io.dot;
 #pragma unroll
   for (int o = G / 2; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-  if (gl == 0 && s_end > s_begin) atomicAdd(&s_dot[row_in_block], dot);
-  __syncthreads();
-  dot = s_dot[row_in_block];
-  for (int s = s_begin + gl; s < s_end; s += G) {
-    const float w = expf(__ldg(io.src.logit + s) - io.src.mx) * io.src.inv;
+  if (nsplit > 1) {
+    if (gl == 0 && s_end > s_begin) atomicAdd(&s_dot[row_in_block], dot);
+    __syncthreads();
+    dot = s_dot[row_in_block];
+  }
+#pragma unroll
+  for (int k = 0; k < FusedIO::kCache; ++k) {
+    const int s = s_begin + gl + k * G;
+    if (s < s_end) io.grad_logit[s] = io.wc[k] * (io.gc[k] - dot);
+  }
+  for (int s = s_begin + gl + FusedIO::kCache * G; s < s_end; s += G) {
+    const float w = __expf(__ldg(io.src.logit + s) - io.src.mx) * io.src.inv;
     io.grad_logit[s] = w * (io.grad_logit[s] - dot);   // own earlier write: same thread
   }
 }
 
 template <int D, typename VT, typename GT, class IO>
-__global__ void __launch_bounds__(kRowsThreads)
+__global__ void __launch_bounds__(kRowsThreads, IO::kFused ? 2 : 0)
 msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, IO io, const float* __restrict__ grad_out,
                      GT* __restrict__ grad_value, Dims d, int nsplit) {
@@ -331,10 +350,10 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     const float tw = group_transpose_reduce<G>(pw, gl);
     const float tx = group_transpose_reduce<G>(px, gl);
     const float ty = group_transpose_reduce<G>(py, gl);
-    if (s < s_end) io.store(s, lvl, tw, Wf * tx, Hf * ty, w_true, Wf, Hf);
+    if (s < s_end) io.store(s, lvl, (s0 - s_begin) / G, tw, tx, ty, w_true, Wf, Hf);
     __syncwarp();
   }
-  finish_softmax_backward<G>(io, s_dot, gib / nsplit, s_begin, s_end, gl);
+  finish_softmax_backward<G>(io, s_dot, gib / nsplit, s_begin, s_end, gl, nsplit);
 }
 
 // --------------------------------------------------------------------------

@@ -180,7 +180,7 @@ struct FusedSource {
 #pragma unroll
     for (int o = G / 2; o >= 1; o >>= 1) m_ = fmaxf(m_, __shfl_xor_sync(0xffffffffu, m_, o));
     float sum = 0.f;
-    for (int s = gl; s < LP; s += G) sum += expf(__ldg(logit + s) - m_);
+    for (int s = gl; s < LP; s += G) sum += __expf(__ldg(logit + s) - m_);
 #pragma unroll
     for (int o = G / 2; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     mx = m_;
@@ -205,10 +205,10 @@ struct FusedSource {
       r.x = rp.x + r.x * sc.x;
       r.y = rp.y + r.y * sc.y;
     } else {
-      r.x = rp.x + r.x / static_cast<float>(lv.W);
-      r.y = rp.y + r.y / static_cast<float>(lv.H);
+      r.x = rp.x + __fdividef(r.x, static_cast<float>(lv.W));
+      r.y = rp.y + __fdividef(r.y, static_cast<float>(lv.H));
     }
-    r.w = expf(r.w - mx) * inv;
+    r.w = __expf(r.w - mx) * inv;
   }
 };
 
