@@ -59,6 +59,7 @@ WORKLOADS = {
                         Q=None, P=4, levels=R50_LEVELS, kind='encoder'),
 }
 M_HEADS, D_HEAD = 8, 32
+MODEL_WORKLOADS = ('pavenet_step',)
 
 
 # ---------------------------------------------------------------------------
@@ -301,6 +302,63 @@ def run_reference_arm(args, world, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_model_step(args, world, rank, local):
+    """BASELINE config 4: clip-sharded PAVE-Net R-50 training step (1 clip per
+    GPU as in the reference, configs/_base_/datasets/posetrack17_video_keypoint.py:88),
+    NCCL gradient all-reduce through DDP.  Metric: clips/s."""
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from pavenet_b200 import _capi, clip_model, clip_sharding
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    torch.manual_seed(0)
+    vdt = None if args.value_dtype == 'f32' else torch.bfloat16
+    model = clip_model.PaveNetR50(value_dtype=vdt).to(device).train()
+    ddp = DDP(model, device_ids=[local], broadcast_buffers=False) if world > 1 else None
+    opt = clip_model.build_optimizer(model)
+    clips_per_gpu = 1
+    batches = [clip_model.synthetic_clip_batch(clips_per_gpu, device, seed=100 * rank + i)
+               for i in range(2)]
+    for i in range(args.warmup):
+        clip_model.train_step(model, opt, *batches[i % 2], ddp_model=ddp)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = _capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = clip_model.train_step(model, opt, *batches[i % 2], ddp_model=ddp)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clock_info = clocks.stop()
+    ms = clip_sharding.max_over_ranks(e0.elapsed_time(e1), device)
+    clips = clip_sharding.sum_over_ranks(clips_per_gpu * args.steps, device)
+    if rank == 0:
+        n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
+        print(json.dumps({
+            'metric': 'PAVE-Net R-50 training clips/s', 'value': clips / (ms * 1e-3), 'unit': 'clips/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 (TF32 convolutions, fp32 GEMMs)' + ('' if vdt is None else ', bf16 value storage'),
+            'data': 'synthetic',
+            'config': {'workload': 'pavenet_step', 'description': 'PAVE-Net R-50, T=3 frames at 800x1333, '
+                       '1 clip per GPU, forward + backward + DDP all-reduce + grad-clip + AdamW',
+                       'trainable_params': n_params, 'parallelism': 'clip-sharded DDP x%d' % world,
+                       'l2_policy': 'inputs larger than L2 (activations of a 3x800x1333 clip)'},
+            'roofline': None, 'cpu_baseline': None, 'e2e': None,
+            'clocks': clock_info, 'gpu_launches': int(_capi.launch_count() - launches0),
+            'final_loss': float(loss)}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def load_peak():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
@@ -327,7 +385,8 @@ def main():
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='encoder_cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='encoder_cfg2',
+                    choices=sorted(WORKLOADS) + list(MODEL_WORKLOADS))
     ap.add_argument('--value-dtype', default='f32', choices=['f32', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -338,6 +397,15 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     world, rank, local = dist_setup(args.gpus)
+    if args.workload in MODEL_WORKLOADS:
+        if args.impl == 'reference':
+            if rank == 0:
+                print(json.dumps({'impl': 'reference', 'unavailable':
+                                  'the reference model cannot be imported here (mmcv/mmdet/opera '
+                                  'dependencies absent); only the op has a CPU reference arm'}))
+            return
+        run_model_step(args, world, rank, local)
+        return
     if args.impl == 'reference':
         run_reference_arm(args, world, rank)
         return

@@ -1,0 +1,432 @@
+"""A self-contained restatement of the PAVE-Net R-50 clip training step
+ around the B200 attention modules.
+
+Purpose: measure clips/s of a clip-sharded training step at 1/2/4/8 GPUs
+(BASELINE.json config 4).  The reference model cannot be imported in this
+environment (mmcv / mmdet / opera dependencies are absent, SURVEY.md
+section 8c), so this is a from-scratch model that follows the reference's
+graph — tensor shapes, layer counts and op sequence — for the canonical T=3
+configuration `configs/videopose/2025-2-13/2025_2_13_res50_num_frames_3_posetrack17.py:8-153`:
+
+  backbone   ResNet-50, frames folded into the batch, stage 1 + all BN frozen
+             (mmdet/models/backbones/resnet.py:632-653)
+  neck       ChannelMapper: 1x1 conv + GN(32) on C3..C5, 3x3/2 conv + GN for the 4th level
+             (mmdet/models/necks/channel_mapper.py:53-79)
+  encoder    6 x [MultiScaleDeformableAttention, LN, FFN(1024), LN] over all
+             T frames (opera/models/utils/transformer.py:21279-21330)
+  two-stage  proposals from the current frame's memory, top-300 (transformer.py:21340-21403)
+  pose dec.  3 x [MHA, LN, MulFramesMultiScaleDeformablePoseAttentionNumFrames3, LN, FFN, LN]
+             with per-frame keypoint refinement, references NOT detached
+             (transformer.py:6711-6746)
+  losses     Hungarian matching (focal + L1 + OKS cost), focal cls loss,
+             RLE keypoint loss with a RealNVP prior
+             (opera/models/dense_heads/videopose_head_mul_frames.py:795-1010; losses/oks_loss.py:162-195)
+  joint dec. 2 x [MHA over the K keypoint queries, LN,
+             MulFramesMultiScaleDeformableAttentionNumFrames3, LN, FFN, LN] per matched person
+             (videopose_head_mul_frames.py:569-742; transformer.py:21458-21536;
+             mmdet/models/utils/transformer.py:843-886)
+  optimizer  AdamW lr 2e-5, wd 1e-4, 0.1x lr for backbone / sampling_offsets, grad-clip 0.1
+
+Parity status of THIS file: unpinned (nothing to run it against here); the
+attention modules inside it are the pinned ones.  It is a throughput vehicle,
+not a re-implementation of the reference's training recipe.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .modules import (MulFramesMultiScaleDeformableAttentionNumFrames3,
+                      MulFramesMultiScaleDeformablePoseAttentionNumFrames3,
+                      MultiScaleDeformableAttention)
+
+POSETRACK_SIGMAS = torch.tensor([.26, .79, .79, .72, .62, .79, .72, .62, 1.07, .87, .89, 1.07, .87,
+                                 .89, .25][:15]) / 10.0  # nose, head, neck(ish), shoulders ... ankles
+
+
+def inverse_sigmoid(x, eps=1e-5):
+    x = x.clamp(0, 1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+def reduce_mean(t):
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = t.clone()
+        dist.all_reduce(t.div_(dist.get_world_size()))
+    return t
+
+
+class SinePositionalEncoding(nn.Module):
+    """mmcv SinePositionalEncoding(num_feats=128, normalize=True, offset=-0.5)."""
+
+    def __init__(self, num_feats=128, temperature=10000, scale=2 * math.pi, offset=-0.5):
+        super().__init__()
+        self.num_feats, self.temperature, self.scale, self.offset = num_feats, temperature, scale, offset
+
+    def forward(self, mask):                      # (N, H, W) bool, True = padding
+        not_mask = (~mask).float()
+        y = not_mask.cumsum(1)
+        x = not_mask.cumsum(2)
+        y = (y + self.offset) / (y[:, -1:, :] + 1e-6) * self.scale
+        x = (x + self.offset) / (x[:, :, -1:] + 1e-6) * self.scale
+        dim_t = torch.arange(self.num_feats, dtype=torch.float32, device=mask.device)
+        dim_t = self.temperature ** (2 * (dim_t // 2) / self.num_feats)
+        px, py = x[..., None] / dim_t, y[..., None] / dim_t
+        px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), 4).flatten(3)
+        py = torch.stack((py[..., 0::2].sin(), py[..., 1::2].cos()), 4).flatten(3)
+        return torch.cat((py, px), 3).permute(0, 3, 1, 2)
+
+
+class FFN(nn.Module):
+    def __init__(self, dims=256, hidden=1024, drop=0.1):
+        super().__init__()
+        self.fc1, self.fc2, self.drop = nn.Linear(dims, hidden), nn.Linear(hidden, dims), nn.Dropout(drop)
+
+    def forward(self, x):
+        return x + self.drop(self.fc2(self.drop(F.relu(self.fc1(x)))))
+
+
+class SelfAttention(nn.Module):
+    """mmcv MultiheadAttention wrapper: q = k = x + pos, v = x, residual + dropout."""
+
+    def __init__(self, dims=256, heads=8, drop=0.1):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(dims, heads, dropout=drop)
+        self.drop = nn.Dropout(drop)
+
+    def forward(self, x, pos):
+        q = x + pos
+        return x + self.drop(self.attn(q, q, x, need_weights=False)[0])
+
+
+class EncoderLayer(nn.Module):
+    def __init__(self, value_dtype):
+        super().__init__()
+        self.attn = MultiScaleDeformableAttention(embed_dims=256, value_dtype=value_dtype)
+        self.norm1, self.ffn, self.norm2 = nn.LayerNorm(256), FFN(), nn.LayerNorm(256)
+
+    def forward(self, x, pos, mask, ref, shapes, lsi):
+        x = self.norm1(self.attn(x, query_pos=pos, key_padding_mask=mask, reference_points=ref,
+                                 spatial_shapes=shapes, level_start_index=lsi))
+        return self.norm2(self.ffn(x))
+
+
+class DecoderLayer(nn.Module):
+    def __init__(self, cross):
+        super().__init__()
+        self.self_attn, self.cross = SelfAttention(), cross
+        self.norm1, self.norm2, self.ffn, self.norm3 = (nn.LayerNorm(256), nn.LayerNorm(256), FFN(),
+                                                        nn.LayerNorm(256))
+
+    def forward(self, x, pos, **cross_kw):
+        x = self.norm1(self.self_attn(x, pos))
+        x = self.norm2(self.cross(x, None, query_pos=pos, **cross_kw))
+        return self.norm3(self.ffn(x))
+
+
+def mlp(inp, hidden, out, n_hidden=2):
+    layers, d = [], inp
+    for _ in range(n_hidden):
+        layers += [nn.Linear(d, hidden), nn.ReLU()]
+        d = hidden
+    return nn.Sequential(*layers, nn.Linear(d, out))
+
+
+class RealNVP(nn.Module):
+    """2-D flow prior of the RLE loss (3 coupling pairs, 64 hidden units)."""
+
+    def __init__(self, n=6, hidden=64):
+        super().__init__()
+        self.register_buffer('masks', torch.tensor([[0., 1.], [1., 0.]] * (n // 2)))
+        self.s = nn.ModuleList(nn.Sequential(nn.Linear(2, hidden), nn.LeakyReLU(), nn.Linear(hidden, hidden),
+                                             nn.LeakyReLU(), nn.Linear(hidden, 2), nn.Tanh()) for _ in range(n))
+        self.t = nn.ModuleList(nn.Sequential(nn.Linear(2, hidden), nn.LeakyReLU(), nn.Linear(hidden, hidden),
+                                             nn.LeakyReLU(), nn.Linear(hidden, 2)) for _ in range(n))
+
+    def log_prob(self, x):
+        log_det, z = x.new_zeros(x.shape[0]), x
+        for i in reversed(range(len(self.s))):
+            m = self.masks[i]
+            z_ = m * z
+            s, t = self.s[i](z_) * (1 - m), self.t[i](z_) * (1 - m)
+            z = (1 - m) * (z - t) * torch.exp(-s) + z_
+            log_det = log_det - s.sum(1)
+        return -0.5 * (z ** 2).sum(1) - math.log(2 * math.pi) + log_det
+
+
+class PaveNetR50(nn.Module):
+    def __init__(self, num_frames=3, num_keypoints=15, num_query=300, value_dtype=None):
+        super().__init__()
+        import torchvision
+        if num_frames != 3:
+            raise ValueError('this restatement covers the canonical T=3 configuration')
+        self.T, self.K, self.Qn = num_frames, num_keypoints, num_query
+        r = torchvision.models.resnet50(weights=None)
+        self.stem = nn.Sequential(r.conv1, r.bn1, r.relu, r.maxpool)
+        self.layer1, self.layer2, self.layer3, self.layer4 = r.layer1, r.layer2, r.layer3, r.layer4
+        for m in self.modules():                      # norm_eval=True, BN requires_grad=False
+            if isinstance(m, nn.BatchNorm2d):
+                for p in m.parameters():
+                    p.requires_grad_(False)
+        for p in list(self.stem.parameters()) + list(self.layer1.parameters()):   # frozen_stages=1
+            p.requires_grad_(False)
+        self.lateral = nn.ModuleList(nn.Sequential(nn.Conv2d(c, 256, 1), nn.GroupNorm(32, 256))
+                                     for c in (512, 1024, 2048))
+        self.extra = nn.Sequential(nn.Conv2d(2048, 256, 3, stride=2, padding=1), nn.GroupNorm(32, 256))
+        self.pos_enc = SinePositionalEncoding()
+        self.level_embeds = nn.Parameter(torch.randn(4, 256))
+        self.encoder = nn.ModuleList(EncoderLayer(value_dtype) for _ in range(6))
+        self.enc_output, self.enc_output_norm = nn.Linear(256, 256), nn.LayerNorm(256)
+        K = num_keypoints
+        self.decoder = nn.ModuleList(
+            DecoderLayer(MulFramesMultiScaleDeformablePoseAttentionNumFrames3(
+                num_points=K, embed_dims=256, value_dtype=value_dtype)) for _ in range(3))
+        self.refine_decoder = nn.ModuleList(
+            DecoderLayer(MulFramesMultiScaleDeformableAttentionNumFrames3(
+                embed_dims=256, im2col_step=128, value_dtype=value_dtype)) for _ in range(2))
+        self.query_embedding = nn.Embedding(num_query, 512)
+        self.refine_query_embedding = nn.Embedding(K, 512)
+        self.cls_branches = nn.ModuleList(nn.Linear(256, 1) for _ in range(4))
+        self.kpt_branches = nn.ModuleList(mlp(256, 512, 2 * K) for _ in range(4))
+        self.pre_kpt_branches = nn.ModuleList(mlp(256, 512, 2 * K) for _ in range(3))
+        self.next_kpt_branches = nn.ModuleList(mlp(256, 512, 2 * K) for _ in range(3))
+        self.sigma_branches = nn.ModuleList(mlp(256, 256, 2 * K, n_hidden=1) for _ in range(4))
+        self.refine_kpt = nn.ModuleList(nn.ModuleList(mlp(256, 256, 2) for _ in range(2)) for _ in range(3))
+        self.refine_sigma = nn.ModuleList(mlp(256, 256, 2, n_hidden=1) for _ in range(2))
+        self.flow = RealNVP()
+        nn.init.constant_(self.cls_branches[0].bias, -4.6)
+
+    def train(self, mode=True):
+        super().train(mode)
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+        self.stem.eval()
+        self.layer1.eval()
+        return self
+
+    # ------------------------------------------------------------------ graph
+    def extract_feat(self, images):                   # (Bc, T, 3, H, W) -> 4 levels of (Bc*T, 256, h, w)
+        x = images.flatten(0, 1).contiguous(memory_format=torch.channels_last)
+        with torch.no_grad():
+            x = self.layer1(self.stem(x))
+        c3 = self.layer2(x)
+        c4 = self.layer3(c3)
+        c5 = self.layer4(c4)
+        return [l(c) for l, c in zip(self.lateral, (c3, c4, c5))] + [self.extra(c5)]
+
+    @staticmethod
+    def reference_grid(shapes_list, device):
+        pts = []
+        for h, w in shapes_list:
+            ys = (torch.arange(h, device=device, dtype=torch.float32) + 0.5) / h
+            xs = (torch.arange(w, device=device, dtype=torch.float32) + 0.5) / w
+            yy, xx = torch.meshgrid(ys, xs, indexing='ij')
+            pts.append(torch.stack([xx.reshape(-1), yy.reshape(-1)], -1))
+        return torch.cat(pts)                          # (S, 2)
+
+    def forward_train(self, images, gt_kpts, gt_areas):
+        """images (Bc, T, 3, H, W); gt_kpts: per clip (G_i, T, K, 3) normalised x, y, visibility;
+        gt_areas: per clip (G_i,) normalised box areas.  Returns a dict of losses."""
+        T, K, Bc = self.T, self.K, images.shape[0]
+        H, W = images.shape[-2:]
+        feats = self.extract_feat(images)
+        dev = images.device
+        shapes_list = [tuple(f.shape[-2:]) for f in feats]
+        shapes = torch.tensor(shapes_list, device=dev)
+        lsi = torch.cat([shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]])
+        masks = [torch.zeros((Bc * T, h, w), dtype=torch.bool, device=dev) for h, w in shapes_list]
+        pos = torch.cat([(self.pos_enc(m) + self.level_embeds[i].view(1, -1, 1, 1)).flatten(2)
+                         for i, m in enumerate(masks)], 2).permute(2, 0, 1)           # (S, Bc*T, 256)
+        x = torch.cat([f.flatten(2) for f in feats], 2).permute(2, 0, 1)               # (S, Bc*T, 256)
+        mask_flat = torch.cat([m.flatten(1) for m in masks], 1)                        # (Bc*T, S)
+        S = x.shape[0]
+        grid = self.reference_grid(shapes_list, dev)
+        ref_enc = grid[None, :, None, :].expand(Bc * T, S, 4, 2).contiguous()          # valid_ratios == 1
+        for layer in self.encoder:
+            x = layer(x, pos, mask_flat, ref_enc, shapes, lsi)
+        memory = x                                                                      # (S, Bc*T, 256)
+
+        # two-stage proposals from the current frame
+        now = memory[:, T // 2::T].permute(1, 0, 2)                                    # (Bc, S, 256)
+        out_mem = self.enc_output_norm(self.enc_output(now))
+        proposals = inverse_sigmoid(grid)[None].expand(Bc, S, 2)
+        enc_cls = self.cls_branches[3](out_mem)
+        enc_kpt = self.kpt_branches[3](out_mem).view(Bc, S, K, 2) + proposals[:, :, None, :]
+        enc_kpt = enc_kpt.flatten(2)
+        enc_sigma = self.sigma_branches[3](out_mem).sigmoid()
+        topk = enc_cls[..., 0].topk(self.Qn, dim=1)[1]
+        ref = torch.gather(enc_kpt, 1, topk[..., None].expand(-1, -1, 2 * K)).detach().sigmoid()
+        tgt = torch.gather(out_mem, 1, topk[..., None].expand(-1, -1, 256)).detach()
+        ref = ref.repeat(1, T, 1)                                                       # (Bc, T*Q, 2K)
+        q_pos, q = self.query_embedding.weight.split(256, 1)
+        query = (tgt + q[None]).permute(1, 0, 2)                                        # (Q, Bc, 256)
+        q_pos = q_pos[None].expand(Bc, -1, -1).permute(1, 0, 2)
+
+        # pose decoder
+        cls_out, kpt_out, sigma_out = [], [], []
+        for lid, layer in enumerate(self.decoder):
+            ref_in = ref[:, :, None, :].expand(-1, -1, 4, -1)                           # (Bc, T*Q, L, 2K)
+            query = layer(query, q_pos, value=memory, key_padding_mask=mask_flat, reference_points=ref_in,
+                          spatial_shapes=shapes, level_start_index=lsi)
+            o = query.permute(1, 0, 2)
+            deltas = torch.cat([self.pre_kpt_branches[lid](o), self.kpt_branches[lid](o),
+                                self.next_kpt_branches[lid](o)], 1)
+            ref = (deltas + inverse_sigmoid(ref)).sigmoid()                             # not detached
+            cls_out.append(self.cls_branches[lid](o))
+            kpt_out.append(ref.view(Bc, T, self.Qn, 2 * K))
+            sigma_out.append(self.sigma_branches[lid](o).sigmoid())
+
+        losses = {}
+        wh = images.new_tensor([W, H])
+        last_match = None
+        stages = [(enc_cls, enc_kpt.sigmoid()[:, None].expand(-1, T, -1, -1), enc_sigma, 'enc')] + \
+                 [(c, k, s, 'd%d' % i) for i, (c, k, s) in enumerate(zip(cls_out, kpt_out, sigma_out))]
+        for cls, kpt, sigma, tag in stages:
+            l_cls, l_kpt, match = self.stage_loss(cls, kpt, sigma, gt_kpts, gt_areas, wh)
+            losses[tag + '.loss_cls'], losses[tag + '.loss_kpt'] = l_cls, l_kpt
+            last_match = match
+        losses.update(self.refine(memory, mask_flat, shapes, lsi, kpt_out[-1], last_match, gt_kpts))
+        return losses
+
+    # ------------------------------------------------------------------ losses
+    def rle(self, pred, sigma, target, weight, num_valid):
+        """pred/sigma/target/weight (N, K, 2)."""
+        bar_mu = (pred - target) / sigma
+        log_phi = self.flow.log_prob(bar_mu.reshape(-1, 2)).reshape(pred.shape[0], -1, 1)
+        nf = (torch.log(sigma) - log_phi) * weight[:, :, :1]
+        amp = 1 / math.sqrt(2 * math.pi)
+        logq = (torch.log(sigma / amp) + (target - pred).abs() / (math.sqrt(2) * sigma + 1e-9)) * weight
+        return (nf + logq).sum() / num_valid
+
+    @torch.no_grad()
+    def match(self, cls, kpt_now, gts, areas, wh):
+        """Hungarian assignment of one clip (cost: 2*focal + 70*L1 + 7*(1-OKS))."""
+        from scipy.optimize import linear_sum_assignment
+        G = gts.shape[0]
+        if G == 0:
+            return kpt_now.new_zeros(0, dtype=torch.long), kpt_now.new_zeros(0, dtype=torch.long)
+        p = cls.sigmoid()[:, 0]
+        cost_cls = (0.25 * (1 - p) ** 2 * -(p + 1e-12).log() - 0.75 * p ** 2 * -(1 - p + 1e-12).log())
+        pred = kpt_now.view(-1, 1, self.K, 2)
+        tgt, vis = gts[None, :, :, :2], (gts[None, :, :, 2] > 0).float()
+        l1 = ((pred - tgt).abs().sum(-1) * vis).sum(-1) / vis.sum(-1).clamp(min=1)
+        d2 = (((pred - tgt) * wh) ** 2).sum(-1)
+        var = (2 * POSETRACK_SIGMAS.to(pred.device)) ** 2
+        oks = (torch.exp(-d2 / (2 * (areas[None, :, None] * wh.prod()).clamp(min=1) * var)) * vis).sum(-1)
+        oks = oks / vis.sum(-1).clamp(min=1)
+        cost = 2.0 * cost_cls[:, None] + 70.0 * l1 + 7.0 * (1 - oks)
+        rows, cols = linear_sum_assignment(cost.cpu().numpy())
+        return (torch.as_tensor(rows, device=pred.device, dtype=torch.long),
+                torch.as_tensor(cols, device=pred.device, dtype=torch.long))
+
+    def stage_loss(self, cls, kpt, sigma, gt_kpts, gt_areas, wh):
+        """cls (Bc, N, 1); kpt (Bc, T, N, 2K); sigma (Bc, N, 2K)."""
+        Bc, K = cls.shape[0], self.K
+        now = self.T // 2
+        labels = torch.zeros_like(cls)
+        preds, sigmas, tgts, wts, matches = [], [], [], [], []
+        for b in range(Bc):
+            rows, cols = self.match(cls[b], kpt[b, now], gt_kpts[b][:, now], gt_areas[b], wh)
+            matches.append((rows, cols))
+            labels[b, rows] = 1.0
+            preds.append(kpt[b, now, rows].view(-1, K, 2))
+            sigmas.append(sigma[b, rows].view(-1, K, 2))
+            tgts.append(gt_kpts[b][cols, now, :, :2])
+            wts.append((gt_kpts[b][cols, now, :, 2:] > 0).float().expand(-1, -1, 2))
+        n_pos = reduce_mean(cls.new_tensor([float(sum(len(r) for r, _ in matches))])).clamp(min=1).item()
+        p = cls.sigmoid()
+        focal = F.binary_cross_entropy_with_logits(cls, labels, reduction='none') * \
+            (labels * 0.25 * (1 - p) ** 2 + (1 - labels) * 0.75 * p ** 2)
+        l_cls = 0.5 * focal.sum() / n_pos
+        pred, sig, tgt, wt = (torch.cat(t) for t in (preds, sigmas, tgts, wts))
+        n_valid = reduce_mean(wt.sum().detach()[None]).clamp(min=1).item()
+        l_kpt = self.rle(pred, sig, tgt, wt, n_valid) if pred.shape[0] else pred.sum() * 0
+        return l_cls, l_kpt, matches
+
+    def refine(self, memory, mask_flat, shapes, lsi, kpt_last, matches, gt_kpts):
+        """Joint decoder over the matched persons: K keypoint queries per person."""
+        T, K = self.T, self.K
+        S = memory.shape[0]
+        poses, img_inds, tgts, wts = [], [], [], []
+        for b, (rows, cols) in enumerate(matches):
+            poses.append(kpt_last[b][:, rows])                                          # (T, g, 2K)
+            img_inds.append(rows.new_full(rows.shape, b))
+            tgts.append(gt_kpts[b][cols, T // 2, :, :2])
+            wts.append((gt_kpts[b][cols, T // 2, :, 2:] > 0).float().expand(-1, -1, 2))
+        poses, img_inds = torch.cat(poses, 1), torch.cat(img_inds)
+        G = img_inds.shape[0]
+        if G == 0:
+            zero = sum(p.sum() for p in self.refine_decoder.parameters()) * 0 + \
+                sum(p.sum() for p in self.refine_kpt.parameters()) * 0 + \
+                sum(p.sum() for p in self.refine_sigma.parameters()) * 0 + \
+                self.refine_query_embedding.weight.sum() * 0
+            return {'d0.loss_kpt_refine': zero, 'd1.loss_kpt_refine': zero}
+        ref = poses.detach().reshape(T * G, K, 2)                                       # frame-major (T*G, K, 2)
+        q_pos, q = self.refine_query_embedding.weight.split(256, 1)
+        query = q[None].expand(G, -1, -1).permute(1, 0, 2)                              # (K, G, 256)
+        q_pos = q_pos[None].expand(G, -1, -1).permute(1, 0, 2)
+        mem = memory.view(S, -1, T, 256)[:, img_inds]                                   # (S, G, T, 256)
+        mask = mask_flat.view(-1, T, S)[img_inds]                                       # (G, T, S)
+        tgt, wt = torch.cat(tgts), torch.cat(wts)
+        n_valid = reduce_mean(wt.sum().detach()[None]).clamp(min=1).item()
+        losses = {}
+        for lid, layer in enumerate(self.refine_decoder):
+            ref_in = ref[:, :, None, :].expand(-1, -1, 4, -1)                           # (T*G, K, L, 2)
+            query = layer(query, q_pos, value=mem, key_padding_mask=mask, reference_points=ref_in,
+                          spatial_shapes=shapes, level_start_index=lsi)
+            o = query.permute(1, 0, 2)                                                  # (G, K, 256)
+            deltas = torch.cat([self.refine_kpt[t][lid](o) for t in range(T)], 0)       # (T*G, K, 2)
+            new_ref = (deltas + inverse_sigmoid(ref)).sigmoid()
+            sigma = self.refine_sigma[lid](o).sigmoid()
+            losses['d%d.loss_kpt_refine' % lid] = self.rle(new_ref[G:2 * G], sigma, tgt, wt, n_valid)
+            ref = new_ref
+        return losses
+
+
+def build_optimizer(model):
+    """AdamW 2e-5 / wd 1e-4 with 0.1x lr on backbone and sampling_offsets
+    (config lines 140-150)."""
+    slow, fast = [], []
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        backbone = name.startswith(('stem', 'layer1', 'layer2', 'layer3', 'layer4'))
+        (slow if backbone or 'sampling_offsets' in name else fast).append(p)
+    return torch.optim.AdamW([{'params': fast, 'lr': 2e-5}, {'params': slow, 'lr': 2e-6}],
+                             weight_decay=1e-4)
+
+
+def synthetic_clip_batch(clips, device, seed, height=800, width=1333, num_frames=3, num_keypoints=15):
+    """PoseTrack-shaped synthetic input: images ~N(0,1); per clip 1-10 persons with
+    K keypoints uniform in a random box, small drift between frames."""
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    images = torch.randn(clips, num_frames, 3, height, width, generator=g)
+    kpts, areas = [], []
+    for _ in range(clips):
+        n = int(torch.randint(1, 11, (1,), generator=g))
+        centre = torch.rand(n, 1, 1, 2, generator=g) * 0.6 + 0.2
+        size = torch.rand(n, 1, 1, 2, generator=g) * 0.3 + 0.1
+        xy = centre + (torch.rand(n, 1, num_keypoints, 2, generator=g) - 0.5) * size
+        xy = (xy + torch.randn(n, num_frames, 1, 2, generator=g) * 0.01).clamp(0.01, 0.99)
+        vis = (torch.rand(n, num_frames, num_keypoints, 1, generator=g) > 0.15).float() * 2
+        kpts.append(torch.cat([xy, vis], -1).to(device))
+        areas.append((size[:, 0, 0, 0] * size[:, 0, 0, 1]).to(device))
+    return images.to(device), kpts, areas
+
+
+def train_step(model, optimizer, images, gt_kpts, gt_areas, ddp_model=None):
+    """forward + backward (+ DDP gradient all-reduce) + grad-clip 0.1 + AdamW step."""
+    net = ddp_model if ddp_model is not None else model
+    losses = net(images, gt_kpts, gt_areas)
+    loss = sum(losses.values())
+    optimizer.zero_grad(set_to_none=True)
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.requires_grad], 0.1)
+    optimizer.step()
+    return loss.detach()
+
+
+PaveNetR50.forward = PaveNetR50.forward_train

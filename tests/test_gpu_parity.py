@@ -613,6 +613,27 @@ def test_modules_fused_prologue_equals_op_by_op(case):
         assert rel_err(g_f[name], g_u[name]) < 2e-4, name
 
 
+def test_clip_model_training_step_small():
+    """The PAVE-Net R-50 restatement (config 4 vehicle) at a small resolution:
+    finite losses, every trainable parameter receives a gradient (a DDP
+    requirement), and a step changes the weights."""
+    from pavenet_b200 import clip_model
+    torch.manual_seed(0)
+    model = clip_model.PaveNetR50(num_query=50).cuda().train()
+    opt = clip_model.build_optimizer(model)
+    images, kpts, areas = clip_model.synthetic_clip_batch(2, 'cuda', seed=3, height=256, width=352)
+    losses = model(images, kpts, areas)
+    assert set(losses) >= {'enc.loss_cls', 'd2.loss_kpt', 'd1.loss_kpt_refine'}
+    total = sum(losses.values())
+    assert torch.isfinite(total)
+    total.backward()
+    missing = [n for n, p in model.named_parameters() if p.requires_grad and p.grad is None]
+    assert not missing, missing
+    before = model.encoder[0].attn.value_proj.weight.detach().clone()
+    clip_model.train_step(model, opt, images, kpts, areas)
+    assert not torch.equal(before, model.encoder[0].attn.value_proj.weight)
+
+
 @pytest.mark.parametrize('pinned', [True, False])
 def test_host_buffer_entry_points(pinned):
     """msda_forward_host / msda_forward_backward_host (pipelined over batch
