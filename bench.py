@@ -256,6 +256,10 @@ def measure_cpu_baseline(wl, budget_s=20.0):
 
 # ---------------------------------------------------------------------------
 def dist_setup(gpus):
+    # NCCL announces its version on STDOUT at NCCL_DEBUG=VERSION, which would precede the
+    # one JSON line this script owes its caller
+    if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+        os.environ['NCCL_DEBUG'] = 'WARN'
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
