@@ -153,6 +153,22 @@ int msda_fused_backward(const void *d_value, const int64_t *d_spatial_shapes,
                         int ref_points_per_level, int value_dtype, void *stream);
 
 /*
+ * The 256 -> 256 projection next to the op (SURVEY.md section 8f rank 2:
+ * `value_proj` + padding mask + storage dtype, multi_scale_deform_attn.py:369-372,
+ * opera/models/utils/transformer.py:1706-1720) on the tcgen05 tensor cores:
+ *   y[rows,256] = x[rows,256] * weight^T + bias      weight (256 out, 256 in), fp32
+ * computed as a 3xTF32 split with fp32 accumulation in tensor memory (fp32-level
+ * accuracy; plain TF32 would not meet the op's parity bound).  mask_mode 0: no
+ * mask; 1: rows with d_row_mask[r] != 0 are written as zeros (mask after the
+ * projection); 2: they are written as the bias (input masked before it).
+ * out_dtype MSDA_F32 or MSDA_BF16.  d_scratch: 2*256*256 floats of device
+ * scratch (the split weight).  d_bias may be NULL.
+ */
+int msda_linear256(const float *d_x, const float *d_weight, const float *d_bias,
+                   const uint8_t *d_row_mask, int mask_mode, void *d_y, int rows,
+                   int out_dtype, float *d_scratch, void *stream);
+
+/*
  * Host-buffer convenience entry points (what a cgo / JNI / ctypes caller
  * without its own device memory management binds).  All pointers are HOST
  * pointers (pinned memory gives asynchronous copies; pageable memory works

@@ -16,7 +16,8 @@ not on a CUDA device.
 """
 from . import _capi
 from .functional import (FusedMultiScaleDeformableAttnFunction, HostWorkspace,
-                         MultiScaleDeformableAttnFunction, ext_module, fused_supported,
+                         Linear256Function, MultiScaleDeformableAttnFunction, ext_module,
+                         fused_supported, linear256, linear256_supported,
                          fuse_frames_as_levels, ms_deform_attn_backward,
                          ms_deform_attn_forward)
 from .modules import (MulFramesMultiScaleDeformableAttentionNumFrames3,
@@ -32,7 +33,8 @@ __version__ = '0.1.0'
 __all__ = [
     'MultiScaleDeformableAttnFunction', 'ext_module', 'ms_deform_attn_forward',
     'ms_deform_attn_backward', 'fuse_frames_as_levels', 'HostWorkspace',
-    'FusedMultiScaleDeformableAttnFunction', 'fused_supported',
+    'FusedMultiScaleDeformableAttnFunction', 'fused_supported', 'Linear256Function',
+    'linear256', 'linear256_supported',
     'MultiScaleDeformableAttention', 'MultiScaleDeformablePoseAttention',
     'MulFramesMultiScaleDeformablePoseAttentionNumFrames3',
     'MulFramesMultiScaleDeformablePoseAttentionNumFrames5',

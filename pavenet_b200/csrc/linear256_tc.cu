@@ -1,0 +1,326 @@
+// linear256_tc.cu — the 256 -> 256 projections around the sampling op
+// (value_proj, and the input-gradient of any such Linear) on Blackwell's 5th
+// generation tensor cores, with fp32-level accuracy.
+//
+//   Y[rows, 256] = X[rows, 256] * W^T + bias        W is (out=256, in=256), row-major
+//
+// after the sampling kernels, these fp32 GEMMs
+// are the largest cost of an attention-module call (cuBLAS runs them as SIMT
+// sgemm because PyTorch keeps TF32 off by default, and so does the reference).
+// Plain TF32 would break the 1e-4 parity contract, so the product is computed
+// as a 3xTF32 split:  x = x_hi + x_lo, w = w_hi + w_lo (hi = top 19 bits),
+//   x*w ~= x_hi*w_hi + x_hi*w_lo + x_lo*w_hi        (error ~2^-21 per product)
+// accumulated in fp32 in tensor memory.
+//
+// Structure (one CTA = one 128-row tile, 128 threads, 1 CTA / SM):
+//   TMA (cp.async.bulk.tensor, SWIZZLE_128B) streams X and the pre-split W in
+//   8 K-chunks of 32 floats through a 2-stage shared-memory ring; the threads
+//   split the X chunk into hi / lo in place; one thread issues
+//   tcgen05.mma.kind::tf32 (M=128, N=256, K=8) x 3 per K-step into a 128x256 fp32
+//   accumulator in TMEM; tcgen05.commit -> mbarrier releases the stage; the
+//   epilogue reads TMEM with tcgen05.ld, adds bias, applies the padding mask
+//   and stores fp32 or bf16 rows — the (B, S, M, D) layout the sampling kernels
+//   read, so no further pass touches the projected value.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "msda_kernels.h"
+
+namespace msda {
+namespace {
+
+constexpr int kDim = 256;          // in == out features
+constexpr int kBM = 128;           // rows per CTA
+constexpr int kBK = 32;            // floats per K chunk = one 128-byte swizzle span
+constexpr int kChunks = kDim / kBK;
+constexpr int kStages = 2;
+constexpr int kUmmaK = 8;          // tf32 MMA K
+constexpr uint32_t kABytes = kBM * kBK * 4;     // 16 KiB
+constexpr uint32_t kBBytes = kDim * kBK * 4;    // 32 KiB
+constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // A_hi, A_lo, B_hi, B_lo
+constexpr uint32_t kTxBytes = kABytes + 2 * kBBytes;          // what TMA delivers per stage
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int kTmemCols = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+// K-major, SWIZZLE_128B operand: 8-row atoms of 1024 bytes, stacked densely.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return static_cast<uint64_t>((smem_addr >> 4) & 0x3fff) | (uint64_t(1) << 16) /*LBO (unused)*/ |
+         (uint64_t(1024 >> 4) << 32) /*SBO*/ | (uint64_t(1) << 46) /*sm100 descriptor*/ |
+         (uint64_t(2) << 61) /*SWIZZLE_128B*/;
+}
+// D fp32, A/B tf32, both K-major, N = 256, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kDim >> 3) << 17) | ((kBM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// W -> (W_hi, W_lo), once per call (65 536 elements)
+__global__ void split_weight_kernel(const float* __restrict__ w, float* __restrict__ w_hi,
+                                    float* __restrict__ w_lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kDim * kDim) {
+    const float x = w[i], hi = tf32_hi(x);
+    w_hi[i] = hi;
+    w_lo[i] = x - hi;
+  }
+}
+
+template <typename OT>
+__device__ __forceinline__ void store_chunk(OT* row_ptr, const float (&v)[32]);
+template <>
+__device__ __forceinline__ void store_chunk<float>(float* p, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4)
+    *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+}
+template <>
+__device__ __forceinline__ void store_chunk<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    uint4 u;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(v[j], v[j + 1]);     u.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[j + 2], v[j + 3]); u.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[j + 4], v[j + 5]); u.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[j + 6], v[j + 7]); u.w = *reinterpret_cast<uint32_t*>(&t);
+    *reinterpret_cast<uint4*>(p + j) = u;
+  }
+}
+
+// mask_mode: 0 none; 1 masked rows are written as zeros (mask applied after the
+// projection, multi_scale_deform_attn.py:369-371); 2 masked rows are written as
+// the bias (mask applied to the input before it, transformer.py:1706-1711).
+template <typename OT>
+__global__ void __launch_bounds__(128, 1)
+linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
+                        const __grid_constant__ CUtensorMap map_whi,
+                        const __grid_constant__ CUtensorMap map_wlo, const float* __restrict__ bias,
+                        const uint8_t* __restrict__ row_mask, int mask_mode, OT* __restrict__ y,
+                        int rows) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B wants 1024-byte alignment
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t bars = base + kStages * kStageBytes;    // full[2], mma_done[2], tmem slot
+  const uint32_t full0 = bars, done0 = bars + 16, tmem_slot = bars + 32;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kStages * kStageBytes + 32);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row0 = blockIdx.x * kBM;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(done0 + 8 * s, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_whi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wlo) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  auto stage_addr = [&](int s) { return base + s * kStageBytes; };
+  auto issue_loads = [&](int chunk, int s) {
+    const uint32_t bar = full0 + 8 * s, a = stage_addr(s);
+    mbar_expect_tx(bar, kTxBytes);
+    tma_load_2d(a, &map_x, bar, chunk * kBK, row0);                        // A (hi, split in place)
+    tma_load_2d(a + 2 * kABytes, &map_whi, bar, chunk * kBK, 0);           // B_hi
+    tma_load_2d(a + 2 * kABytes + kBBytes, &map_wlo, bar, chunk * kBK, 0); // B_lo
+  };
+  if (tid == 0) {
+    issue_loads(0, 0);
+    issue_loads(1, 1);
+  }
+
+  for (int kc = 0; kc < kChunks; ++kc) {
+    const int s = kc & 1;
+    const uint32_t parity = (kc >> 1) & 1;
+    mbar_wait(full0 + 8 * s, parity);
+    // split the X chunk: hi stays where TMA put it, lo goes to the twin buffer
+    // (same offsets, so the 128-byte swizzle pattern is preserved)
+    {
+      float4* a_hi = reinterpret_cast<float4*>(base_ptr + s * kStageBytes);
+      float4* a_lo = reinterpret_cast<float4*>(base_ptr + s * kStageBytes + kABytes);
+#pragma unroll
+      for (int i = tid; i < static_cast<int>(kABytes / 16); i += 128) {
+        const float4 x = a_hi[i];
+        const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+        a_hi[i] = h;
+        a_lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core reads
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a = stage_addr(s);
+#pragma unroll
+      for (int k = 0; k < kBK / kUmmaK; ++k) {
+        const uint32_t koff = k * kUmmaK * 4;   // bytes inside the 128-byte span
+        const uint64_t a_hi = umma_desc(a + koff), a_lo = umma_desc(a + kABytes + koff);
+        const uint64_t b_hi = umma_desc(a + 2 * kABytes + koff);
+        const uint64_t b_lo = umma_desc(a + 2 * kABytes + kBBytes + koff);
+        umma_tf32(tmem_d, a_lo, b_hi, (kc | k) != 0);   // small terms first
+        umma_tf32(tmem_d, a_hi, b_lo, 1);
+        umma_tf32(tmem_d, a_hi, b_hi, 1);
+      }
+      umma_commit(done0 + 8 * s);                // arrives when the MMAs above have read the stage
+      if (kc + kStages < kChunks) {
+        mbar_wait(done0 + 8 * s, parity);
+        issue_loads(kc + kStages, s);
+      }
+    }
+  }
+  // the last commit covers every MMA issued before it
+  mbar_wait(done0 + 8 * ((kChunks - 1) & 1), ((kChunks - 1) >> 1) & 1);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // epilogue: warp w owns TMEM lanes 32w .. 32w+31 = rows of the tile
+  const int r = row0 + tid;
+  const bool in_range = r < rows;
+  const bool masked = in_range && row_mask != nullptr && mask_mode != 0 && row_mask[r] != 0;
+  OT* yrow = y + static_cast<int64_t>(in_range ? r : 0) * kDim;
+#pragma unroll 1
+  for (int c0 = 0; c0 < kDim; c0 += 32) {
+    uint32_t u[32];
+    const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + c0;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+        "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]),
+          "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]),
+          "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]),
+          "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float b = bias ? __ldg(bias + c0 + j) : 0.f;
+      float acc = __uint_as_float(u[j]) + b;
+      if (masked) acc = (mask_mode == 1) ? 0.f : b;
+      v[j] = acc;
+    }
+    if (in_range) store_chunk<OT>(yrow + c0, v);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// (rows x 256) fp32 row-major matrix, boxes of 32 floats x box_rows rows, 128-byte swizzle
+bool make_map(CUtensorMap* map, const float* ptr, int rows, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kDim), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kDim) * 4};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+// returns cudaSuccess, cudaErrorNotSupported (no driver entry point), or the launch error
+cudaError_t launch_linear256(const float* x, const float* w, const float* bias,
+                             const uint8_t* row_mask, int mask_mode, void* y, int rows, int out_dtype,
+                             float* scratch, cudaStream_t st) {
+  float* w_hi = scratch;
+  float* w_lo = scratch + kDim * kDim;
+  split_weight_kernel<<<(kDim * kDim + 255) / 256, 256, 0, st>>>(w, w_hi, w_lo);
+  CUtensorMap mx, mhi, mlo;
+  if (!make_map(&mx, x, rows, kBM) || !make_map(&mhi, w_hi, kDim, kDim) ||
+      !make_map(&mlo, w_lo, kDim, kDim))
+    return cudaErrorNotSupported;
+  const unsigned grid = (rows + kBM - 1) / kBM;
+  cudaError_t e;
+  if (out_dtype == MSDA_BF16) {
+    e = cudaFuncSetAttribute(linear256_tf32x3_kernel<__nv_bfloat16>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    linear256_tf32x3_kernel<__nv_bfloat16><<<grid, 128, kSmemBytes, st>>>(
+        mx, mhi, mlo, bias, row_mask, mask_mode, static_cast<__nv_bfloat16*>(y), rows);
+  } else {
+    e = cudaFuncSetAttribute(linear256_tf32x3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kSmemBytes);
+    if (e != cudaSuccess) return e;
+    linear256_tf32x3_kernel<float><<<grid, 128, kSmemBytes, st>>>(mx, mhi, mlo, bias, row_mask, mask_mode,
+                                                                  static_cast<float*>(y), rows);
+  }
+  note_launches(2);
+  return cudaGetLastError();
+}
+
+}  // namespace msda

@@ -278,6 +278,27 @@ int msda_fused_backward(const void* d_value, const int64_t* d_spatial_shapes,
   return MSDA_OK;
 }
 
+int msda_linear256(const float* d_x, const float* d_weight, const float* d_bias,
+                   const uint8_t* d_row_mask, int mask_mode, void* d_y, int rows, int out_dtype,
+                   float* d_scratch, void* stream) {
+  if (!d_x || !d_weight || !d_y || !d_scratch)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256: NULL pointer argument");
+  if (rows <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256: rows must be positive");
+  if (out_dtype != MSDA_F32 && out_dtype != MSDA_BF16)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256: out_dtype must be MSDA_F32 or MSDA_BF16");
+  if (mask_mode < 0 || mask_mode > 2 || (mask_mode != 0 && !d_row_mask))
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256: bad mask_mode / row_mask");
+  if (misaligned16(d_x) || misaligned16(d_weight) || misaligned16(d_y) || misaligned16(d_scratch))
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_linear256 needs 16-byte aligned buffers");
+  const cudaError_t e = launch_linear256(d_x, d_weight, d_bias, d_row_mask, mask_mode, d_y, rows,
+                                         out_dtype, d_scratch, static_cast<cudaStream_t>(stream));
+  if (e == cudaErrorNotSupported)
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_linear256: cuTensorMapEncodeTiled unavailable or failed");
+  if (e != cudaSuccess)
+    return fail(MSDA_ERR_CUDA, "msda_linear256 launch failed: %s", cudaGetErrorString(e));
+  return MSDA_OK;
+}
+
 // ---------------------------------------------------------------------------
 // host-buffer entry points
 //

@@ -40,6 +40,11 @@ cudaError_t launch_backward_fused(const void* value, const int64_t* shapes, cons
                                   float* grad_off, float* grad_logit, float* grad_loc,
                                   const Dims& d, int value_dtype, int sm_count, cudaStream_t st);
 
+// Y = X W^T + bias for 256 -> 256 projections on tcgen05 (3xTF32), linear256_tc.cu
+cudaError_t launch_linear256(const float* x, const float* w, const float* bias,
+                             const uint8_t* row_mask, int mask_mode, void* y, int rows, int out_dtype,
+                             float* scratch, cudaStream_t st);
+
 // number of kernel launches the last launch_* call on this thread enqueued
 int last_launches();
 void note_launches(int n);

@@ -19,6 +19,7 @@ __all__ = [
     'MultiScaleDeformableAttnFunction', 'ext_module', 'ms_deform_attn_forward',
     'ms_deform_attn_backward', 'fuse_frames_as_levels', 'BF16_GRAD_VALUE_ATOMICS',
     'HostWorkspace', 'FusedMultiScaleDeformableAttnFunction', 'fused_supported',
+    'Linear256Function', 'linear256', 'linear256_supported',
 ]
 
 #: When value is stored in bf16, accumulate grad_value in an fp32 scratch
@@ -430,3 +431,87 @@ class FusedMultiScaleDeformableAttnFunction(Function):
         if need_scale:
             grad_scale = (grad_loc * offsets).sum(dim=(2, 4))
         return grad_value, None, None, grad_offsets, grad_logits, grad_ref, grad_scale
+
+
+# ---------------------------------------------------------------------------
+# 256 -> 256 projections on the tcgen05 tensor cores
+# ---------------------------------------------------------------------------
+def linear256_supported(x, weight):
+    """True when `linear256` has a kernel for these tensors: CUDA, fp32,
+    in_features == out_features == 256."""
+    return (x.is_cuda and weight.is_cuda and x.dtype == torch.float32
+            and weight.dtype == torch.float32 and tuple(weight.shape) == (256, 256)
+            and x.shape[-1] == 256 and x.numel() > 0)
+
+
+def _linear256_raw(x2d, weight, bias, row_mask, mask_mode, out_dtype):
+    lib = _capi.load()
+    rows = x2d.shape[0]
+    with torch.cuda.device(x2d.device):
+        y = torch.empty((rows, 256), dtype=out_dtype, device=x2d.device)
+        scratch = torch.empty(2 * 256 * 256, dtype=torch.float32, device=x2d.device)
+        status = lib.msda_linear256(
+            x2d.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(),
+            None if row_mask is None else row_mask.data_ptr(), mask_mode, y.data_ptr(), rows,
+            _DTYPE_CODE[out_dtype], scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _capi.check(status, 'msda_linear256')
+    return y
+
+
+class Linear256Function(Function):
+    """y = x W^T + b with the forward and the input-gradient GEMM on the tcgen05
+    tensor cores (3xTF32 split, fp32 accumulation in tensor memory), the padding
+    mask and the storage dtype folded into the epilogue.
+
+    mask_mode 1: masked rows of y are zero (mask after the projection,
+    multi_scale_deform_attn.py:369-371); 2: the input rows are treated as zero,
+    so y = bias there (mask before it, transformer.py:1706-1711)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, row_mask, mask_mode, out_dtype):
+        shape = x.shape
+        x2d = x.reshape(-1, 256).contiguous()
+        weight = weight.contiguous()
+        mask_u8 = None
+        if row_mask is not None and mask_mode:
+            mask_u8 = row_mask.reshape(-1).to(torch.uint8).contiguous()
+            if mask_u8.numel() != x2d.shape[0]:
+                raise RuntimeError('row_mask has %d entries for %d rows' % (mask_u8.numel(), x2d.shape[0]))
+        y = _linear256_raw(x2d, weight, None if bias is None else bias.contiguous(), mask_u8,
+                           mask_mode if mask_u8 is not None else 0, out_dtype)
+        ctx.save_for_backward(x2d, weight, mask_u8)
+        ctx.mask_mode = mask_mode if mask_u8 is not None else 0
+        ctx.has_bias = bias is not None
+        ctx.x_shape = shape
+        return y.view(*shape[:-1], 256)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_y):
+        x2d, weight, mask_u8 = ctx.saved_tensors
+        g = grad_y.reshape(-1, 256)
+        if g.dtype != torch.float32:
+            g = g.float()
+        g = g.contiguous()
+        grad_x = grad_w = grad_b = None
+        if ctx.needs_input_grad[0]:
+            # dX = dY W: the same kernel with W^T as the weight; masked rows get no gradient
+            grad_x = _linear256_raw(g, weight.t().contiguous(), None, mask_u8,
+                                    1 if ctx.mask_mode else 0, torch.float32).view(ctx.x_shape)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            keep = None if mask_u8 is None else (mask_u8 == 0).unsqueeze(1)
+            if ctx.needs_input_grad[1]:
+                if ctx.mask_mode == 1:
+                    grad_w = (g * keep).t() @ x2d          # masked outputs were forced to zero
+                elif ctx.mask_mode == 2:
+                    grad_w = g.t() @ (x2d * keep)          # masked inputs were zero
+                else:
+                    grad_w = g.t() @ x2d
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                grad_b = (g * keep).sum(0) if ctx.mask_mode == 1 else g.sum(0)
+        return grad_x, grad_w, grad_b, None, None, None
+
+
+def linear256(x, weight, bias=None, row_mask=None, mask_mode=0, out_dtype=torch.float32):
+    """Functional front-end of `Linear256Function` (see there)."""
+    return Linear256Function.apply(x, weight, bias, row_mask, mask_mode, out_dtype)

@@ -33,7 +33,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .functional import (FusedMultiScaleDeformableAttnFunction, MultiScaleDeformableAttnFunction,
-                         fuse_frames_as_levels, fused_supported)
+                         fuse_frames_as_levels, fused_supported, linear256, linear256_supported)
 from .registry import ATTENTION, OPERA_ATTENTION
 
 __all__ = [
@@ -99,8 +99,28 @@ class _DeformAttnBase(nn.Module):
     #: False reproduces the reference's op-by-op composition
     fuse_prologue = True
 
+    #: run the 256 -> 256 projections (value_proj, output_proj, and sampling_offsets when it
+    #: has 256 outputs) on the tcgen05 tensor cores (3xTF32, fp32-level accuracy) with mask and
+    #: storage dtype folded into the epilogue; False uses nn.Linear / cuBLAS fp32 op by op
+    tensor_core_linear = True
+
     def _can_fuse(self, value, offsets):
         return self.fuse_prologue and fused_supported(value, offsets)
+
+    def _project(self, layer, x, row_mask=None, mask_mode=0, out_dtype=None):
+        """layer(x), with the padding mask applied after (mask_mode 1) or before
+        (mask_mode 2) the projection and an optional storage dtype."""
+        if self.tensor_core_linear and linear256_supported(x, layer.weight):
+            return linear256(x, layer.weight, layer.bias, row_mask, mask_mode,
+                             out_dtype or torch.float32)
+        if row_mask is not None and mask_mode == 2:
+            x = x.masked_fill(row_mask[..., None], 0.0)
+        y = layer(x)
+        if row_mask is not None and mask_mode == 1:
+            y = y.masked_fill(row_mask[..., None], 0.0)
+        if out_dtype is not None and y.dtype != out_dtype:
+            y = y.to(out_dtype)
+        return y
 
     def __init__(self, embed_dims, num_heads, num_levels, num_points, im2col_step, dropout,
                  batch_first, norm_cfg, init_cfg, value_dtype):
@@ -182,11 +202,9 @@ class MultiScaleDeformableAttention(_DeformAttnBase):
         # per call (multi_scale_deform_attn.py:367); the kernel cannot read
         # outside `value` for in-range levels, so the sync is not reproduced.
 
-        value = self.value_proj(value)
-        if key_padding_mask is not None:
-            value = value.masked_fill(key_padding_mask[..., None], 0.0)
-        value = self._store(value).view(bs, num_value, self.num_heads, -1)
-        sampling_offsets = self.sampling_offsets(query).view(
+        value = self._project(self.value_proj, value, key_padding_mask, 1, self.value_dtype)
+        value = value.view(bs, num_value, self.num_heads, -1)
+        sampling_offsets = self._project(self.sampling_offsets, query).view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
         attention_weights = self.attention_weights(query).view(
             bs, num_query, self.num_heads, self.num_levels * self.num_points)
@@ -201,7 +219,7 @@ class MultiScaleDeformableAttention(_DeformAttnBase):
                 scale = reference_points[..., 2:] * (0.5 / self.num_points)
             output = _run_fused(value, spatial_shapes, level_start_index, sampling_offsets,
                                 attention_weights, ref, scale)
-            output = self.output_proj(output)
+            output = self._project(self.output_proj, output)
             if not self.batch_first:
                 output = output.permute(1, 0, 2)
             return self.dropout(output) + identity
@@ -220,7 +238,7 @@ class MultiScaleDeformableAttention(_DeformAttnBase):
                              f'but get {reference_points.shape[-1]} instead.')
         output = _run_op(value, spatial_shapes, level_start_index, sampling_locations,
                          attention_weights, self.im2col_step)
-        output = self.output_proj(output)
+        output = self._project(self.output_proj, output)
         if not self.batch_first:
             output = output.permute(1, 0, 2)
         return self.dropout(output) + identity
@@ -275,10 +293,8 @@ class MultiScaleDeformablePoseAttention(_DeformAttnBase):
         bs, num_query, _ = query.shape
         bs, num_key, _ = value.shape
 
-        value = self.value_proj(value)
-        if key_padding_mask is not None:
-            value = value.masked_fill(key_padding_mask[..., None], 0.0)
-        value = self._store(value).view(bs, num_key, self.num_heads, -1)
+        value = self._project(self.value_proj, value, key_padding_mask, 1, self.value_dtype)
+        value = value.view(bs, num_key, self.num_heads, -1)
         sampling_offsets = self.sampling_offsets(query).view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
         attention_weights = self.attention_weights(query).view(
@@ -298,7 +314,7 @@ class MultiScaleDeformablePoseAttention(_DeformAttnBase):
             output = _run_op(value, spatial_shapes, level_start_index, sampling_locations,
                              attention_weights, self.im2col_step)
         # the reference permutes unconditionally here (transformer.py:425)
-        output = self.output_proj(output).permute(1, 0, 2)
+        output = self._project(self.output_proj, output).permute(1, 0, 2)
         return self.dropout(output) + inp_residual
 
 
@@ -381,9 +397,7 @@ class _MulFramesPoseAttention(_MulFramesBase):
                              f'but get {reference_points.shape[-1]} instead.')
         # NOTE the order: mask first, then project (transformer.py:1706-1711),
         # unlike the single-frame classes
-        if key_padding_mask is not None:
-            value = value.masked_fill(key_padding_mask[..., None], 0.0)
-        value = self._store(self.value_proj(value))
+        value = self._project(self.value_proj, value, key_padding_mask, 2, self.value_dtype)
 
         # (bs, T, Q, L, K, 2): keypoints of every frame, and their pose boxes
         kpts = reference_points.reshape(bs, T, num_query, L, P, 2)
@@ -423,7 +437,7 @@ class _MulFramesPoseAttention(_MulFramesBase):
                                     self.im2col_step).reshape(bs, num_query, M, -1))
             output = self._fuse_reference_style(outs, logits).flatten(-2, -1)
 
-        output = self.output_proj(output).permute(1, 0, 2)
+        output = self._project(self.output_proj, output).permute(1, 0, 2)
         return self.dropout(output) + inp_residual
 
 
@@ -497,9 +511,9 @@ class _MulFramesJointAttention(_MulFramesBase):
         bs, num_value, num_frames, _ = value.shape
         if num_frames != T:
             raise ValueError('value holds %d frames, module built for %d' % (num_frames, T))
-        if key_padding_mask is not None:
-            value = value.masked_fill(key_padding_mask.transpose(1, 2)[..., None], 0.0)
-        value = self._store(self.value_proj(value))  # (G, S, T, C)
+        value = self._project(self.value_proj, value,
+                              None if key_padding_mask is None else key_padding_mask.transpose(1, 2),
+                              2, self.value_dtype)  # (G, S, T, C)
 
         ref_dim = reference_points.shape[-1]
         if ref_dim == 2:
@@ -560,7 +574,7 @@ class _MulFramesJointAttention(_MulFramesBase):
                                     self.im2col_step).reshape(bs, num_query, M, -1))
             output = self._fuse_reference_style(outs, logits).flatten(-2, -1)
 
-        output = self.output_proj(output)
+        output = self._project(self.output_proj, output)
         if not self.batch_first:
             output = output.permute(1, 0, 2)
         return self.dropout(output) + identity

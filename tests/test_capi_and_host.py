@@ -19,7 +19,7 @@ from conftest import ROOT, rel_err
 def _declared_functions():
     text = open(os.path.join(ROOT, 'include', 'pavenet_msda.h')).read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
-    return sorted(set(re.findall(r'\b(msda_[a-z_]+)\s*\(', text)))
+    return sorted(set(re.findall(r'\b(msda_[a-z_0-9]+)\s*\(', text)))
 
 
 def test_library_is_built_in_tree():

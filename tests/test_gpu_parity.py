@@ -613,6 +613,83 @@ def test_modules_fused_prologue_equals_op_by_op(case):
         assert rel_err(g_f[name], g_u[name]) < 2e-4, name
 
 
+# --------------------------------------------------------------------------
+# 256 -> 256 projection on the tcgen05 tensor cores (3xTF32)
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize('rows', [1, 127, 128, 129, 1000, 66669])
+def test_linear256_matches_fp64(rows):
+    """Forward against an fp64 reference: 3xTF32 must stay at fp32-level accuracy
+    (plain TF32 would be ~5e-4), including ragged last tiles."""
+    import pavenet_b200
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn(rows, 256, generator=g).cuda()
+    w = (torch.randn(256, 256, generator=g) * 0.06).cuda()
+    b = torch.randn(256, generator=g).cuda()
+    y = pavenet_b200.linear256(x, w, b)
+    ref = x.double() @ w.double().t() + b.double()
+    assert y.shape == (rows, 256) and y.dtype == torch.float32
+    assert rel_err(y, ref) < 1e-5
+    y_nobias = pavenet_b200.linear256(x, w, None)
+    assert rel_err(y_nobias, x.double() @ w.double().t()) < 1e-5
+
+
+def test_linear256_masks_dtype_and_gradients():
+    import pavenet_b200
+    g = torch.Generator().manual_seed(7)
+    B, S = 3, 700
+    x = torch.randn(B, S, 256, generator=g).cuda().requires_grad_()
+    lin = torch.nn.Linear(256, 256).cuda()
+    mask = (torch.rand(B, S, generator=g) < 0.2).cuda()
+    go = torch.randn(B, S, 256, generator=g).cuda()
+    for mode in (0, 1, 2):
+        for p in (x, lin.weight, lin.bias):
+            p.grad = None
+        y = pavenet_b200.linear256(x, lin.weight, lin.bias, mask if mode else None, mode)
+        y.backward(go)
+        got = (y.detach(), x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+        for p in (x, lin.weight, lin.bias):
+            p.grad = None
+        xin = x.masked_fill(mask[..., None], 0.0) if mode == 2 else x
+        yr = lin(xin)
+        if mode == 1:
+            yr = yr.masked_fill(mask[..., None], 0.0)
+        yr.backward(go)
+        ref = (yr.detach(), x.grad, lin.weight.grad, lin.bias.grad)
+        for a, b_, name in zip(got, ref, ('y', 'grad_x', 'grad_w', 'grad_b')):
+            assert rel_err(a, b_) < 1e-5, (mode, name)
+    y16 = pavenet_b200.linear256(x.detach(), lin.weight, lin.bias, mask, 1, torch.bfloat16)
+    assert y16.dtype == torch.bfloat16
+    assert rel_err(y16.float(), lin(x.detach()).masked_fill(mask[..., None], 0.0)) < 5e-3
+
+
+def test_modules_tensor_core_linear_equals_cublas():
+    """Module outputs and gradients with the tensor-core projections against the
+    same module on nn.Linear (cuBLAS fp32)."""
+    g = torch.Generator().manual_seed(11)
+    shapes = torch.tensor(MID_LEVELS)
+    lsi = O.level_start_index(shapes).cuda()
+    S = int(shapes.prod(1).sum())
+    mod = _full_size_module('MulFramesMultiScaleDeformablePoseAttentionNumFrames3', num_points=15)
+    Bc, Q, T = 2, 30, 3
+    q = torch.randn(Q, Bc, 256, generator=g).cuda()
+    mem = torch.randn(S, Bc * T, 256, generator=g).cuda()
+    kw = dict(query_pos=torch.randn(Q, Bc, 256, generator=g).cuda(),
+              key_padding_mask=(torch.rand(Bc * T, S, generator=g) < 0.1).cuda(),
+              reference_points=torch.rand(Bc, T * Q, 4, 30, generator=g).cuda(),
+              spatial_shapes=shapes.cuda(), level_start_index=lsi)
+    res = []
+    for tc in (True, False):
+        mod.tensor_core_linear = tc
+        mod.zero_grad()
+        qi, mi = q.clone().requires_grad_(), mem.clone().requires_grad_()
+        out = mod(qi, None, mi, **kw)
+        out.square().sum().backward()
+        res.append((out.detach(), qi.grad, mi.grad, mod.value_proj.weight.grad.clone(),
+                    mod.output_proj.bias.grad.clone()))
+    for a, b_ in zip(*res):
+        assert rel_err(a, b_) < 2e-5
+
+
 def test_clip_model_training_step_small():
     """The PAVE-Net R-50 restatement (config 4 vehicle) at a small resolution:
     finite losses, every trainable parameter receives a gradient (a DDP
