@@ -33,16 +33,26 @@ namespace {
 
 constexpr int kDim = 256;          // in == out features
 constexpr int kBM = 128;           // rows per CTA
-constexpr int kBK = 32;            // floats per K chunk = one 128-byte swizzle span
-constexpr int kChunks = kDim / kBK;
 constexpr int kStages = 2;
 constexpr int kUmmaK = 8;          // tf32 MMA K
-constexpr uint32_t kABytes = kBM * kBK * 4;     // 16 KiB
-constexpr uint32_t kBBytes = kDim * kBK * 4;    // 32 KiB
-constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // A_hi, A_lo, B_hi, B_lo
-constexpr uint32_t kTxBytes = kABytes + 2 * kBBytes;          // what TMA delivers per stage
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 128 /*barriers*/;
 constexpr int kTmemCols = 256;
+
+// BK = floats per K chunk = one swizzle span: 32 (128-byte swizzle, 192 KiB of shared
+// memory, one CTA per SM) or 16 (64-byte swizzle, 96 KiB, two CTAs per SM so one tile's
+// epilogue overlaps the other's main loop).
+template <int BK>
+struct Cfg {
+  static constexpr int kBK = BK;
+  static constexpr int kChunks = kDim / BK;
+  static constexpr uint32_t kABytes = kBM * BK * 4;
+  static constexpr uint32_t kBBytes = kDim * BK * 4;
+  static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // A_hi, A_lo, B_hi, B_lo
+  static constexpr uint32_t kTxBytes = kABytes + 2 * kBBytes;          // what TMA delivers per stage
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 128 /*barriers*/;
+  static constexpr uint32_t kSwizzleBytes = BK * 4;                    // 128 or 64
+  static constexpr uint64_t kLayoutType = BK == 32 ? 2 : 4;            // SWIZZLE_128B / SWIZZLE_64B
+  static constexpr uint64_t kSBO = 8 * kSwizzleBytes;                  // bytes between 8-row atoms
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -71,11 +81,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
-// K-major, SWIZZLE_128B operand: 8-row atoms of 1024 bytes, stacked densely.
+// K-major swizzled operand: 8-row atoms (8 x swizzle span bytes), stacked densely.
+template <class C>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   return static_cast<uint64_t>((smem_addr >> 4) & 0x3fff) | (uint64_t(1) << 16) /*LBO (unused)*/ |
-         (uint64_t(1024 >> 4) << 32) /*SBO*/ | (uint64_t(1) << 46) /*sm100 descriptor*/ |
-         (uint64_t(2) << 61) /*SWIZZLE_128B*/;
+         ((C::kSBO >> 4) << 32) /*SBO*/ | (uint64_t(1) << 46) /*sm100 descriptor*/ |
+         (C::kLayoutType << 61);
 }
 // D fp32, A/B tf32, both K-major, N = 256, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kDim >> 3) << 17) | ((kBM >> 4) << 24);
@@ -130,13 +141,19 @@ __device__ __forceinline__ void store_chunk<__nv_bfloat16>(__nv_bfloat16* p, con
 // mask_mode: 0 none; 1 masked rows are written as zeros (mask applied after the
 // projection, multi_scale_deform_attn.py:369-371); 2 masked rows are written as
 // the bias (mask applied to the input before it, transformer.py:1706-1711).
-template <typename OT>
-__global__ void __launch_bounds__(128, 1)
+constexpr int kThreads = 160;   // warps 0-3: split, MMA issue (thread 0), epilogue; warp 4: TMA producer
+
+template <typename OT, int BK>
+__global__ void __launch_bounds__(kThreads, BK == 32 ? 1 : 2)
 linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
                         const __grid_constant__ CUtensorMap map_whi,
                         const __grid_constant__ CUtensorMap map_wlo, const float* __restrict__ bias,
                         const uint8_t* __restrict__ row_mask, int mask_mode, OT* __restrict__ y,
                         int rows) {
+  using C = Cfg<BK>;
+  constexpr int kBK = C::kBK, kChunks = C::kChunks;
+  constexpr uint32_t kABytes = C::kABytes, kBBytes = C::kBBytes, kStageBytes = C::kStageBytes,
+                     kTxBytes = C::kTxBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B wants 1024-byte alignment
@@ -176,83 +193,88 @@ linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
     tma_load_2d(a + 2 * kABytes, &map_whi, bar, chunk * kBK, 0);           // B_hi
     tma_load_2d(a + 2 * kABytes + kBBytes, &map_wlo, bar, chunk * kBK, 0); // B_lo
   };
-  if (tid == 0) {
-    issue_loads(0, 0);
-    issue_loads(1, 1);
+  if (warp == 4) {
+    // ---- TMA producer: keeps the ring full; a stage is refilled as soon as the MMAs that
+    // read it have retired (tcgen05.commit -> mma_done) ----
+    if (tid == 128) {
+      for (int c = 0; c < kChunks; ++c) {
+        const int s = c & 1;
+        if (c >= kStages) mbar_wait(done0 + 8 * s, ((c - kStages) >> 1) & 1);
+        issue_loads(c, s);
+      }
+    }
+  } else {
+    for (int kc = 0; kc < kChunks; ++kc) {
+      const int s = kc & 1;
+      const uint32_t parity = (kc >> 1) & 1;
+      mbar_wait(full0 + 8 * s, parity);
+      // split the X chunk: hi stays where TMA put it, lo goes to the twin buffer
+      // (same offsets, so the swizzle pattern is preserved)
+      {
+        float4* a_hi = reinterpret_cast<float4*>(base_ptr + s * kStageBytes);
+        float4* a_lo = reinterpret_cast<float4*>(base_ptr + s * kStageBytes + kABytes);
+#pragma unroll
+        for (int i = tid; i < static_cast<int>(kABytes / 16); i += 128) {
+          const float4 x = a_hi[i];
+          const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+          a_hi[i] = h;
+          a_lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core reads
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");                 // the 4 consumer warps only
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a = stage_addr(s);
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          const uint32_t koff = k * kUmmaK * 4;   // bytes inside the swizzle span
+          const uint64_t a_hi = umma_desc<C>(a + koff), a_lo = umma_desc<C>(a + kABytes + koff);
+          const uint64_t b_hi = umma_desc<C>(a + 2 * kABytes + koff);
+          const uint64_t b_lo = umma_desc<C>(a + 2 * kABytes + kBBytes + koff);
+          umma_tf32(tmem_d, a_lo, b_hi, (kc | k) != 0);   // small terms first
+          umma_tf32(tmem_d, a_hi, b_lo, 1);
+          umma_tf32(tmem_d, a_hi, b_hi, 1);
+        }
+        umma_commit(done0 + 8 * s);   // arrives when the MMAs above have read the stage
+      }
+    }
+    // the last commit covers every MMA issued before it
+    mbar_wait(done0 + 8 * ((kChunks - 1) & 1), ((kChunks - 1) >> 1) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
 
-  for (int kc = 0; kc < kChunks; ++kc) {
-    const int s = kc & 1;
-    const uint32_t parity = (kc >> 1) & 1;
-    mbar_wait(full0 + 8 * s, parity);
-    // split the X chunk: hi stays where TMA put it, lo goes to the twin buffer
-    // (same offsets, so the 128-byte swizzle pattern is preserved)
-    {
-      float4* a_hi = reinterpret_cast<float4*>(base_ptr + s * kStageBytes);
-      float4* a_lo = reinterpret_cast<float4*>(base_ptr + s * kStageBytes + kABytes);
-#pragma unroll
-      for (int i = tid; i < static_cast<int>(kABytes / 16); i += 128) {
-        const float4 x = a_hi[i];
-        const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
-        a_hi[i] = h;
-        a_lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+  if (warp < 4) {
+    // epilogue: warp w owns TMEM lanes 32w .. 32w+31 = rows of the tile
+    const int r = row0 + tid;
+    const bool in_range = r < rows;
+    const bool masked = in_range && row_mask != nullptr && mask_mode != 0 && row_mask[r] != 0;
+    OT* yrow = y + static_cast<int64_t>(in_range ? r : 0) * kDim;
+  #pragma unroll 1
+    for (int c0 = 0; c0 < kDim; c0 += 32) {
+      uint32_t u[32];
+      const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+          "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+            "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]),
+            "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]),
+            "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]),
+            "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float v[32];
+  #pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float b = bias ? __ldg(bias + c0 + j) : 0.f;
+        float acc = __uint_as_float(u[j]) + b;
+        if (masked) acc = (mask_mode == 1) ? 0.f : b;
+        v[j] = acc;
       }
+      if (in_range) store_chunk<OT>(yrow + c0, v);
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core reads
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a = stage_addr(s);
-#pragma unroll
-      for (int k = 0; k < kBK / kUmmaK; ++k) {
-        const uint32_t koff = k * kUmmaK * 4;   // bytes inside the 128-byte span
-        const uint64_t a_hi = umma_desc(a + koff), a_lo = umma_desc(a + kABytes + koff);
-        const uint64_t b_hi = umma_desc(a + 2 * kABytes + koff);
-        const uint64_t b_lo = umma_desc(a + 2 * kABytes + kBBytes + koff);
-        umma_tf32(tmem_d, a_lo, b_hi, (kc | k) != 0);   // small terms first
-        umma_tf32(tmem_d, a_hi, b_lo, 1);
-        umma_tf32(tmem_d, a_hi, b_hi, 1);
-      }
-      umma_commit(done0 + 8 * s);                // arrives when the MMAs above have read the stage
-      if (kc + kStages < kChunks) {
-        mbar_wait(done0 + 8 * s, parity);
-        issue_loads(kc + kStages, s);
-      }
-    }
-  }
-  // the last commit covers every MMA issued before it
-  mbar_wait(done0 + 8 * ((kChunks - 1) & 1), ((kChunks - 1) >> 1) & 1);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-  // epilogue: warp w owns TMEM lanes 32w .. 32w+31 = rows of the tile
-  const int r = row0 + tid;
-  const bool in_range = r < rows;
-  const bool masked = in_range && row_mask != nullptr && mask_mode != 0 && row_mask[r] != 0;
-  OT* yrow = y + static_cast<int64_t>(in_range ? r : 0) * kDim;
-#pragma unroll 1
-  for (int c0 = 0; c0 < kDim; c0 += 32) {
-    uint32_t u[32];
-    const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + c0;
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
-        "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
-          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]),
-          "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]),
-          "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]),
-          "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float b = bias ? __ldg(bias + c0 + j) : 0.f;
-      float acc = __uint_as_float(u[j]) + b;
-      if (masked) acc = (mask_mode == 1) ? 0.f : b;
-      v[j] = acc;
-    }
-    if (in_range) store_chunk<OT>(yrow + c0, v);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -278,17 +300,35 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// (rows x 256) fp32 row-major matrix, boxes of 32 floats x box_rows rows, 128-byte swizzle
-bool make_map(CUtensorMap* map, const float* ptr, int rows, int box_rows) {
+// (rows x 256) fp32 row-major matrix, boxes of bk floats x box_rows rows, swizzle span = bk floats
+bool make_map(CUtensorMap* map, const float* ptr, int rows, int box_rows, int bk) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kDim), static_cast<cuuint64_t>(rows)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kDim) * 4};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename OT, int BK>
+cudaError_t launch_variant(const float* x, const float* w_hi, const float* w_lo, const float* bias,
+                           const uint8_t* row_mask, int mask_mode, void* y, int rows, cudaStream_t st) {
+  CUtensorMap mx, mhi, mlo;
+  if (!make_map(&mx, x, rows, kBM, BK) || !make_map(&mhi, w_hi, kDim, kDim, BK) ||
+      !make_map(&mlo, w_lo, kDim, kDim, BK))
+    return cudaErrorNotSupported;
+  constexpr uint32_t smem = Cfg<BK>::kSmemBytes;
+  const cudaError_t e = cudaFuncSetAttribute(linear256_tf32x3_kernel<OT, BK>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  const unsigned grid = (rows + kBM - 1) / kBM;
+  linear256_tf32x3_kernel<OT, BK><<<grid, kThreads, smem, st>>>(mx, mhi, mlo, bias, row_mask, mask_mode,
+                                                           static_cast<OT*>(y), rows);
+  return cudaGetLastError();
 }
 
 }  // namespace
@@ -300,27 +340,13 @@ cudaError_t launch_linear256(const float* x, const float* w, const float* bias,
   float* w_hi = scratch;
   float* w_lo = scratch + kDim * kDim;
   split_weight_kernel<<<(kDim * kDim + 255) / 256, 256, 0, st>>>(w, w_hi, w_lo);
-  CUtensorMap mx, mhi, mlo;
-  if (!make_map(&mx, x, rows, kBM) || !make_map(&mhi, w_hi, kDim, kDim) ||
-      !make_map(&mlo, w_lo, kDim, kDim))
-    return cudaErrorNotSupported;
-  const unsigned grid = (rows + kBM - 1) / kBM;
-  cudaError_t e;
-  if (out_dtype == MSDA_BF16) {
-    e = cudaFuncSetAttribute(linear256_tf32x3_kernel<__nv_bfloat16>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return e;
-    linear256_tf32x3_kernel<__nv_bfloat16><<<grid, 128, kSmemBytes, st>>>(
-        mx, mhi, mlo, bias, row_mask, mask_mode, static_cast<__nv_bfloat16*>(y), rows);
-  } else {
-    e = cudaFuncSetAttribute(linear256_tf32x3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             kSmemBytes);
-    if (e != cudaSuccess) return e;
-    linear256_tf32x3_kernel<float><<<grid, 128, kSmemBytes, st>>>(mx, mhi, mlo, bias, row_mask, mask_mode,
-                                                                  static_cast<float*>(y), rows);
-  }
   note_launches(2);
-  return cudaGetLastError();
+  const bool bk32 = tuning().linear_bk == 32;
+  if (out_dtype == MSDA_BF16)
+    return bk32 ? launch_variant<__nv_bfloat16, 32>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st)
+                : launch_variant<__nv_bfloat16, 16>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st);
+  return bk32 ? launch_variant<float, 32>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st)
+              : launch_variant<float, 16>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st);
 }
 
 }  // namespace msda

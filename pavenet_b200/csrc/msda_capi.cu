@@ -37,6 +37,7 @@ const Tuning& tuning() {
     x.force_generic = env_int("PAVENET_MSDA_FORCE_GENERIC", 0);
     x.fwd_split = env_int("PAVENET_MSDA_FWD_SPLIT", 0);
     x.bwd_split = env_int("PAVENET_MSDA_BWD_SPLIT", 0);
+    x.linear_bk = env_int("PAVENET_MSDA_LINEAR_BK", 16) == 32 ? 32 : 16;
     return x;
   }();
   return t;

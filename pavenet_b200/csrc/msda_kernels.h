@@ -15,6 +15,7 @@ struct Tuning {
   int force_generic = 0;
   int fwd_split = 0;  // 0 = heuristic
   int bwd_split = 0;  // 0 = heuristic
+  int linear_bk = 16; // linear256 K-chunk: 16 (two CTAs per SM) or 32 (one)
 };
 const Tuning& tuning();
 
@@ -45,8 +46,7 @@ cudaError_t launch_linear256(const float* x, const float* w, const float* bias,
                              const uint8_t* row_mask, int mask_mode, void* y, int rows, int out_dtype,
                              float* scratch, cudaStream_t st);
 
-// number of kernel launches the last launch_* call on this thread enqueued
-int last_launches();
+// adds n to the library-wide launch counter (msda_launch_count)
 void note_launches(int n);
 
 }  // namespace msda
