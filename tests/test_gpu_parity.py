@@ -319,6 +319,43 @@ def test_full_size_encoder_properties(fn):
     assert rel_err(ll.grad[:1, sl], rgl) < BWD_TOL_F32
 
 
+def test_largest_configuration_slices_match_oracle(fn):
+    """BASELINE config 5 at its largest: 8 frames of a 1200x2000 image
+    (S = 49 877 keys per frame, 408 MB of value, offsets up to 1.02e8 elements
+    inside one fused batch entry).  Forward and backward on the whole problem;
+    a handful of queries from the first and last frame against the CPU oracle."""
+    big = [(150, 250), (75, 125), (38, 63), (19, 32)]
+    g = torch.Generator(device='cuda').manual_seed(5)
+    shapes = torch.tensor(big)
+    S = int(shapes.prod(1).sum())
+    lsi = O.level_start_index(shapes)
+    B, Q, M, D, L, P = 8, 4096, 8, 32, 4, 4
+    value = torch.randn(B, S, M, D, device='cuda', generator=g)
+    loc = torch.rand(B, Q, M, L, P, 2, device='cuda', generator=g) * 1.1 - 0.05
+    aw = torch.softmax(torch.randn(B, Q, M, L * P, device='cuda', generator=g), -1).view(B, Q, M, L, P)
+    go = torch.randn(B, Q, M * D, device='cuda', generator=g)
+    out, gv, gl, ga = _fwd_bwd(fn, value, shapes.cuda(), lsi.cuda(), loc, aw, go)
+    for b in (0, B - 1):
+        sl = slice(100, 116)
+        ref = O.c_forward(value[b:b + 1].cpu(), shapes, lsi, loc[b:b + 1, sl].cpu(), aw[b:b + 1, sl].cpu())
+        assert rel_err(out[b:b + 1, sl], ref) < FWD_TOL_F32
+        _, rgl, rga = O.c_backward(value[b:b + 1].cpu(), shapes, lsi, loc[b:b + 1, sl].cpu(),
+                                   aw[b:b + 1, sl].cpu(), go[b:b + 1, sl].cpu())
+        assert rel_err(gl[b:b + 1, sl], rgl) < BWD_TOL_F32
+        assert rel_err(ga[b:b + 1, sl], rga) < BWD_TOL_F32
+    # the fused 8-frame view of the same tensor: one batch entry of 8*S keys, 32 "levels"
+    from pavenet_b200 import fuse_frames_as_levels
+    s_f, i_f = fuse_frames_as_levels(shapes.cuda(), lsi.cuda(), B, S)
+    loc_f = loc[:, :64].permute(1, 2, 0, 3, 4, 5).reshape(1, 64, M, B * L, P, 2).contiguous()
+    aw_f = (aw[:, :64].permute(1, 2, 0, 3, 4).reshape(1, 64, M, B * L, P) / B).contiguous()
+    fused = fn(value.view(1, B * S, M, D), s_f, i_f, loc_f, aw_f, 64)
+    per_frame = sum(out[b:b + 1, :64] for b in range(B)) / B
+    assert rel_err(fused, per_frame) < 1e-5
+    # grad_value: total mass conservation over the whole problem
+    inside = ((loc > 0.04) & (loc < 0.96)).all(-1)
+    assert torch.isfinite(gv).all() and gv.abs().sum() > 0 and inside.any()
+
+
 def test_full_size_pose_decoder_fused_equals_per_frame(fn):
     """Config 3: 300 pose queries x 17 keypoints x T=5 frames.  One fused call
     over T*L levels must equal the reference's T per-frame calls fused with
