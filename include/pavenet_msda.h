@@ -168,6 +168,14 @@ int msda_linear256(const float *d_x, const float *d_weight, const float *d_bias,
                    const uint8_t *d_row_mask, int mask_mode, void *d_y, int rows,
                    int out_dtype, float *d_scratch, void *stream);
 
+/* Weight gradient of the same projection: grad_weight[256 out][256 in] =
+ * grad_y^T x over `rows` rows (overwritten), split-K over the rows on tcgen05 with
+ * 3xTF32 and a vector-reduction epilogue.  mask_mode as in msda_linear256: 1 drops
+ * masked rows of grad_y, 2 drops masked rows of x. */
+int msda_linear256_wgrad(const float *d_grad_y, const float *d_x,
+                         const uint8_t *d_row_mask, int mask_mode,
+                         float *d_grad_weight, int rows, void *stream);
+
 /*
  * Host-buffer convenience entry points (what a cgo / JNI / ctypes caller
  * without its own device memory management binds).  All pointers are HOST

@@ -283,6 +283,183 @@ linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
   }
 }
 
+// ---------------------------------------------------------------------------
+// weight gradient:  dW[o][i] = sum_r dY[r][o] * X[r][i]      (256 x 256, K = rows)
+//
+// Split-K over the rows: each CTA owns a contiguous slice of rows, accumulates a
+// full 256 x 256 fp32 partial in TMEM (two M=128 halves x N=256 = all 512
+// columns), and reduces it into dW with red.global.add.v4.f32.  Both operands
+// are activations laid out (rows, 256), i.e. MN-major for this product: TMA
+// fetches 16-row slabs as eight 32-float-wide column blocks (one 3-D box), which
+// is the canonical MN-major operand layout for 32-bit types (128-byte rows swizzled in
+// 32-byte units, 4 k-rows per atom, atoms along M/N at LBO, along K at SBO); both
+// slabs are split into hi / lo in place for the 3xTF32 product.
+// ---------------------------------------------------------------------------
+constexpr int kWgRows = 16;                                   // rows (K) per stage
+constexpr int kWgStages = 3;
+constexpr uint32_t kWgSlab = kWgRows * kDim * 4;              // 16 KiB: one operand, hi or lo
+constexpr uint32_t kWgStageBytes = 4 * kWgSlab;               // dY_hi, dY_lo, X_hi, X_lo
+constexpr uint32_t kWgSmemBytes = kWgStages * kWgStageBytes + 1024 + 128;
+constexpr uint32_t kWgAtomStride = kWgRows * 128;             // bytes between 32-float column blocks
+// D fp32, A/B tf32, both MN-major, N = 256, M = 128
+constexpr uint32_t kIdescMN = kIdesc | (1u << 15) | (1u << 16);
+
+// 32-bit MN-major operands have exactly one legal shared-memory layout: 128-byte rows
+// swizzled in 32-byte units, in atoms of 4 k-rows (CUTLASS: "for mn-major tf32 operands,
+// SW128_32B is the only available smem layout"); TMA produces it with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  LBO: next 32-float column block; SBO: next 4 k-rows.
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr) {
+  return static_cast<uint64_t>((smem_addr >> 4) & 0x3fff) | (uint64_t(kWgAtomStride >> 4) << 16) /*LBO*/ |
+         (uint64_t(512 >> 4) << 32) /*SBO*/ | (uint64_t(1) << 46) | (uint64_t(1) << 61) /*SWIZZLE_128B_BASE32B*/;
+}
+__device__ __forceinline__ void umma_tf32_mn(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdescMN), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// zero_dy / zero_x: rows with row_mask != 0 contribute nothing through dY (mask applied
+// after the projection) or through X (mask applied to the input before it)
+__global__ void __launch_bounds__(kThreads, 1)
+linear256_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                       const uint8_t* __restrict__ row_mask, int zero_dy, int zero_x,
+                       float* __restrict__ dw, int rows, int rows_per_cta) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t bars = base + kWgStages * kWgStageBytes;
+  const uint32_t full0 = bars, done0 = bars + 32, tmem_slot = bars + 64;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + kWgStages * kWgStageBytes + 64);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row_begin = blockIdx.x * rows_per_cta;
+  const int row_end = min(rows, row_begin + rows_per_cta);
+  const int n_stages = (row_end - row_begin + kWgRows - 1) / kWgRows;   // >= 1 by construction
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(done0 + 8 * s, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp == 4) {
+    if (tid == 128) {
+      for (int c = 0; c < n_stages; ++c) {
+        const int s = c % kWgStages;
+        if (c >= kWgStages) mbar_wait(done0 + 8 * s, ((c / kWgStages) - 1) & 1);
+        const uint32_t bar = full0 + 8 * s, a = base + s * kWgStageBytes;
+        mbar_expect_tx(bar, 2 * kWgSlab);
+        tma_load_3d(a, &map_dy, bar, 0, row_begin + c * kWgRows, 0);
+        tma_load_3d(a + 2 * kWgSlab, &map_x, bar, 0, row_begin + c * kWgRows, 0);
+      }
+    }
+  } else {
+    for (int c = 0; c < n_stages; ++c) {
+      const int s = c % kWgStages;
+      mbar_wait(full0 + 8 * s, (c / kWgStages) & 1);
+      // split both slabs into hi / lo (and drop masked rows)
+      {
+        uint8_t* st = base_ptr + s * kWgStageBytes;
+        const int row0 = row_begin + c * kWgRows;
+#pragma unroll 4
+        for (int i = tid; i < static_cast<int>(2 * kWgSlab / 16); i += 128) {
+          const int which = i / static_cast<int>(kWgSlab / 16);          // 0: dY, 1: X
+          const int j = i - which * static_cast<int>(kWgSlab / 16);
+          float4* hi = reinterpret_cast<float4*>(st + which * 2 * kWgSlab) + j;
+          float4* lo = reinterpret_cast<float4*>(st + which * 2 * kWgSlab + kWgSlab) + j;
+          float4 x = *hi;
+          if (row_mask != nullptr && (which == 0 ? zero_dy : zero_x)) {
+            const int r = row0 + ((j >> 3) & (kWgRows - 1));             // 8 float4 per 128-byte row
+            if (r < rows && row_mask[r]) x = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+          *hi = h;
+          *lo = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a = base + s * kWgStageBytes;
+#pragma unroll
+        for (int kg = 0; kg < kWgRows / kUmmaK; ++kg) {                    // 8 rows per MMA
+          const uint32_t koff = kg * 1024;
+          const uint64_t b_hi = umma_desc_mn(a + 2 * kWgSlab + koff), b_lo = umma_desc_mn(a + 3 * kWgSlab + koff);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {                                    // output rows o in [128h, 128h+128)
+            const uint32_t aoff = h * 4 * kWgAtomStride + koff;
+            const uint64_t a_hi = umma_desc_mn(a + aoff), a_lo = umma_desc_mn(a + kWgSlab + aoff);
+            const uint32_t d = tmem_d + h * kDim;
+            umma_tf32_mn(d, a_lo, b_hi, (c | kg) != 0);
+            umma_tf32_mn(d, a_hi, b_lo, 1);
+            umma_tf32_mn(d, a_hi, b_hi, 1);
+          }
+        }
+        umma_commit(done0 + 8 * s);
+      }
+    }
+    const int last = n_stages - 1;
+    mbar_wait(done0 + 8 * (last % kWgStages), (last / kWgStages) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: lane = output row o within the half, 32 input columns per TMEM load
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      float* drow = dw + static_cast<int64_t>(h * 128 + tid) * kDim;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kDim; c0 += 32) {
+        uint32_t u[32];
+        const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + h * kDim + c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+            "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+              "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]),
+              "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]),
+              "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]),
+              "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + j),
+                       "f"(__uint_as_float(u[j])), "f"(__uint_as_float(u[j + 1])),
+                       "f"(__uint_as_float(u[j + 2])), "f"(__uint_as_float(u[j + 3]))
+                       : "memory");
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(512));
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -310,6 +487,21 @@ bool make_map(CUtensorMap* map, const float* ptr, int rows, int box_rows, int bk
   const cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// (rows x 256) fp32 viewed as {32 floats, rows, 8 column blocks}: one box = a 16-row slab laid
+// out block-major, each block a run of 128-byte rows (MN-major SWIZZLE_128B operand)
+bool make_map_mn(CUtensorMap* map, const float* ptr, int rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(rows), 8};
+  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(kDim) * 4, 128};
+  const cuuint32_t box[3] = {32, static_cast<cuuint32_t>(kWgRows), 8};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -347,6 +539,25 @@ cudaError_t launch_linear256(const float* x, const float* w, const float* bias,
                 : launch_variant<__nv_bfloat16, 16>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st);
   return bk32 ? launch_variant<float, 32>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st)
               : launch_variant<float, 16>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st);
+}
+
+// dW (256 x 256, fp32) = dY^T X; dW is overwritten
+cudaError_t launch_linear256_wgrad(const float* dy, const float* x, const uint8_t* row_mask,
+                                   int mask_mode, float* dw, int rows, int sm_count, cudaStream_t st) {
+  CUtensorMap mdy, mx;
+  if (!make_map_mn(&mdy, dy, rows) || !make_map_mn(&mx, x, rows)) return cudaErrorNotSupported;
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * kDim * kDim, st);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(linear256_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           kWgSmemBytes);
+  if (e != cudaSuccess) return e;
+  int rows_per_cta = (rows + sm_count - 1) / sm_count;
+  rows_per_cta = (rows_per_cta + kWgRows - 1) / kWgRows * kWgRows;
+  const unsigned grid = (rows + rows_per_cta - 1) / rows_per_cta;
+  linear256_wgrad_kernel<<<grid, kThreads, kWgSmemBytes, st>>>(
+      mdy, mx, row_mask, mask_mode == 1, mask_mode == 2, dw, rows, rows_per_cta);
+  note_launches(1);
+  return cudaGetLastError();
 }
 
 }  // namespace msda

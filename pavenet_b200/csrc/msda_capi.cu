@@ -300,6 +300,27 @@ int msda_linear256(const float* d_x, const float* d_weight, const float* d_bias,
   return MSDA_OK;
 }
 
+int msda_linear256_wgrad(const float* d_grad_y, const float* d_x, const uint8_t* d_row_mask,
+                         int mask_mode, float* d_grad_weight, int rows, void* stream) {
+  if (!d_grad_y || !d_x || !d_grad_weight)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256_wgrad: NULL pointer argument");
+  if (rows <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256_wgrad: rows must be positive");
+  if (mask_mode < 0 || mask_mode > 2 || (mask_mode != 0 && !d_row_mask))
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256_wgrad: bad mask_mode / row_mask");
+  if (misaligned16(d_grad_y) || misaligned16(d_x) || misaligned16(d_grad_weight))
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_linear256_wgrad needs 16-byte aligned buffers");
+  int sms = 0;
+  const int rc = current_sm_count(&sms);
+  if (rc) return rc;
+  const cudaError_t e = launch_linear256_wgrad(d_grad_y, d_x, d_row_mask, mask_mode, d_grad_weight, rows,
+                                               sms, static_cast<cudaStream_t>(stream));
+  if (e == cudaErrorNotSupported)
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_linear256_wgrad: cuTensorMapEncodeTiled unavailable or failed");
+  if (e != cudaSuccess)
+    return fail(MSDA_ERR_CUDA, "msda_linear256_wgrad launch failed: %s", cudaGetErrorString(e));
+  return MSDA_OK;
+}
+
 // ---------------------------------------------------------------------------
 // host-buffer entry points
 //

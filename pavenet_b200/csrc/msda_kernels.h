@@ -46,6 +46,9 @@ cudaError_t launch_linear256(const float* x, const float* w, const float* bias,
                              const uint8_t* row_mask, int mask_mode, void* y, int rows, int out_dtype,
                              float* scratch, cudaStream_t st);
 
+cudaError_t launch_linear256_wgrad(const float* dy, const float* x, const uint8_t* row_mask,
+                                   int mask_mode, float* dw, int rows, int sm_count, cudaStream_t st);
+
 // adds n to the library-wide launch counter (msda_launch_count)
 void note_launches(int n);
 

@@ -498,17 +498,19 @@ class Linear256Function(Function):
             # dX = dY W: the same kernel with W^T as the weight; masked rows get no gradient
             grad_x = _linear256_raw(g, weight.t().contiguous(), None, mask_u8,
                                     1 if ctx.mask_mode else 0, torch.float32).view(ctx.x_shape)
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            keep = None if mask_u8 is None else (mask_u8 == 0).unsqueeze(1)
-            if ctx.needs_input_grad[1]:
-                if ctx.mask_mode == 1:
-                    grad_w = (g * keep).t() @ x2d          # masked outputs were forced to zero
-                elif ctx.mask_mode == 2:
-                    grad_w = g.t() @ (x2d * keep)          # masked inputs were zero
-                else:
-                    grad_w = g.t() @ x2d
-            if ctx.has_bias and ctx.needs_input_grad[2]:
-                grad_b = (g * keep).sum(0) if ctx.mask_mode == 1 else g.sum(0)
+        if ctx.needs_input_grad[1]:
+            # dW = dY^T X, split-K on the tensor cores; mode 1 drops the masked rows of dY
+            # (their outputs were forced to zero), mode 2 those of X (their inputs were)
+            lib = _capi.load()
+            with torch.cuda.device(g.device):
+                grad_w = torch.empty((256, 256), dtype=torch.float32, device=g.device)
+                status = lib.msda_linear256_wgrad(
+                    g.data_ptr(), x2d.data_ptr(), None if mask_u8 is None else mask_u8.data_ptr(),
+                    ctx.mask_mode, grad_w.data_ptr(), g.shape[0],
+                    torch.cuda.current_stream().cuda_stream)
+            _capi.check(status, 'msda_linear256_wgrad')
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            grad_b = (g * (mask_u8 == 0).unsqueeze(1)).sum(0) if ctx.mask_mode == 1 else g.sum(0)
         return grad_x, grad_w, grad_b, None, None, None
 
 

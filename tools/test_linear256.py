@@ -37,3 +37,29 @@ for fn, name in ((ours, 'tcgen05 3xTF32'), (ref, 'torch fp32 (cuBLAS)')):
     for _ in range(50): fn()
     e1.record(); torch.cuda.synchronize()
     print(name, '%.4f ms' % (e0.elapsed_time(e1) / 50))
+
+# ---- weight gradient ----
+print('== wgrad')
+for rows in (16, 100, 1000, 66669):
+    dy = torch.randn(rows, 256, device=dev); x = torch.randn(rows, 256, device=dev)
+    dw = torch.full((256, 256), float('nan'), device=dev)
+    rc = lib.msda_linear256_wgrad(dy.data_ptr(), x.data_ptr(), None, 0, dw.data_ptr(), rows, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref = dy.double().t() @ x.double()
+    err = (dw.double() - ref).abs().max().item() / ref.abs().max().item()
+    err32 = ((dy.t() @ x).double() - ref).abs().max().item() / ref.abs().max().item()
+    print('rc', rc, lib.msda_last_error() if rc else '', 'rows', rows, 'rel err ours %.3e torch fp32 %.3e' % (err, err32), 'nan', int(torch.isnan(dw).sum()))
+rows = 66669
+dy = torch.randn(rows, 256, device=dev); x = torch.randn(rows, 256, device=dev); dw = torch.empty(256, 256, device=dev)
+def ours_w():
+    lib.msda_linear256_wgrad(dy.data_ptr(), x.data_ptr(), None, 0, dw.data_ptr(), rows, torch.cuda.current_stream().cuda_stream)
+def ref_w():
+    dy.t() @ x
+for fn, name in ((ours_w, 'wgrad tcgen05 3xTF32'), (ref_w, 'wgrad torch fp32 (cuBLAS)')):
+    for _ in range(5): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50): fn()
+    e1.record(); torch.cuda.synchronize()
+    print(name, '%.4f ms' % (e0.elapsed_time(e1) / 50))
