@@ -85,32 +85,6 @@ struct Vec16<__nv_bfloat16> {
   }
 };
 
-// Predicated 16-byte row-segment load from (uniform base + 32-bit byte offset).
-// When `pred` is false nothing is loaded and v keeps its previous contents.
-__device__ __forceinline__ void ldg16_pred(const char* base, uint32_t byte_off, int pred,
-                                           float (&v)[4]) {
-  asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %6, 0;\n\t"
-      "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
-      : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3])
-      : "l"(base + byte_off), "r"(0), "r"(pred));
-}
-__device__ __forceinline__ void ldg16_pred(const char* base, uint32_t byte_off, int pred,
-                                           float (&v)[8]) {
-  // 8 bf16 -> 8 floats; the packed words persist in v's bit patterns only after
-  // conversion, so a skipped load must leave v untouched: convert under the predicate
-  uint32_t x = 0, y = 0, z = 0, w = 0;
-  asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
-      "@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
-      : "+r"(x), "+r"(y), "+r"(z), "+r"(w)
-      : "l"(base + byte_off), "r"(pred));
-  if (pred) {
-    v[0] = __uint_as_float(x << 16); v[1] = __uint_as_float(x & 0xffff0000u);
-    v[2] = __uint_as_float(y << 16); v[3] = __uint_as_float(y & 0xffff0000u);
-    v[4] = __uint_as_float(z << 16); v[5] = __uint_as_float(z & 0xffff0000u);
-    v[6] = __uint_as_float(w << 16); v[7] = __uint_as_float(w & 0xffff0000u);
-  }
-}
-
 // Streaming (read-once) loads for locations / weights / grad_output: keep them
 // from displacing value rows in L1.
 __device__ __forceinline__ float2 ld_stream_f2(const float* p) {
