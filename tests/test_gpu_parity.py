@@ -144,6 +144,35 @@ def test_rows_kernels_match_oracle_fp32(fn, B, Q, M, D, P, shapes):
     assert rel_err(gl, rgl) < 5e-5
 
 
+def test_randomised_shapes_against_oracle(fn):
+    """40 seeded random problems over every dispatch axis — D in {2..64} (rows and
+    generic kernels), ragged level sizes incl. 1xN maps, 1..6 levels, 1..19 points,
+    row splits (small Q x many samples), locations far outside the map — forward and
+    all three gradients against the C oracle."""
+    import random
+    rng = random.Random(20251017)
+    for trial in range(40):
+        D = rng.choice([2, 8, 16, 16, 32, 32, 32, 64, 24])
+        M = rng.choice([1, 2, 4, 8])
+        L = rng.randint(1, 6)
+        P = rng.randint(1, 19)
+        B = rng.randint(1, 3)
+        Q = rng.choice([1, 3, 17, 64, 300])
+        shapes = [(rng.randint(1, 24), rng.randint(1, 24)) for _ in range(L)]
+        value, shapes_t, loc, aw, go = _random_problem(1000 + trial, B, Q, M, D, P, shapes,
+                                                       spread=rng.choice([0.0, 0.1, 0.6]))
+        lsi = O.level_start_index(shapes_t)
+        out, gv, gl, ga = _fwd_bwd(fn, value.cuda(), shapes_t.cuda(), lsi.cuda(), loc.cuda(),
+                                   aw.cuda(), go)
+        ref = O.c_forward(value, shapes_t, lsi, loc, aw)
+        rgv, rgl, rga = O.c_backward(value, shapes_t, lsi, loc, aw, go)
+        tag = (trial, B, Q, M, D, L, P, shapes)
+        assert rel_err(out, ref) < FWD_TOL_F32, tag
+        assert rel_err(gv, rgv) < BWD_TOL_F32, tag
+        assert rel_err(gl, rgl) < BWD_TOL_F32, tag
+        assert rel_err(ga, rga) < BWD_TOL_F32, tag
+
+
 def test_rows_and_generic_kernels_agree(op_golden):
     """The D=32 fast path and the scalar generic path are two implementations
     of the same maths; both go through the C ABI.  Forced by running the
