@@ -153,28 +153,40 @@ int msda_fused_backward(const void *d_value, const int64_t *d_spatial_shapes,
                         int ref_points_per_level, int value_dtype, void *stream);
 
 /*
- * The 256 -> 256 projection next to the op (SURVEY.md section 8f rank 2:
- * `value_proj` + padding mask + storage dtype, multi_scale_deform_attn.py:369-372,
+ * The projections next to the op (`value_proj` +
+ * padding mask + storage dtype, `output_proj`, `sampling_offsets`,
+ * `attention_weights`; multi_scale_deform_attn.py:369-377,
  * opera/models/utils/transformer.py:1706-1720) on the tcgen05 tensor cores:
- *   y[rows,256] = x[rows,256] * weight^T + bias      weight (256 out, 256 in), fp32
- * computed as a 3xTF32 split with fp32 accumulation in tensor memory (fp32-level
- * accuracy; plain TF32 would not meet the op's parity bound).  mask_mode 0: no
- * mask; 1: rows with d_row_mask[r] != 0 are written as zeros (mask after the
- * projection); 2: they are written as the bias (input masked before it).
- * out_dtype MSDA_F32 or MSDA_BF16.  d_scratch: 2*256*256 floats of device
- * scratch (the split weight).  d_bias may be NULL.
+ *   y[rows,out] = x[rows,in] * weight^T + bias        weight (out, in), fp32
+ * for (in_features, out_features) in {(256,256), (256,128), (128,256)} -- the
+ * three shapes the embed_dims = 256 modules and their input gradients need;
+ * anything else returns MSDA_ERR_UNSUPPORTED.  Computed as a 3xTF32 split with
+ * fp32 accumulation in tensor memory (fp32-level accuracy; plain TF32 would not
+ * meet the op's parity bound).  mask_mode 0: no mask; 1: rows with
+ * d_row_mask[r] != 0 are written as zeros (mask after the projection); 2: they
+ * are written as the bias (input masked before it).  out_dtype MSDA_F32 or
+ * MSDA_BF16.  d_scratch: 2*in*out floats of device scratch (the split weight).
+ * d_bias may be NULL.
  */
 int msda_linear256(const float *d_x, const float *d_weight, const float *d_bias,
                    const uint8_t *d_row_mask, int mask_mode, void *d_y, int rows,
-                   int out_dtype, float *d_scratch, void *stream);
+                   int in_features, int out_features, int out_dtype,
+                   float *d_scratch, void *stream);
 
-/* Weight gradient of the same projection: grad_weight[256 out][256 in] =
- * grad_y^T x over `rows` rows (overwritten), split-K over the rows on tcgen05 with
- * 3xTF32 and a vector-reduction epilogue.  mask_mode as in msda_linear256: 1 drops
+/* Weight gradient of the same projection: grad_weight[out][in] = grad_y^T x
+ * over `rows` rows (overwritten), split-K over the rows on tcgen05 with 3xTF32
+ * and a vector-reduction epilogue.  mask_mode as in msda_linear256: 1 drops
  * masked rows of grad_y, 2 drops masked rows of x. */
 int msda_linear256_wgrad(const float *d_grad_y, const float *d_x,
                          const uint8_t *d_row_mask, int mask_mode,
-                         float *d_grad_weight, int rows, void *stream);
+                         float *d_grad_weight, int rows, int in_features,
+                         int out_features, void *stream);
+
+/* Bias gradient of the same projection: grad_bias[width] = column sums of
+ * grad_y[rows][width] (overwritten), width 128 or 256; rows with
+ * d_row_mask[r] != 0 are skipped (pass NULL to sum every row). */
+int msda_colsum256(const float *d_grad_y, const uint8_t *d_row_mask,
+                   float *d_grad_bias, int rows, int width, void *stream);
 
 /*
  * Host-buffer convenience entry points (what a cgo / JNI / ctypes caller

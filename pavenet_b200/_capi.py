@@ -17,6 +17,7 @@ EXPORTED_SYMBOLS = (
     'msda_abi_version', 'msda_last_error', 'msda_launch_count',
     'msda_kernel_name', 'msda_forward', 'msda_backward', 'msda_fused_forward',
     'msda_fused_backward', 'msda_linear256', 'msda_linear256_wgrad',
+    'msda_colsum256',
     'msda_workspace_create', 'msda_workspace_destroy', 'msda_workspace_set_piece_bytes',
     'msda_host_alloc',
     'msda_host_free', 'msda_forward_host',
@@ -53,9 +54,11 @@ def _declare(lib):
     lib.msda_fused_backward.restype = c_int
     lib.msda_fused_backward.argtypes = [c_void_p] * 13 + [c_int] * 9 + [c_void_p]
     lib.msda_linear256.restype = c_int
-    lib.msda_linear256.argtypes = [c_void_p] * 4 + [c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]
+    lib.msda_linear256.argtypes = [c_void_p] * 4 + [c_int, c_void_p] + [c_int] * 4 + [c_void_p, c_void_p]
     lib.msda_linear256_wgrad.restype = c_int
-    lib.msda_linear256_wgrad.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]
+    lib.msda_linear256_wgrad.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]
+    lib.msda_colsum256.restype = c_int
+    lib.msda_colsum256.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
     lib.msda_workspace_create.restype = c_int
     lib.msda_workspace_create.argtypes = [ctypes.POINTER(c_void_p)]
     lib.msda_workspace_destroy.restype = None

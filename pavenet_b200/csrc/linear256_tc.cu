@@ -31,21 +31,22 @@
 namespace msda {
 namespace {
 
-constexpr int kDim = 256;          // in == out features
 constexpr int kBM = 128;           // rows per CTA
 constexpr int kStages = 2;
 constexpr int kUmmaK = 8;          // tf32 MMA K
-constexpr int kTmemCols = 256;
+// in / out features are 128 or 256 (template parameters KIN / NOUT below): 256 -> 256 for
+// value_proj, output_proj and the encoder's sampling_offsets, 256 -> 128 for its
+// attention_weights, 128 -> 256 for that layer's input gradient.
 
 // BK = floats per K chunk = one swizzle span: 32 (128-byte swizzle, 192 KiB of shared
 // memory, one CTA per SM) or 16 (64-byte swizzle, 96 KiB, two CTAs per SM so one tile's
 // epilogue overlaps the other's main loop).
-template <int BK>
+template <int BK, int KIN, int NOUT>
 struct Cfg {
   static constexpr int kBK = BK;
-  static constexpr int kChunks = kDim / BK;
+  static constexpr int kChunks = KIN / BK;
   static constexpr uint32_t kABytes = kBM * BK * 4;
-  static constexpr uint32_t kBBytes = kDim * BK * 4;
+  static constexpr uint32_t kBBytes = NOUT * BK * 4;
   static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // A_hi, A_lo, B_hi, B_lo
   static constexpr uint32_t kTxBytes = kABytes + 2 * kBBytes;          // what TMA delivers per stage
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 128 /*barriers*/;
@@ -88,15 +89,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
          ((C::kSBO >> 4) << 32) /*SBO*/ | (uint64_t(1) << 46) /*sm100 descriptor*/ |
          (C::kLayoutType << 61);
 }
-// D fp32, A/B tf32, both K-major, N = 256, M = 128
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kDim >> 3) << 17) | ((kBM >> 4) << 24);
+// instruction descriptor: D fp32, A/B tf32, M = 128, N = n; mn_major sets both operands MN-major
+__host__ __device__ constexpr uint32_t idesc_tf32(int n, bool mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(kBM >> 4) << 24) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u);
+}
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -105,11 +110,11 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
-// W -> (W_hi, W_lo), once per call (65 536 elements)
+// W -> (W_hi, W_lo), once per call (at most 65 536 elements)
 __global__ void split_weight_kernel(const float* __restrict__ w, float* __restrict__ w_hi,
-                                    float* __restrict__ w_lo) {
+                                    float* __restrict__ w_lo, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < kDim * kDim) {
+  if (i < n) {
     const float x = w[i], hi = tf32_hi(x);
     w_hi[i] = hi;
     w_lo[i] = x - hi;
@@ -143,15 +148,16 @@ __device__ __forceinline__ void store_chunk<__nv_bfloat16>(__nv_bfloat16* p, con
 // the bias (mask applied to the input before it, transformer.py:1706-1711).
 constexpr int kThreads = 160;   // warps 0-3: split, MMA issue (thread 0), epilogue; warp 4: TMA producer
 
-template <typename OT, int BK>
+template <typename OT, int BK, int KIN, int NOUT>
 __global__ void __launch_bounds__(kThreads, BK == 32 ? 1 : 2)
 linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
                         const __grid_constant__ CUtensorMap map_whi,
                         const __grid_constant__ CUtensorMap map_wlo, const float* __restrict__ bias,
                         const uint8_t* __restrict__ row_mask, int mask_mode, OT* __restrict__ y,
                         int rows) {
-  using C = Cfg<BK>;
+  using C = Cfg<BK, KIN, NOUT>;
   constexpr int kBK = C::kBK, kChunks = C::kChunks;
+  constexpr uint32_t kIdesc = idesc_tf32(NOUT, false);
   constexpr uint32_t kABytes = C::kABytes, kBBytes = C::kBBytes, kStageBytes = C::kStageBytes,
                      kTxBytes = C::kTxBytes;
   extern __shared__ uint8_t smem_raw[];
@@ -167,7 +173,7 @@ linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "n"(kTmemCols));
+                 "n"(NOUT));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
@@ -233,9 +239,9 @@ linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
           const uint64_t a_hi = umma_desc<C>(a + koff), a_lo = umma_desc<C>(a + kABytes + koff);
           const uint64_t b_hi = umma_desc<C>(a + 2 * kABytes + koff);
           const uint64_t b_lo = umma_desc<C>(a + 2 * kABytes + kBBytes + koff);
-          umma_tf32(tmem_d, a_lo, b_hi, (kc | k) != 0);   // small terms first
-          umma_tf32(tmem_d, a_hi, b_lo, 1);
-          umma_tf32(tmem_d, a_hi, b_hi, 1);
+          umma_tf32(tmem_d, a_lo, b_hi, kIdesc, (kc | k) != 0);   // small terms first
+          umma_tf32(tmem_d, a_hi, b_lo, kIdesc, 1);
+          umma_tf32(tmem_d, a_hi, b_hi, kIdesc, 1);
         }
         umma_commit(done0 + 8 * s);   // arrives when the MMAs above have read the stage
       }
@@ -250,9 +256,9 @@ linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
     const int r = row0 + tid;
     const bool in_range = r < rows;
     const bool masked = in_range && row_mask != nullptr && mask_mode != 0 && row_mask[r] != 0;
-    OT* yrow = y + static_cast<int64_t>(in_range ? r : 0) * kDim;
+    OT* yrow = y + static_cast<int64_t>(in_range ? r : 0) * NOUT;
   #pragma unroll 1
-    for (int c0 = 0; c0 < kDim; c0 += 32) {
+    for (int c0 = 0; c0 < NOUT; c0 += 32) {
       uint32_t u[32];
       const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + c0;
       asm volatile(
@@ -279,7 +285,7 @@ linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(NOUT));
   }
 }
 
@@ -297,12 +303,17 @@ linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
 // ---------------------------------------------------------------------------
 constexpr int kWgRows = 16;                                   // rows (K) per stage
 constexpr int kWgStages = 3;
-constexpr uint32_t kWgSlab = kWgRows * kDim * 4;              // 16 KiB: one operand, hi or lo
-constexpr uint32_t kWgStageBytes = 4 * kWgSlab;               // dY_hi, dY_lo, X_hi, X_lo
-constexpr uint32_t kWgSmemBytes = kWgStages * kWgStageBytes + 1024 + 128;
 constexpr uint32_t kWgAtomStride = kWgRows * 128;             // bytes between 32-float column blocks
-// D fp32, A/B tf32, both MN-major, N = 256, M = 128
-constexpr uint32_t kIdescMN = kIdesc | (1u << 15) | (1u << 16);
+
+template <int MOUT, int NIN>
+struct WgCfg {
+  static constexpr uint32_t kSlabA = kWgRows * MOUT * 4;      // dY slab, hi or lo
+  static constexpr uint32_t kSlabB = kWgRows * NIN * 4;       // X slab, hi or lo
+  static constexpr uint32_t kStageBytes = 2 * kSlabA + 2 * kSlabB;   // dY_hi, dY_lo, X_hi, X_lo
+  static constexpr uint32_t kSmemBytes = kWgStages * kStageBytes + 1024 + 128;
+  static constexpr int kHalves = MOUT / 128;                  // M = 128 accumulators
+  static constexpr int kTmemCols = kHalves * NIN;             // 256 or 512
+};
 
 // 32-bit MN-major operands have exactly one legal shared-memory layout: 128-byte rows
 // swizzled in 32-byte units, in atoms of 4 k-rows (CUTLASS: "for mn-major tf32 operands,
@@ -312,14 +323,6 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr) {
   return static_cast<uint64_t>((smem_addr >> 4) & 0x3fff) | (uint64_t(kWgAtomStride >> 4) << 16) /*LBO*/ |
          (uint64_t(512 >> 4) << 32) /*SBO*/ | (uint64_t(1) << 46) | (uint64_t(1) << 61) /*SWIZZLE_128B_BASE32B*/;
 }
-__device__ __forceinline__ void umma_tf32_mn(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdescMN), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
                                             int c1, int c2) {
   asm volatile(
@@ -328,27 +331,50 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// split one 16-row slab into hi / lo in place; rows with row_mask != 0 are dropped
+__device__ __forceinline__ void split_slab(uint8_t* hi_base, uint32_t slab_bytes, int tid, int row0, int rows,
+                                           const uint8_t* row_mask) {
+  float4* hi = reinterpret_cast<float4*>(hi_base);
+  float4* lo = reinterpret_cast<float4*>(hi_base + slab_bytes);
+#pragma unroll 4
+  for (int j = tid; j < static_cast<int>(slab_bytes / 16); j += 128) {
+    float4 x = hi[j];
+    if (row_mask != nullptr) {
+      const int r = row0 + ((j >> 3) & (kWgRows - 1));             // 8 float4 per 128-byte row
+      if (r < rows && row_mask[r]) x = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+    hi[j] = h;
+    lo[j] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+  }
+}
+
 // zero_dy / zero_x: rows with row_mask != 0 contribute nothing through dY (mask applied
 // after the projection) or through X (mask applied to the input before it)
+template <int MOUT, int NIN>
 __global__ void __launch_bounds__(kThreads, 1)
 linear256_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                        const uint8_t* __restrict__ row_mask, int zero_dy, int zero_x,
                        float* __restrict__ dw, int rows, int rows_per_cta) {
+  using W = WgCfg<MOUT, NIN>;
+  constexpr uint32_t kSlabA = W::kSlabA, kSlabB = W::kSlabB, kStageBytes = W::kStageBytes;
+  constexpr uint32_t kIdescMN = idesc_tf32(NIN, true);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw);
-  const uint32_t bars = base + kWgStages * kWgStageBytes;
+  const uint32_t bars = base + kWgStages * kStageBytes;
   const uint32_t full0 = bars, done0 = bars + 32, tmem_slot = bars + 64;
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + kWgStages * kWgStageBytes + 64);
+      reinterpret_cast<volatile uint32_t*>(base_ptr + kWgStages * kStageBytes + 64);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row_begin = blockIdx.x * rows_per_cta;
   const int row_end = min(rows, row_begin + rows_per_cta);
   const int n_stages = (row_end - row_begin + kWgRows - 1) / kWgRows;   // >= 1 by construction
 
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(W::kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
@@ -370,54 +396,41 @@ linear256_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
       for (int c = 0; c < n_stages; ++c) {
         const int s = c % kWgStages;
         if (c >= kWgStages) mbar_wait(done0 + 8 * s, ((c / kWgStages) - 1) & 1);
-        const uint32_t bar = full0 + 8 * s, a = base + s * kWgStageBytes;
-        mbar_expect_tx(bar, 2 * kWgSlab);
+        const uint32_t bar = full0 + 8 * s, a = base + s * kStageBytes;
+        mbar_expect_tx(bar, kSlabA + kSlabB);
         tma_load_3d(a, &map_dy, bar, 0, row_begin + c * kWgRows, 0);
-        tma_load_3d(a + 2 * kWgSlab, &map_x, bar, 0, row_begin + c * kWgRows, 0);
+        tma_load_3d(a + 2 * kSlabA, &map_x, bar, 0, row_begin + c * kWgRows, 0);
       }
     }
   } else {
     for (int c = 0; c < n_stages; ++c) {
       const int s = c % kWgStages;
       mbar_wait(full0 + 8 * s, (c / kWgStages) & 1);
-      // split both slabs into hi / lo (and drop masked rows)
       {
-        uint8_t* st = base_ptr + s * kWgStageBytes;
+        uint8_t* st = base_ptr + s * kStageBytes;
         const int row0 = row_begin + c * kWgRows;
-#pragma unroll 4
-        for (int i = tid; i < static_cast<int>(2 * kWgSlab / 16); i += 128) {
-          const int which = i / static_cast<int>(kWgSlab / 16);          // 0: dY, 1: X
-          const int j = i - which * static_cast<int>(kWgSlab / 16);
-          float4* hi = reinterpret_cast<float4*>(st + which * 2 * kWgSlab) + j;
-          float4* lo = reinterpret_cast<float4*>(st + which * 2 * kWgSlab + kWgSlab) + j;
-          float4 x = *hi;
-          if (row_mask != nullptr && (which == 0 ? zero_dy : zero_x)) {
-            const int r = row0 + ((j >> 3) & (kWgRows - 1));             // 8 float4 per 128-byte row
-            if (r < rows && row_mask[r]) x = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
-          *hi = h;
-          *lo = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-        }
+        split_slab(st, kSlabA, tid, row0, rows, zero_dy ? row_mask : nullptr);
+        split_slab(st + 2 * kSlabA, kSlabB, tid, row0, rows, zero_x ? row_mask : nullptr);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a = base + s * kWgStageBytes;
+        const uint32_t a = base + s * kStageBytes;
 #pragma unroll
         for (int kg = 0; kg < kWgRows / kUmmaK; ++kg) {                    // 8 rows per MMA
           const uint32_t koff = kg * 1024;
-          const uint64_t b_hi = umma_desc_mn(a + 2 * kWgSlab + koff), b_lo = umma_desc_mn(a + 3 * kWgSlab + koff);
+          const uint64_t b_hi = umma_desc_mn(a + 2 * kSlabA + koff);
+          const uint64_t b_lo = umma_desc_mn(a + 2 * kSlabA + kSlabB + koff);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {                                    // output rows o in [128h, 128h+128)
+          for (int h = 0; h < W::kHalves; ++h) {                           // output rows o in [128h, 128h+128)
             const uint32_t aoff = h * 4 * kWgAtomStride + koff;
-            const uint64_t a_hi = umma_desc_mn(a + aoff), a_lo = umma_desc_mn(a + kWgSlab + aoff);
-            const uint32_t d = tmem_d + h * kDim;
-            umma_tf32_mn(d, a_lo, b_hi, (c | kg) != 0);
-            umma_tf32_mn(d, a_hi, b_lo, 1);
-            umma_tf32_mn(d, a_hi, b_hi, 1);
+            const uint64_t a_hi = umma_desc_mn(a + aoff), a_lo = umma_desc_mn(a + kSlabA + aoff);
+            const uint32_t d = tmem_d + h * NIN;
+            umma_tf32(d, a_lo, b_hi, kIdescMN, (c | kg) != 0);
+            umma_tf32(d, a_hi, b_lo, kIdescMN, 1);
+            umma_tf32(d, a_hi, b_hi, kIdescMN, 1);
           }
         }
         umma_commit(done0 + 8 * s);
@@ -428,12 +441,12 @@ linear256_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // epilogue: lane = output row o within the half, 32 input columns per TMEM load
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-      float* drow = dw + static_cast<int64_t>(h * 128 + tid) * kDim;
+    for (int h = 0; h < W::kHalves; ++h) {
+      float* drow = dw + static_cast<int64_t>(h * 128 + tid) * NIN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < kDim; c0 += 32) {
+      for (int c0 = 0; c0 < NIN; c0 += 32) {
         uint32_t u[32];
-        const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + h * kDim + c0;
+        const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + h * NIN + c0;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
             "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -456,7 +469,7 @@ linear256_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(512));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(W::kTmemCols));
   }
 }
 
@@ -477,85 +490,159 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// (rows x 256) fp32 row-major matrix, boxes of bk floats x box_rows rows, swizzle span = bk floats
-bool make_map(CUtensorMap* map, const float* ptr, int rows, int box_rows, int bk) {
+// (rows x width) fp32 row-major matrix, boxes of bk floats x box_rows rows, swizzle span = bk floats
+bool make_map(CUtensorMap* map, const float* ptr, int rows, int width, int box_rows, int bk) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
-  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kDim), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kDim) * 4};
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(width) * 4};
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// (rows x 256) fp32 viewed as {32 floats, rows, 8 column blocks}: one box = a 16-row slab laid
-// out block-major, each block a run of 128-byte rows (MN-major SWIZZLE_128B operand)
-bool make_map_mn(CUtensorMap* map, const float* ptr, int rows) {
+// (rows x width) fp32 viewed as {32 floats, rows, width/32 column blocks}: one box = a 16-row slab
+// laid out block-major, each block a run of 128-byte rows (MN-major SW128_32B operand)
+bool make_map_mn(CUtensorMap* map, const float* ptr, int rows, int width) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
-  const cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(rows), 8};
-  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(kDim) * 4, 128};
-  const cuuint32_t box[3] = {32, static_cast<cuuint32_t>(kWgRows), 8};
+  const cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(width / 32)};
+  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(width) * 4, 128};
+  const cuuint32_t box[3] = {32, static_cast<cuuint32_t>(kWgRows), static_cast<cuuint32_t>(width / 32)};
   const cuuint32_t estr[3] = {1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename OT, int BK>
+template <typename OT, int BK, int KIN, int NOUT>
 cudaError_t launch_variant(const float* x, const float* w_hi, const float* w_lo, const float* bias,
                            const uint8_t* row_mask, int mask_mode, void* y, int rows, cudaStream_t st) {
   CUtensorMap mx, mhi, mlo;
-  if (!make_map(&mx, x, rows, kBM, BK) || !make_map(&mhi, w_hi, kDim, kDim, BK) ||
-      !make_map(&mlo, w_lo, kDim, kDim, BK))
+  if (!make_map(&mx, x, rows, KIN, kBM, BK) || !make_map(&mhi, w_hi, NOUT, KIN, NOUT, BK) ||
+      !make_map(&mlo, w_lo, NOUT, KIN, NOUT, BK))
     return cudaErrorNotSupported;
-  constexpr uint32_t smem = Cfg<BK>::kSmemBytes;
-  const cudaError_t e = cudaFuncSetAttribute(linear256_tf32x3_kernel<OT, BK>,
+  constexpr uint32_t smem = Cfg<BK, KIN, NOUT>::kSmemBytes;
+  const cudaError_t e = cudaFuncSetAttribute(linear256_tf32x3_kernel<OT, BK, KIN, NOUT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   const unsigned grid = (rows + kBM - 1) / kBM;
-  linear256_tf32x3_kernel<OT, BK><<<grid, kThreads, smem, st>>>(mx, mhi, mlo, bias, row_mask, mask_mode,
-                                                           static_cast<OT*>(y), rows);
+  linear256_tf32x3_kernel<OT, BK, KIN, NOUT><<<grid, kThreads, smem, st>>>(
+      mx, mhi, mlo, bias, row_mask, mask_mode, static_cast<OT*>(y), rows);
   return cudaGetLastError();
 }
 
-}  // namespace
-
-// returns cudaSuccess, cudaErrorNotSupported (no driver entry point), or the launch error
-cudaError_t launch_linear256(const float* x, const float* w, const float* bias,
-                             const uint8_t* row_mask, int mask_mode, void* y, int rows, int out_dtype,
-                             float* scratch, cudaStream_t st) {
-  float* w_hi = scratch;
-  float* w_lo = scratch + kDim * kDim;
-  split_weight_kernel<<<(kDim * kDim + 255) / 256, 256, 0, st>>>(w, w_hi, w_lo);
-  note_launches(2);
+template <int KIN, int NOUT>
+cudaError_t launch_shape(const float* x, const float* w_hi, const float* w_lo, const float* bias,
+                         const uint8_t* row_mask, int mask_mode, void* y, int rows, int out_dtype,
+                         cudaStream_t st) {
   const bool bk32 = tuning().linear_bk == 32;
   if (out_dtype == MSDA_BF16)
-    return bk32 ? launch_variant<__nv_bfloat16, 32>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st)
-                : launch_variant<__nv_bfloat16, 16>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st);
-  return bk32 ? launch_variant<float, 32>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st)
-              : launch_variant<float, 16>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st);
+    return bk32 ? launch_variant<__nv_bfloat16, 32, KIN, NOUT>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st)
+                : launch_variant<__nv_bfloat16, 16, KIN, NOUT>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st);
+  return bk32 ? launch_variant<float, 32, KIN, NOUT>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st)
+              : launch_variant<float, 16, KIN, NOUT>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st);
 }
 
-// dW (256 x 256, fp32) = dY^T X; dW is overwritten
-cudaError_t launch_linear256_wgrad(const float* dy, const float* x, const uint8_t* row_mask,
-                                   int mask_mode, float* dw, int rows, int sm_count, cudaStream_t st) {
+template <int MOUT, int NIN>
+cudaError_t launch_wgrad_shape(const float* dy, const float* x, const uint8_t* row_mask, int mask_mode,
+                               float* dw, int rows, int sm_count, cudaStream_t st) {
   CUtensorMap mdy, mx;
-  if (!make_map_mn(&mdy, dy, rows) || !make_map_mn(&mx, x, rows)) return cudaErrorNotSupported;
-  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * kDim * kDim, st);
+  if (!make_map_mn(&mdy, dy, rows, MOUT) || !make_map_mn(&mx, x, rows, NIN)) return cudaErrorNotSupported;
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * MOUT * NIN, st);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(linear256_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           kWgSmemBytes);
+  constexpr uint32_t smem = WgCfg<MOUT, NIN>::kSmemBytes;
+  e = cudaFuncSetAttribute(linear256_wgrad_kernel<MOUT, NIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int rows_per_cta = (rows + sm_count - 1) / sm_count;
   rows_per_cta = (rows_per_cta + kWgRows - 1) / kWgRows * kWgRows;
   const unsigned grid = (rows + rows_per_cta - 1) / rows_per_cta;
-  linear256_wgrad_kernel<<<grid, kThreads, kWgSmemBytes, st>>>(
+  linear256_wgrad_kernel<MOUT, NIN><<<grid, kThreads, smem, st>>>(
       mdy, mx, row_mask, mask_mode == 1, mask_mode == 2, dw, rows, rows_per_cta);
+  note_launches(1);
+  return cudaGetLastError();
+}
+
+// bias gradient: out[c] = sum over rows of dy[r][c] (rows with row_mask != 0 skipped).
+// torch's reduction over dim 0 of a (rows, 256) tensor runs at ~0.8 TB/s; this streams it once.
+template <int WIDTH>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ row_mask, float* __restrict__ out,
+              int rows, int rows_per_block) {
+  constexpr int CG = WIDTH / 4, RL = 256 / CG;      // column groups of 4 floats, row lanes
+  __shared__ float4 s_part[RL][CG];
+  const int cg = threadIdx.x % CG, lane_r = threadIdx.x / CG;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = r0 + lane_r; r < r1; r += RL) {
+    if (row_mask != nullptr && row_mask[r]) continue;
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(dy + static_cast<int64_t>(r) * WIDTH) + cg);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  s_part[lane_r][cg] = acc;
+  __syncthreads();
+  if (lane_r == 0) {
+    for (int k = 1; k < RL; ++k) {
+      const float4 v = s_part[k][cg];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + 4 * cg), "f"(acc.x), "f"(acc.y),
+                 "f"(acc.z), "f"(acc.w)
+                 : "memory");
+  }
+}
+
+}  // namespace
+
+bool linear_shape_supported(int in_features, int out_features) {
+  return (in_features == 256 && (out_features == 256 || out_features == 128)) ||
+         (in_features == 128 && out_features == 256);
+}
+
+// y = x w^T + bias; returns cudaSuccess, cudaErrorNotSupported (shape, or no driver entry point),
+// or the launch error
+cudaError_t launch_linear256(const float* x, const float* w, const float* bias,
+                             const uint8_t* row_mask, int mask_mode, void* y, int rows, int in_features,
+                             int out_features, int out_dtype, float* scratch, cudaStream_t st) {
+  if (!linear_shape_supported(in_features, out_features)) return cudaErrorNotSupported;
+  const int n = in_features * out_features;
+  float* w_hi = scratch;
+  float* w_lo = scratch + n;
+  split_weight_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, w_hi, w_lo, n);
+  note_launches(2);
+  if (in_features == 256 && out_features == 256)
+    return launch_shape<256, 256>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, out_dtype, st);
+  if (in_features == 256)
+    return launch_shape<256, 128>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, out_dtype, st);
+  return launch_shape<128, 256>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, out_dtype, st);
+}
+
+// dW (out x in, fp32) = dY^T X; dW is overwritten
+cudaError_t launch_linear256_wgrad(const float* dy, const float* x, const uint8_t* row_mask,
+                                   int mask_mode, float* dw, int rows, int in_features, int out_features,
+                                   int sm_count, cudaStream_t st) {
+  if (in_features == 256 && out_features == 256)
+    return launch_wgrad_shape<256, 256>(dy, x, row_mask, mask_mode, dw, rows, sm_count, st);
+  if (in_features == 256 && out_features == 128)
+    return launch_wgrad_shape<128, 256>(dy, x, row_mask, mask_mode, dw, rows, sm_count, st);
+  if (in_features == 128 && out_features == 256)
+    return launch_wgrad_shape<256, 128>(dy, x, row_mask, mask_mode, dw, rows, sm_count, st);
+  return cudaErrorNotSupported;
+}
+
+cudaError_t launch_colsum256(const float* dy, const uint8_t* row_mask, float* out, int rows, int width,
+                             int sm_count, cudaStream_t st) {
+  if (width != 256 && width != 128) return cudaErrorNotSupported;
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * width, st);
+  if (e != cudaSuccess) return e;
+  const int blocks_wanted = sm_count * 8;
+  int rows_per_block = (rows + blocks_wanted - 1) / blocks_wanted;
+  rows_per_block = (rows_per_block + 7) / 8 * 8;
+  const unsigned grid = (rows + rows_per_block - 1) / rows_per_block;
+  if (width == 256) colsum_kernel<256><<<grid, 256, 0, st>>>(dy, row_mask, out, rows, rows_per_block);
+  else colsum_kernel<128><<<grid, 256, 0, st>>>(dy, row_mask, out, rows, rows_per_block);
   note_launches(1);
   return cudaGetLastError();
 }

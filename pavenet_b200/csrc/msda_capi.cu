@@ -280,11 +280,14 @@ int msda_fused_backward(const void* d_value, const int64_t* d_spatial_shapes,
 }
 
 int msda_linear256(const float* d_x, const float* d_weight, const float* d_bias,
-                   const uint8_t* d_row_mask, int mask_mode, void* d_y, int rows, int out_dtype,
-                   float* d_scratch, void* stream) {
+                   const uint8_t* d_row_mask, int mask_mode, void* d_y, int rows, int in_features,
+                   int out_features, int out_dtype, float* d_scratch, void* stream) {
   if (!d_x || !d_weight || !d_y || !d_scratch)
     return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256: NULL pointer argument");
   if (rows <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256: rows must be positive");
+  if (!linear_shape_supported(in_features, out_features))
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_linear256: (in, out) = (%d, %d) is not one of (256,256), (256,128), (128,256)",
+                in_features, out_features);
   if (out_dtype != MSDA_F32 && out_dtype != MSDA_BF16)
     return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256: out_dtype must be MSDA_F32 or MSDA_BF16");
   if (mask_mode < 0 || mask_mode > 2 || (mask_mode != 0 && !d_row_mask))
@@ -292,7 +295,7 @@ int msda_linear256(const float* d_x, const float* d_weight, const float* d_bias,
   if (misaligned16(d_x) || misaligned16(d_weight) || misaligned16(d_y) || misaligned16(d_scratch))
     return fail(MSDA_ERR_UNSUPPORTED, "msda_linear256 needs 16-byte aligned buffers");
   const cudaError_t e = launch_linear256(d_x, d_weight, d_bias, d_row_mask, mask_mode, d_y, rows,
-                                         out_dtype, d_scratch, static_cast<cudaStream_t>(stream));
+                                         in_features, out_features, out_dtype, d_scratch, static_cast<cudaStream_t>(stream));
   if (e == cudaErrorNotSupported)
     return fail(MSDA_ERR_UNSUPPORTED, "msda_linear256: cuTensorMapEncodeTiled unavailable or failed");
   if (e != cudaSuccess)
@@ -301,10 +304,14 @@ int msda_linear256(const float* d_x, const float* d_weight, const float* d_bias,
 }
 
 int msda_linear256_wgrad(const float* d_grad_y, const float* d_x, const uint8_t* d_row_mask,
-                         int mask_mode, float* d_grad_weight, int rows, void* stream) {
+                         int mask_mode, float* d_grad_weight, int rows, int in_features,
+                         int out_features, void* stream) {
   if (!d_grad_y || !d_x || !d_grad_weight)
     return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256_wgrad: NULL pointer argument");
   if (rows <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256_wgrad: rows must be positive");
+  if (!linear_shape_supported(in_features, out_features))
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_linear256_wgrad: (in, out) = (%d, %d) is not one of (256,256), (256,128), (128,256)",
+                in_features, out_features);
   if (mask_mode < 0 || mask_mode > 2 || (mask_mode != 0 && !d_row_mask))
     return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256_wgrad: bad mask_mode / row_mask");
   if (misaligned16(d_grad_y) || misaligned16(d_x) || misaligned16(d_grad_weight))
@@ -313,11 +320,30 @@ int msda_linear256_wgrad(const float* d_grad_y, const float* d_x, const uint8_t*
   const int rc = current_sm_count(&sms);
   if (rc) return rc;
   const cudaError_t e = launch_linear256_wgrad(d_grad_y, d_x, d_row_mask, mask_mode, d_grad_weight, rows,
-                                               sms, static_cast<cudaStream_t>(stream));
+                                               in_features, out_features, sms, static_cast<cudaStream_t>(stream));
   if (e == cudaErrorNotSupported)
     return fail(MSDA_ERR_UNSUPPORTED, "msda_linear256_wgrad: cuTensorMapEncodeTiled unavailable or failed");
   if (e != cudaSuccess)
     return fail(MSDA_ERR_CUDA, "msda_linear256_wgrad launch failed: %s", cudaGetErrorString(e));
+  return MSDA_OK;
+}
+
+int msda_colsum256(const float* d_grad_y, const uint8_t* d_row_mask, float* d_grad_bias, int rows,
+                   int width, void* stream) {
+  if (!d_grad_y || !d_grad_bias)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_colsum256: NULL pointer argument");
+  if (rows <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_colsum256: rows must be positive");
+  if (width != 128 && width != 256)
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_colsum256: width must be 128 or 256, got %d", width);
+  if (misaligned16(d_grad_y) || misaligned16(d_grad_bias))
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_colsum256 needs 16-byte aligned buffers");
+  int sms = 0;
+  const int rc = current_sm_count(&sms);
+  if (rc) return rc;
+  const cudaError_t e = launch_colsum256(d_grad_y, d_row_mask, d_grad_bias, rows, width, sms,
+                                         static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess)
+    return fail(MSDA_ERR_CUDA, "msda_colsum256 launch failed: %s", cudaGetErrorString(e));
   return MSDA_OK;
 }
 

@@ -41,13 +41,17 @@ cudaError_t launch_backward_fused(const void* value, const int64_t* shapes, cons
                                   float* grad_off, float* grad_logit, float* grad_loc,
                                   const Dims& d, int value_dtype, int sm_count, cudaStream_t st);
 
-// Y = X W^T + bias for 256 -> 256 projections on tcgen05 (3xTF32), linear256_tc.cu
+// Y = X W^T + bias, dW = dY^T X and the bias gradient for the 128/256-wide projections of the
+// attention modules on tcgen05 (3xTF32), linear256_tc.cu
+bool linear_shape_supported(int in_features, int out_features);
 cudaError_t launch_linear256(const float* x, const float* w, const float* bias,
-                             const uint8_t* row_mask, int mask_mode, void* y, int rows, int out_dtype,
-                             float* scratch, cudaStream_t st);
-
+                             const uint8_t* row_mask, int mask_mode, void* y, int rows, int in_features,
+                             int out_features, int out_dtype, float* scratch, cudaStream_t st);
 cudaError_t launch_linear256_wgrad(const float* dy, const float* x, const uint8_t* row_mask,
-                                   int mask_mode, float* dw, int rows, int sm_count, cudaStream_t st);
+                                   int mask_mode, float* dw, int rows, int in_features, int out_features,
+                                   int sm_count, cudaStream_t st);
+cudaError_t launch_colsum256(const float* dy, const uint8_t* row_mask, float* out, int rows, int width,
+                             int sm_count, cudaStream_t st);
 
 // adds n to the library-wide launch counter (msda_launch_count)
 void note_launches(int n);

@@ -434,34 +434,42 @@ class FusedMultiScaleDeformableAttnFunction(Function):
 
 
 # ---------------------------------------------------------------------------
-# 256 -> 256 projections on the tcgen05 tensor cores
+# the 128/256-wide projections on the tcgen05 tensor cores
 # ---------------------------------------------------------------------------
+_LINEAR_SHAPES = ((256, 256), (128, 256), (256, 128))     # weight.shape = (out, in)
+
+
 def linear256_supported(x, weight):
-    """True when `linear256` has a kernel for these tensors: CUDA, fp32,
-    in_features == out_features == 256."""
+    """True when `linear256` has kernels for these tensors: CUDA, fp32, weight
+    (out, in) one of (256,256), (128,256), (256,128) -- every projection of an
+    embed_dims = 256 attention module with num_heads*levels*points in {64, 128}
+    (offsets 128/256 wide, attention weights 128 wide)."""
     return (x.is_cuda and weight.is_cuda and x.dtype == torch.float32
-            and weight.dtype == torch.float32 and tuple(weight.shape) == (256, 256)
-            and x.shape[-1] == 256 and x.numel() > 0)
+            and weight.dtype == torch.float32 and tuple(weight.shape) in _LINEAR_SHAPES
+            and x.shape[-1] == weight.shape[1] and x.numel() > 0)
 
 
 def _linear256_raw(x2d, weight, bias, row_mask, mask_mode, out_dtype):
     lib = _capi.load()
     rows = x2d.shape[0]
+    n_out, n_in = weight.shape
     with torch.cuda.device(x2d.device):
-        y = torch.empty((rows, 256), dtype=out_dtype, device=x2d.device)
-        scratch = torch.empty(2 * 256 * 256, dtype=torch.float32, device=x2d.device)
+        y = torch.empty((rows, n_out), dtype=out_dtype, device=x2d.device)
+        scratch = torch.empty(2 * n_out * n_in, dtype=torch.float32, device=x2d.device)
         status = lib.msda_linear256(
             x2d.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(),
             None if row_mask is None else row_mask.data_ptr(), mask_mode, y.data_ptr(), rows,
-            _DTYPE_CODE[out_dtype], scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            n_in, n_out, _DTYPE_CODE[out_dtype], scratch.data_ptr(),
+            torch.cuda.current_stream().cuda_stream)
     _capi.check(status, 'msda_linear256')
     return y
 
 
 class Linear256Function(Function):
-    """y = x W^T + b with the forward and the input-gradient GEMM on the tcgen05
-    tensor cores (3xTF32 split, fp32 accumulation in tensor memory), the padding
-    mask and the storage dtype folded into the epilogue.
+    """y = x W^T + b with the forward, the input-gradient GEMM, the weight
+    gradient and the bias gradient on hand-written kernels: the three GEMMs on
+    the tcgen05 tensor cores (3xTF32 split, fp32 accumulation in tensor memory),
+    the padding mask and the storage dtype folded into the epilogue.
 
     mask_mode 1: masked rows of y are zero (mask after the projection,
     multi_scale_deform_attn.py:369-371); 2: the input rows are treated as zero,
@@ -470,7 +478,8 @@ class Linear256Function(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, row_mask, mask_mode, out_dtype):
         shape = x.shape
-        x2d = x.reshape(-1, 256).contiguous()
+        n_out, n_in = weight.shape
+        x2d = x.reshape(-1, n_in).contiguous()
         weight = weight.contiguous()
         mask_u8 = None
         if row_mask is not None and mask_mode:
@@ -483,13 +492,14 @@ class Linear256Function(Function):
         ctx.mask_mode = mask_mode if mask_u8 is not None else 0
         ctx.has_bias = bias is not None
         ctx.x_shape = shape
-        return y.view(*shape[:-1], 256)
+        return y.view(*shape[:-1], n_out)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_y):
         x2d, weight, mask_u8 = ctx.saved_tensors
-        g = grad_y.reshape(-1, 256)
+        n_out, n_in = weight.shape
+        g = grad_y.reshape(-1, n_out)
         if g.dtype != torch.float32:
             g = g.float()
         g = g.contiguous()
@@ -503,14 +513,22 @@ class Linear256Function(Function):
             # (their outputs were forced to zero), mode 2 those of X (their inputs were)
             lib = _capi.load()
             with torch.cuda.device(g.device):
-                grad_w = torch.empty((256, 256), dtype=torch.float32, device=g.device)
+                grad_w = torch.empty((n_out, n_in), dtype=torch.float32, device=g.device)
                 status = lib.msda_linear256_wgrad(
                     g.data_ptr(), x2d.data_ptr(), None if mask_u8 is None else mask_u8.data_ptr(),
-                    ctx.mask_mode, grad_w.data_ptr(), g.shape[0],
+                    ctx.mask_mode, grad_w.data_ptr(), g.shape[0], n_in, n_out,
                     torch.cuda.current_stream().cuda_stream)
             _capi.check(status, 'msda_linear256_wgrad')
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            grad_b = (g * (mask_u8 == 0).unsqueeze(1)).sum(0) if ctx.mask_mode == 1 else g.sum(0)
+            # column sums of dY in one streaming pass (masked rows skipped in mode 1)
+            lib = _capi.load()
+            with torch.cuda.device(g.device):
+                grad_b = torch.empty(n_out, dtype=torch.float32, device=g.device)
+                status = lib.msda_colsum256(
+                    g.data_ptr(),
+                    mask_u8.data_ptr() if (mask_u8 is not None and ctx.mask_mode == 1) else None,
+                    grad_b.data_ptr(), g.shape[0], n_out, torch.cuda.current_stream().cuda_stream)
+            _capi.check(status, 'msda_colsum256')
         return grad_x, grad_w, grad_b, None, None, None
 
 

@@ -99,8 +99,8 @@ class _DeformAttnBase(nn.Module):
     #: False reproduces the reference's op-by-op composition
     fuse_prologue = True
 
-    #: run the 256 -> 256 projections (value_proj, output_proj, and sampling_offsets when it
-    #: has 256 outputs) on the tcgen05 tensor cores (3xTF32, fp32-level accuracy) with mask and
+    #: run the 128/256-wide projections (value_proj, output_proj, and sampling_offsets /
+    #: attention_weights when they have 128 or 256 outputs) on the tcgen05 tensor cores (3xTF32, fp32-level accuracy) with mask and
     #: storage dtype folded into the epilogue; False uses nn.Linear / cuBLAS fp32 op by op
     tensor_core_linear = True
 
@@ -206,7 +206,7 @@ class MultiScaleDeformableAttention(_DeformAttnBase):
         value = value.view(bs, num_value, self.num_heads, -1)
         sampling_offsets = self._project(self.sampling_offsets, query).view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
-        attention_weights = self.attention_weights(query).view(
+        attention_weights = self._project(self.attention_weights, query).view(
             bs, num_query, self.num_heads, self.num_levels * self.num_points)
         if reference_points.shape[-1] not in (2, 4):
             raise ValueError(f'Last dim of reference_points must be 2 or 4, '
@@ -295,9 +295,9 @@ class MultiScaleDeformablePoseAttention(_DeformAttnBase):
 
         value = self._project(self.value_proj, value, key_padding_mask, 1, self.value_dtype)
         value = value.view(bs, num_key, self.num_heads, -1)
-        sampling_offsets = self.sampling_offsets(query).view(
+        sampling_offsets = self._project(self.sampling_offsets, query).view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
-        attention_weights = self.attention_weights(query).view(
+        attention_weights = self._project(self.attention_weights, query).view(
             bs, num_query, self.num_heads, self.num_levels * self.num_points)
         if reference_points.shape[-1] != self.num_points * 2:
             raise ValueError(f'Last dim of reference_points must be 2K, '

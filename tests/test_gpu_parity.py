@@ -680,33 +680,39 @@ def test_modules_fused_prologue_equals_op_by_op(case):
 
 
 # --------------------------------------------------------------------------
-# 256 -> 256 projection on the tcgen05 tensor cores (3xTF32)
+# the 128/256-wide projections on the tcgen05 tensor cores (3xTF32)
 # --------------------------------------------------------------------------
+LINEAR_SHAPES = [(256, 256), (256, 128), (128, 256)]      # (in, out)
+
+
+@pytest.mark.parametrize('n_in,n_out', LINEAR_SHAPES)
 @pytest.mark.parametrize('rows', [1, 127, 128, 129, 1000, 66669])
-def test_linear256_matches_fp64(rows):
+def test_linear256_matches_fp64(rows, n_in, n_out):
     """Forward against an fp64 reference: 3xTF32 must stay at fp32-level accuracy
     (plain TF32 would be ~5e-4), including ragged last tiles."""
     import pavenet_b200
     g = torch.Generator().manual_seed(rows)
-    x = torch.randn(rows, 256, generator=g).cuda()
-    w = (torch.randn(256, 256, generator=g) * 0.06).cuda()
-    b = torch.randn(256, generator=g).cuda()
+    x = torch.randn(rows, n_in, generator=g).cuda()
+    w = (torch.randn(n_out, n_in, generator=g) * 0.06).cuda()
+    b = torch.randn(n_out, generator=g).cuda()
+    assert pavenet_b200.linear256_supported(x, w)
     y = pavenet_b200.linear256(x, w, b)
     ref = x.double() @ w.double().t() + b.double()
-    assert y.shape == (rows, 256) and y.dtype == torch.float32
+    assert y.shape == (rows, n_out) and y.dtype == torch.float32
     assert rel_err(y, ref) < 1e-5
     y_nobias = pavenet_b200.linear256(x, w, None)
     assert rel_err(y_nobias, x.double() @ w.double().t()) < 1e-5
 
 
-def test_linear256_masks_dtype_and_gradients():
+@pytest.mark.parametrize('n_in,n_out', LINEAR_SHAPES)
+def test_linear256_masks_dtype_and_gradients(n_in, n_out):
     import pavenet_b200
     g = torch.Generator().manual_seed(7)
     B, S = 3, 700
-    x = torch.randn(B, S, 256, generator=g).cuda().requires_grad_()
-    lin = torch.nn.Linear(256, 256).cuda()
+    x = torch.randn(B, S, n_in, generator=g).cuda().requires_grad_()
+    lin = torch.nn.Linear(n_in, n_out).cuda()
     mask = (torch.rand(B, S, generator=g) < 0.2).cuda()
-    go = torch.randn(B, S, 256, generator=g).cuda()
+    go = torch.randn(B, S, n_out, generator=g).cuda()
     for mode in (0, 1, 2):
         for p in (x, lin.weight, lin.bias):
             p.grad = None
@@ -726,6 +732,20 @@ def test_linear256_masks_dtype_and_gradients():
     y16 = pavenet_b200.linear256(x.detach(), lin.weight, lin.bias, mask, 1, torch.bfloat16)
     assert y16.dtype == torch.bfloat16
     assert rel_err(y16.float(), lin(x.detach()).masked_fill(mask[..., None], 0.0)) < 5e-3
+
+
+def test_linear256_refuses_other_shapes():
+    import pavenet_b200
+    from pavenet_b200 import _capi
+    x = torch.randn(10, 192).cuda()
+    w = torch.randn(256, 192).cuda()
+    assert not pavenet_b200.linear256_supported(x, w)
+    lib = _capi.load()
+    y = torch.empty(10, 256).cuda()
+    scratch = torch.empty(2 * 256 * 192).cuda()
+    rc = lib.msda_linear256(x.data_ptr(), w.data_ptr(), None, None, 0, y.data_ptr(), 10, 192, 256, 0,
+                            scratch.data_ptr(), None)
+    assert rc != 0 and b'(192, 256)' in lib.msda_last_error()
 
 
 def test_modules_tensor_core_linear_equals_cublas():
