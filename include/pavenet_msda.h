@@ -153,27 +153,43 @@ int msda_fused_backward(const void *d_value, const int64_t *d_spatial_shapes,
                         int ref_points_per_level, int value_dtype, void *stream);
 
 /*
- * The projections next to the op (`value_proj` +
- * padding mask + storage dtype, `output_proj`, `sampling_offsets`,
- * `attention_weights`; multi_scale_deform_attn.py:369-377,
- * opera/models/utils/transformer.py:1706-1720) on the tcgen05 tensor cores:
- *   y[rows,out] = x[rows,in] * weight^T + bias        weight (out, in), fp32
- * for (in_features, out_features) in {(256,256), (256,128), (128,256)} -- the
- * three shapes the embed_dims = 256 modules and their input gradients need;
- * anything else returns MSDA_ERR_UNSUPPORTED.  Computed as a 3xTF32 split with
- * fp32 accumulation in tensor memory (fp32-level accuracy; plain TF32 would not
- * meet the op's parity bound).  mask_mode 0: no mask; 1: rows with
- * d_row_mask[r] != 0 are written as zeros (mask after the projection); 2: they
- * are written as the bias (input masked before it).  out_dtype MSDA_F32 or
- * MSDA_BF16.  d_scratch: 2*in*out floats of device scratch (the split weight).
- * d_bias may be NULL.
+ * The fp32 Linear layers next to the op (SURVEY.md section 8f ranks 2 and 4:
+ * `value_proj` + padding mask + storage dtype, `output_proj` + dropout +
+ * residual, `sampling_offsets`, `attention_weights`,
+ * multi_scale_deform_attn.py:369-377,406-412, opera/models/utils/transformer.py:1706-1720;
+ * and the 256 <-> 1024 feed-forward pair of the transformer layers that carry
+ * them, mmcv/cnn/bricks/transformer.py FFN) on the tcgen05 tensor cores:
+ *   y[rows,out] = epilogue(x[rows,in] * weight^T)        weight (out, in), fp32
+ * in_features and out_features each one of 128, 256, 1024 (128x128 and 1024x1024
+ * excluded); anything else returns MSDA_ERR_UNSUPPORTED.  Computed as a 3xTF32
+ * split with fp32 accumulation in tensor memory (fp32-level accuracy; plain TF32
+ * would not meet the op's parity bound).  The epilogue applies, in this order:
+ *   + d_bias (may be NULL);
+ *   relu != 0: max(v, 0);
+ *   d_gate != NULL ([rows,out] fp32): v = gate > 0 ? v * gate_scale : 0  (the
+ *     backward of ReLU followed by dropout, with gate = the saved activation);
+ *   dropout_p > 0: v = keep ? v / (1 - p) : 0, keep decided by a counter-based hash
+ *     of (element index, dropout_seed) -- msda_dropout_backward regenerates it;
+ *   mask_mode 1: rows with d_row_mask[r] != 0 are written as zeros (mask after the
+ *     projection); 2: they are written as the bias (input masked before it);
+ *   + d_residual ([rows,out] fp32, may be NULL);
+ * and stores out_dtype MSDA_F32 or MSDA_BF16.  d_scratch: 2*in*out floats of
+ * device scratch (the split weight).
  */
+int msda_linear_fused(const float *d_x, const float *d_weight, const float *d_bias,
+                      const uint8_t *d_row_mask, int mask_mode, int relu,
+                      const float *d_gate, float gate_scale, float dropout_p,
+                      uint64_t dropout_seed, const float *d_residual, void *d_y,
+                      int rows, int in_features, int out_features, int out_dtype,
+                      float *d_scratch, void *stream);
+
+/* msda_linear_fused with bias and mask only (no ReLU, gate, dropout, residual). */
 int msda_linear256(const float *d_x, const float *d_weight, const float *d_bias,
                    const uint8_t *d_row_mask, int mask_mode, void *d_y, int rows,
                    int in_features, int out_features, int out_dtype,
                    float *d_scratch, void *stream);
 
-/* Weight gradient of the same projection: grad_weight[out][in] = grad_y^T x
+/* Weight gradient of the same layer: grad_weight[out][in] = grad_y^T x
  * over `rows` rows (overwritten), split-K over the rows on tcgen05 with 3xTF32
  * and a vector-reduction epilogue.  mask_mode as in msda_linear256: 1 drops
  * masked rows of grad_y, 2 drops masked rows of x. */
@@ -182,11 +198,19 @@ int msda_linear256_wgrad(const float *d_grad_y, const float *d_x,
                          float *d_grad_weight, int rows, int in_features,
                          int out_features, void *stream);
 
-/* Bias gradient of the same projection: grad_bias[width] = column sums of
- * grad_y[rows][width] (overwritten), width 128 or 256; rows with
+/* Bias gradient of the same layer: grad_bias[width] = column sums of
+ * grad_y[rows][width] (overwritten), width 128, 256 or 1024; rows with
  * d_row_mask[r] != 0 are skipped (pass NULL to sum every row). */
 int msda_colsum256(const float *d_grad_y, const uint8_t *d_row_mask,
                    float *d_grad_bias, int rows, int width, void *stream);
+
+/* Backward of msda_linear_fused's dropout: grad_out = grad_y * keep / (1 - p) with
+ * the keep decisions regenerated from (dropout_p, dropout_seed); when d_grad_bias
+ * is not NULL it also receives the column sums of grad_out (the bias gradient),
+ * from the same pass. */
+int msda_dropout_backward(const float *d_grad_y, float *d_grad_out,
+                          float *d_grad_bias, int rows, int width, float dropout_p,
+                          uint64_t dropout_seed, void *stream);
 
 /*
  * Host-buffer convenience entry points (what a cgo / JNI / ctypes caller

@@ -15,18 +15,19 @@ There is no CPU path: ops raise if the CUDA library is missing or a tensor is
 not on a CUDA device.
 """
 from . import _capi
-from .functional import (FusedMultiScaleDeformableAttnFunction, HostWorkspace,
+from .functional import (FusedFFNFunction, FusedMultiScaleDeformableAttnFunction, HostWorkspace,
                          Linear256Function, MultiScaleDeformableAttnFunction, ext_module,
-                         fused_supported, linear256, linear256_supported,
+                         ffn_supported, fused_ffn, fused_supported, linear256, linear256_supported,
                          fuse_frames_as_levels, ms_deform_attn_backward,
                          ms_deform_attn_forward)
-from .modules import (MulFramesMultiScaleDeformableAttentionNumFrames3,
+from .modules import (FFN, MulFramesMultiScaleDeformableAttentionNumFrames3,
                       MulFramesMultiScaleDeformableAttentionNumFrames5,
                       MulFramesMultiScaleDeformablePoseAttentionNumFrames3,
                       MulFramesMultiScaleDeformablePoseAttentionNumFrames5,
                       MultiScaleDeformableAttention,
                       MultiScaleDeformablePoseAttention)
-from .registry import ATTENTION, OPERA_ATTENTION, build_attention, install
+from .registry import (ATTENTION, FEEDFORWARD_NETWORK, OPERA_ATTENTION, build_attention,
+                       build_feedforward_network, install)
 
 __version__ = '0.1.0'
 
@@ -34,7 +35,8 @@ __all__ = [
     'MultiScaleDeformableAttnFunction', 'ext_module', 'ms_deform_attn_forward',
     'ms_deform_attn_backward', 'fuse_frames_as_levels', 'HostWorkspace',
     'FusedMultiScaleDeformableAttnFunction', 'fused_supported', 'Linear256Function',
-    'linear256', 'linear256_supported',
+    'linear256', 'linear256_supported', 'FusedFFNFunction', 'fused_ffn', 'ffn_supported', 'FFN',
+    'FEEDFORWARD_NETWORK', 'build_feedforward_network',
     'MultiScaleDeformableAttention', 'MultiScaleDeformablePoseAttention',
     'MulFramesMultiScaleDeformablePoseAttentionNumFrames3',
     'MulFramesMultiScaleDeformablePoseAttentionNumFrames5',

@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = (
     'msda_abi_version', 'msda_last_error', 'msda_launch_count',
     'msda_kernel_name', 'msda_forward', 'msda_backward', 'msda_fused_forward',
     'msda_fused_backward', 'msda_linear256', 'msda_linear256_wgrad',
-    'msda_colsum256',
+    'msda_colsum256', 'msda_linear_fused', 'msda_dropout_backward',
     'msda_workspace_create', 'msda_workspace_destroy', 'msda_workspace_set_piece_bytes',
     'msda_host_alloc',
     'msda_host_free', 'msda_forward_host',
@@ -57,6 +57,12 @@ def _declare(lib):
     lib.msda_linear256.argtypes = [c_void_p] * 4 + [c_int, c_void_p] + [c_int] * 4 + [c_void_p, c_void_p]
     lib.msda_linear256_wgrad.restype = c_int
     lib.msda_linear256_wgrad.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]
+    lib.msda_linear_fused.restype = c_int
+    lib.msda_linear_fused.argtypes = ([c_void_p] * 4 + [c_int, c_int, c_void_p, ctypes.c_float, ctypes.c_float,
+                                      ctypes.c_uint64, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p, c_void_p])
+    lib.msda_dropout_backward.restype = c_int
+    lib.msda_dropout_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_float,
+                                          ctypes.c_uint64, c_void_p]
     lib.msda_colsum256.restype = c_int
     lib.msda_colsum256.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
     lib.msda_workspace_create.restype = c_int

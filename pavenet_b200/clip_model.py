@@ -38,6 +38,7 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import modules
 from .modules import (MulFramesMultiScaleDeformableAttentionNumFrames3,
                       MulFramesMultiScaleDeformablePoseAttentionNumFrames3,
                       MultiScaleDeformableAttention)
@@ -79,13 +80,9 @@ class SinePositionalEncoding(nn.Module):
         return torch.cat((py, px), 3).permute(0, 3, 1, 2)
 
 
-class FFN(nn.Module):
-    def __init__(self, dims=256, hidden=1024, drop=0.1):
-        super().__init__()
-        self.fc1, self.fc2, self.drop = nn.Linear(dims, hidden), nn.Linear(hidden, dims), nn.Dropout(drop)
-
-    def forward(self, x):
-        return x + self.drop(self.fc2(self.drop(F.relu(self.fc1(x)))))
+def FFN(dims=256, hidden=1024, drop=0.1):
+    """feedforward_channels=1024, ffn_dropout=0.1 (config lines 54-56): x + drop(fc2(drop(relu(fc1(x)))))."""
+    return modules.FFN(embed_dims=dims, feedforward_channels=hidden, ffn_drop=drop)
 
 
 class SelfAttention(nn.Module):
@@ -104,7 +101,9 @@ class SelfAttention(nn.Module):
 class EncoderLayer(nn.Module):
     def __init__(self, value_dtype):
         super().__init__()
-        self.attn = MultiScaleDeformableAttention(embed_dims=256, value_dtype=value_dtype)
+        # batch_first: tokens stay (frames, S, 256) through the encoder, so no projection needs a
+        # transposing copy (a constructor option of the reference class, multi_scale_deform_attn.py:244)
+        self.attn = MultiScaleDeformableAttention(embed_dims=256, value_dtype=value_dtype, batch_first=True)
         self.norm1, self.ffn, self.norm2 = nn.LayerNorm(256), FFN(), nn.LayerNorm(256)
 
     def forward(self, x, pos, mask, ref, shapes, lsi):
@@ -207,6 +206,14 @@ class PaveNetR50(nn.Module):
         self.layer1.eval()
         return self
 
+    #: diagnostic hook: set to a callable(name) to get a call at each phase boundary of
+    #: forward_train (tools/phase_step.py synchronises and timestamps there)
+    phase_hook = None
+
+    def _mark(self, name):
+        if self.phase_hook is not None:
+            self.phase_hook(name)
+
     # ------------------------------------------------------------------ graph
     def extract_feat(self, images):                   # (Bc, T, 3, H, W) -> 4 levels of (Bc*T, 256, h, w)
         x = images.flatten(0, 1).contiguous(memory_format=torch.channels_last)
@@ -233,24 +240,26 @@ class PaveNetR50(nn.Module):
         T, K, Bc = self.T, self.K, images.shape[0]
         H, W = images.shape[-2:]
         feats = self.extract_feat(images)
+        self._mark('backbone+neck')
         dev = images.device
         shapes_list = [tuple(f.shape[-2:]) for f in feats]
         shapes = torch.tensor(shapes_list, device=dev)
         lsi = torch.cat([shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]])
         masks = [torch.zeros((Bc * T, h, w), dtype=torch.bool, device=dev) for h, w in shapes_list]
         pos = torch.cat([(self.pos_enc(m) + self.level_embeds[i].view(1, -1, 1, 1)).flatten(2)
-                         for i, m in enumerate(masks)], 2).permute(2, 0, 1)           # (S, Bc*T, 256)
-        x = torch.cat([f.flatten(2) for f in feats], 2).permute(2, 0, 1)               # (S, Bc*T, 256)
+                         for i, m in enumerate(masks)], 2).transpose(1, 2).contiguous()  # (Bc*T, S, 256)
+        x = torch.cat([f.flatten(2) for f in feats], 2).transpose(1, 2).contiguous()   # (Bc*T, S, 256)
         mask_flat = torch.cat([m.flatten(1) for m in masks], 1)                        # (Bc*T, S)
-        S = x.shape[0]
+        S = x.shape[1]
         grid = self.reference_grid(shapes_list, dev)
         ref_enc = grid[None, :, None, :].expand(Bc * T, S, 4, 2).contiguous()          # valid_ratios == 1
         for layer in self.encoder:
             x = layer(x, pos, mask_flat, ref_enc, shapes, lsi)
-        memory = x                                                                      # (S, Bc*T, 256)
+        memory = x.transpose(0, 1)             # (S, Bc*T, 256) view: what the decoders' modules take
+        self._mark('encoder')
 
         # two-stage proposals from the current frame
-        now = memory[:, T // 2::T].permute(1, 0, 2)                                    # (Bc, S, 256)
+        now = x[T // 2::T]                                                              # (Bc, S, 256)
         out_mem = self.enc_output_norm(self.enc_output(now))
         proposals = inverse_sigmoid(grid)[None].expand(Bc, S, 2)
         enc_cls = self.cls_branches[3](out_mem)
@@ -279,6 +288,7 @@ class PaveNetR50(nn.Module):
             kpt_out.append(ref.view(Bc, T, self.Qn, 2 * K))
             sigma_out.append(self.sigma_branches[lid](o).sigmoid())
 
+        self._mark('two-stage + pose decoder')
         losses = {}
         wh = images.new_tensor([W, H])
         last_match = None
@@ -288,7 +298,9 @@ class PaveNetR50(nn.Module):
             l_cls, l_kpt, match = self.stage_loss(cls, kpt, sigma, gt_kpts, gt_areas, wh)
             losses[tag + '.loss_cls'], losses[tag + '.loss_kpt'] = l_cls, l_kpt
             last_match = match
+        self._mark('matching + losses')
         losses.update(self.refine(memory, mask_flat, shapes, lsi, kpt_out[-1], last_match, gt_kpts))
+        self._mark('joint decoder')
         return losses
 
     # ------------------------------------------------------------------ losses
@@ -357,6 +369,7 @@ class PaveNetR50(nn.Module):
             tgts.append(gt_kpts[b][cols, T // 2, :, :2])
             wts.append((gt_kpts[b][cols, T // 2, :, 2:] > 0).float().expand(-1, -1, 2))
         poses, img_inds = torch.cat(poses, 1), torch.cat(img_inds)
+        group_sizes = [int(rows.shape[0]) for rows, _ in matches]
         G = img_inds.shape[0]
         if G == 0:
             zero = sum(p.sum() for p in self.refine_decoder.parameters()) * 0 + \
@@ -368,15 +381,17 @@ class PaveNetR50(nn.Module):
         q_pos, q = self.refine_query_embedding.weight.split(256, 1)
         query = q[None].expand(G, -1, -1).permute(1, 0, 2)                              # (K, G, 256)
         q_pos = q_pos[None].expand(G, -1, -1).permute(1, 0, 2)
-        mem = memory.view(S, -1, T, 256)[:, img_inds]                                   # (S, G, T, 256)
-        mask = mask_flat.view(-1, T, S)[img_inds]                                       # (G, T, S)
+        # the reference gathers memory[:, img_inds] -> (S, G, T, 256) here; the persons of a clip
+        # share its tokens instead (value_group_sizes), so nothing is gathered or re-projected
+        mem = memory.transpose(0, 1).reshape(-1, T, S, 256).permute(2, 0, 1, 3)         # (S, Bc, T, 256) view
+        mask = mask_flat.view(-1, T, S)                                                 # (Bc, T, S)
         tgt, wt = torch.cat(tgts), torch.cat(wts)
         n_valid = reduce_mean(wt.sum().detach()[None]).clamp(min=1).item()
         losses = {}
         for lid, layer in enumerate(self.refine_decoder):
             ref_in = ref[:, :, None, :].expand(-1, -1, 4, -1)                           # (T*G, K, L, 2)
             query = layer(query, q_pos, value=mem, key_padding_mask=mask, reference_points=ref_in,
-                          spatial_shapes=shapes, level_start_index=lsi)
+                          spatial_shapes=shapes, level_start_index=lsi, value_group_sizes=group_sizes)
             o = query.permute(1, 0, 2)                                                  # (G, K, 256)
             deltas = torch.cat([self.refine_kpt[t][lid](o) for t in range(T)], 0)       # (T*G, K, 2)
             new_ref = (deltas + inverse_sigmoid(ref)).sigmoid()
@@ -395,8 +410,9 @@ def build_optimizer(model):
             continue
         backbone = name.startswith(('stem', 'layer1', 'layer2', 'layer3', 'layer4'))
         (slow if backbone or 'sampling_offsets' in name else fast).append(p)
+    on_gpu = all(p.is_cuda for p in fast + slow)
     return torch.optim.AdamW([{'params': fast, 'lr': 2e-5}, {'params': slow, 'lr': 2e-6}],
-                             weight_decay=1e-4)
+                             weight_decay=1e-4, fused=on_gpu)   # one multi-tensor kernel per group
 
 
 def synthetic_clip_batch(clips, device, seed, height=800, width=1333, num_frames=3, num_keypoints=15):

@@ -1,26 +1,28 @@
-// linear256_tc.cu — the 256 -> 256 projections around the sampling op
-// (value_proj, and the input-gradient of any such Linear) on Blackwell's 5th
-// generation tensor cores, with fp32-level accuracy.
+// linear256_tc.cu — the fp32 Linear layers around the sampling op on Blackwell's 5th
+// generation tensor cores, with fp32-level accuracy: value_proj, output_proj,
+// sampling_offsets, attention_weights (widths 128 / 256), the 256 <-> 1024 feed-forward
+// pair of the transformer layers, and the input-, weight- and bias-gradients of each.
 //
-//   Y[rows, 256] = X[rows, 256] * W^T + bias        W is (out=256, in=256), row-major
+//   Y[rows, out] = epilogue(X[rows, in] * W^T)        W is (out, in), row-major
 //
-// after the sampling kernels, these fp32 GEMMs
-// are the largest cost of an attention-module call (cuBLAS runs them as SIMT
-// sgemm because PyTorch keeps TF32 off by default, and so does the reference).
-// Plain TF32 would break the 1e-4 parity contract, so the product is computed
-// as a 3xTF32 split:  x = x_hi + x_lo, w = w_hi + w_lo (hi = top 19 bits),
+// after the sampling kernels, these fp32 GEMMs are
+// the largest cost of an attention-module call and of a transformer layer (cuBLAS runs
+// them as SIMT sgemm because PyTorch keeps TF32 off by default, and so does the
+// reference).  Plain TF32 would break the 1e-4 parity contract, so the product is
+// computed as a 3xTF32 split:  x = x_hi + x_lo, w = w_hi + w_lo (hi = top 19 bits),
 //   x*w ~= x_hi*w_hi + x_hi*w_lo + x_lo*w_hi        (error ~2^-21 per product)
 // accumulated in fp32 in tensor memory.
 //
-// Structure (one CTA = one 128-row tile, 128 threads, 1 CTA / SM):
-//   TMA (cp.async.bulk.tensor, SWIZZLE_128B) streams X and the pre-split W in
-//   8 K-chunks of 32 floats through a 2-stage shared-memory ring; the threads
+// Structure (one CTA = one 128-row x NT-column tile, NT = min(out, 256)):
+//   TMA (cp.async.bulk.tensor, 64- or 128-byte swizzle) streams X and the pre-split W in
+//   K-chunks of 16 or 32 floats through a 2-stage shared-memory ring; the threads
 //   split the X chunk into hi / lo in place; one thread issues
-//   tcgen05.mma.kind::tf32 (M=128, N=256, K=8) x 3 per K-step into a 128x256 fp32
+//   tcgen05.mma.kind::tf32 (M=128, N=NT, K=8) x 3 per K-step into a 128 x NT fp32
 //   accumulator in TMEM; tcgen05.commit -> mbarrier releases the stage; the
-//   epilogue reads TMEM with tcgen05.ld, adds bias, applies the padding mask
-//   and stores fp32 or bf16 rows — the (B, S, M, D) layout the sampling kernels
-//   read, so no further pass touches the projected value.
+//   epilogue reads TMEM with tcgen05.ld and applies, in this order, bias, ReLU, a
+//   gate (the backward of ReLU + dropout), dropout, the padding mask and a residual,
+//   then stores fp32 or bf16 rows — for value_proj the (B, S, M, D) layout the
+//   sampling kernels read, so no further pass touches the projected value.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -34,19 +36,18 @@ namespace {
 constexpr int kBM = 128;           // rows per CTA
 constexpr int kStages = 2;
 constexpr int kUmmaK = 8;          // tf32 MMA K
-// in / out features are 128 or 256 (template parameters KIN / NOUT below): 256 -> 256 for
-// value_proj, output_proj and the encoder's sampling_offsets, 256 -> 128 for its
-// attention_weights, 128 -> 256 for that layer's input gradient.
+// in features KIN are 128, 256 or 1024; out features are cut into column tiles of
+// NT = 128 or 256 (template parameters below).
 
 // BK = floats per K chunk = one swizzle span: 32 (128-byte swizzle, 192 KiB of shared
 // memory, one CTA per SM) or 16 (64-byte swizzle, 96 KiB, two CTAs per SM so one tile's
 // epilogue overlaps the other's main loop).
-template <int BK, int KIN, int NOUT>
+template <int BK, int KIN, int NT>
 struct Cfg {
   static constexpr int kBK = BK;
   static constexpr int kChunks = KIN / BK;
   static constexpr uint32_t kABytes = kBM * BK * 4;
-  static constexpr uint32_t kBBytes = NOUT * BK * 4;
+  static constexpr uint32_t kBBytes = NT * BK * 4;
   static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // A_hi, A_lo, B_hi, B_lo
   static constexpr uint32_t kTxBytes = kABytes + 2 * kBBytes;          // what TMA delivers per stage
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 128 /*barriers*/;
@@ -121,6 +122,20 @@ __global__ void split_weight_kernel(const float* __restrict__ w, float* __restri
   }
 }
 
+// Counter-based dropout: element (row, col) of a (rows, n_total) matrix is kept iff a
+// 32-bit mix of its linear index and the call's seed is >= threshold = p * 2^32.  The
+// backward regenerates the same decision from the seed (dropout_backward kernel below).
+__device__ __forceinline__ bool dropout_keep(uint32_t idx, uint32_t seed_lo, uint32_t seed_hi,
+                                             uint32_t threshold) {
+  uint32_t x = (idx ^ seed_lo) * 0x9E3779B1u;
+  x ^= x >> 16;
+  x = (x + seed_hi) * 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x >= threshold;
+}
+
 template <typename OT>
 __device__ __forceinline__ void store_chunk(OT* row_ptr, const float (&v)[32]);
 template <>
@@ -146,18 +161,18 @@ __device__ __forceinline__ void store_chunk<__nv_bfloat16>(__nv_bfloat16* p, con
 // mask_mode: 0 none; 1 masked rows are written as zeros (mask applied after the
 // projection, multi_scale_deform_attn.py:369-371); 2 masked rows are written as
 // the bias (mask applied to the input before it, transformer.py:1706-1711).
+// (LinearEpilogue is declared in msda_kernels.h.)
 constexpr int kThreads = 160;   // warps 0-3: split, MMA issue (thread 0), epilogue; warp 4: TMA producer
 
-template <typename OT, int BK, int KIN, int NOUT>
+template <typename OT, int BK, int KIN, int NT>
 __global__ void __launch_bounds__(kThreads, BK == 32 ? 1 : 2)
 linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
                         const __grid_constant__ CUtensorMap map_whi,
-                        const __grid_constant__ CUtensorMap map_wlo, const float* __restrict__ bias,
-                        const uint8_t* __restrict__ row_mask, int mask_mode, OT* __restrict__ y,
-                        int rows) {
-  using C = Cfg<BK, KIN, NOUT>;
+                        const __grid_constant__ CUtensorMap map_wlo, const LinearEpilogue ep,
+                        OT* __restrict__ y, int rows, int n_total) {
+  using C = Cfg<BK, KIN, NT>;
   constexpr int kBK = C::kBK, kChunks = C::kChunks;
-  constexpr uint32_t kIdesc = idesc_tf32(NOUT, false);
+  constexpr uint32_t kIdesc = idesc_tf32(NT, false);
   constexpr uint32_t kABytes = C::kABytes, kBBytes = C::kBBytes, kStageBytes = C::kStageBytes,
                      kTxBytes = C::kTxBytes;
   extern __shared__ uint8_t smem_raw[];
@@ -169,11 +184,14 @@ linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kStages * kStageBytes + 32);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int row0 = blockIdx.x * kBM;
+  // column tiles of one row tile are neighbours in the grid, so they share X through L2
+  const int n_tiles = n_total / NT;
+  const int row0 = (blockIdx.x / n_tiles) * kBM;
+  const int n0 = (blockIdx.x % n_tiles) * NT;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "n"(NOUT));
+                 "n"(NT));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
@@ -196,8 +214,8 @@ linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
     const uint32_t bar = full0 + 8 * s, a = stage_addr(s);
     mbar_expect_tx(bar, kTxBytes);
     tma_load_2d(a, &map_x, bar, chunk * kBK, row0);                        // A (hi, split in place)
-    tma_load_2d(a + 2 * kABytes, &map_whi, bar, chunk * kBK, 0);           // B_hi
-    tma_load_2d(a + 2 * kABytes + kBBytes, &map_wlo, bar, chunk * kBK, 0); // B_lo
+    tma_load_2d(a + 2 * kABytes, &map_whi, bar, chunk * kBK, n0);           // B_hi
+    tma_load_2d(a + 2 * kABytes + kBBytes, &map_wlo, bar, chunk * kBK, n0); // B_lo
   };
   if (warp == 4) {
     // ---- TMA producer: keeps the ring full; a stage is refilled as soon as the MMAs that
@@ -255,10 +273,14 @@ linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
     // epilogue: warp w owns TMEM lanes 32w .. 32w+31 = rows of the tile
     const int r = row0 + tid;
     const bool in_range = r < rows;
-    const bool masked = in_range && row_mask != nullptr && mask_mode != 0 && row_mask[r] != 0;
-    OT* yrow = y + static_cast<int64_t>(in_range ? r : 0) * NOUT;
+    const bool masked = in_range && ep.row_mask != nullptr && ep.mask_mode != 0 && ep.row_mask[r] != 0;
+    const int64_t row_off = static_cast<int64_t>(in_range ? r : 0) * n_total + n0;
+    OT* yrow = y + row_off;
+    const float* gate = ep.gate ? ep.gate + row_off : nullptr;
+    const float* res = ep.residual ? ep.residual + row_off : nullptr;
+    const uint32_t drop_idx0 = static_cast<uint32_t>(row_off);
   #pragma unroll 1
-    for (int c0 = 0; c0 < NOUT; c0 += 32) {
+    for (int c0 = 0; c0 < NT; c0 += 32) {
       uint32_t u[32];
       const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + c0;
       asm volatile(
@@ -274,10 +296,37 @@ linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
       float v[32];
   #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float b = bias ? __ldg(bias + c0 + j) : 0.f;
+        const float b = ep.bias ? __ldg(ep.bias + n0 + c0 + j) : 0.f;
         float acc = __uint_as_float(u[j]) + b;
-        if (masked) acc = (mask_mode == 1) ? 0.f : b;
+        if (masked) acc = (ep.mask_mode == 1) ? 0.f : b;
         v[j] = acc;
+      }
+      if (ep.relu) {
+  #pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (gate != nullptr && in_range) {
+  #pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 g = __ldcs(reinterpret_cast<const float4*>(gate + c0 + j));
+          v[j] = g.x > 0.f ? v[j] * ep.gate_scale : 0.f;
+          v[j + 1] = g.y > 0.f ? v[j + 1] * ep.gate_scale : 0.f;
+          v[j + 2] = g.z > 0.f ? v[j + 2] * ep.gate_scale : 0.f;
+          v[j + 3] = g.w > 0.f ? v[j + 3] * ep.gate_scale : 0.f;
+        }
+      }
+      if (ep.dropout_threshold != 0u) {
+  #pragma unroll
+        for (int j = 0; j < 32; ++j)
+          v[j] = dropout_keep(drop_idx0 + c0 + j, ep.seed_lo, ep.seed_hi, ep.dropout_threshold)
+                     ? v[j] * ep.dropout_scale : 0.f;
+      }
+      if (res != nullptr && in_range) {
+  #pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 g = __ldcs(reinterpret_cast<const float4*>(res + c0 + j));
+          v[j] += g.x; v[j + 1] += g.y; v[j + 2] += g.z; v[j + 3] += g.w;
+        }
       }
       if (in_range) store_chunk<OT>(yrow + c0, v);
     }
@@ -285,7 +334,7 @@ linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(NOUT));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(NT));
   }
 }
 
@@ -355,8 +404,12 @@ template <int MOUT, int NIN>
 __global__ void __launch_bounds__(kThreads, 1)
 linear256_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                        const uint8_t* __restrict__ row_mask, int zero_dy, int zero_x,
-                       float* __restrict__ dw, int rows, int rows_per_cta) {
+                       float* __restrict__ dw, int rows, int rows_per_cta, int n_tiles, int in_total) {
+  // MOUT x NIN is one tile of dW; blockIdx.y walks the tiles of a wider weight
+  // (column blocks of dY select the tile's output rows, column blocks of X its inputs)
   using W = WgCfg<MOUT, NIN>;
+  const int m_t = blockIdx.y / n_tiles, n_t = blockIdx.y % n_tiles;
+  dw += static_cast<int64_t>(m_t) * MOUT * in_total + n_t * NIN;
   constexpr uint32_t kSlabA = W::kSlabA, kSlabB = W::kSlabB, kStageBytes = W::kStageBytes;
   constexpr uint32_t kIdescMN = idesc_tf32(NIN, true);
   extern __shared__ uint8_t smem_raw[];
@@ -398,8 +451,8 @@ linear256_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
         if (c >= kWgStages) mbar_wait(done0 + 8 * s, ((c / kWgStages) - 1) & 1);
         const uint32_t bar = full0 + 8 * s, a = base + s * kStageBytes;
         mbar_expect_tx(bar, kSlabA + kSlabB);
-        tma_load_3d(a, &map_dy, bar, 0, row_begin + c * kWgRows, 0);
-        tma_load_3d(a + 2 * kSlabA, &map_x, bar, 0, row_begin + c * kWgRows, 0);
+        tma_load_3d(a, &map_dy, bar, 0, row_begin + c * kWgRows, m_t * (MOUT / 32));
+        tma_load_3d(a + 2 * kSlabA, &map_x, bar, 0, row_begin + c * kWgRows, n_t * (NIN / 32));
       }
     }
   } else {
@@ -442,7 +495,7 @@ linear256_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
     // epilogue: lane = output row o within the half, 32 input columns per TMEM load
 #pragma unroll 1
     for (int h = 0; h < W::kHalves; ++h) {
-      float* drow = dw + static_cast<int64_t>(h * 128 + tid) * NIN;
+      float* drow = dw + static_cast<int64_t>(h * 128 + tid) * in_total;
 #pragma unroll 1
       for (int c0 = 0; c0 < NIN; c0 += 32) {
         uint32_t u[32];
@@ -503,91 +556,119 @@ bool make_map(CUtensorMap* map, const float* ptr, int rows, int width, int box_r
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// (rows x width) fp32 viewed as {32 floats, rows, width/32 column blocks}: one box = a 16-row slab
-// laid out block-major, each block a run of 128-byte rows (MN-major SW128_32B operand)
-bool make_map_mn(CUtensorMap* map, const float* ptr, int rows, int width) {
+// (rows x width) fp32 viewed as {32 floats, rows, width/32 column blocks}: one box = a 16-row slab of
+// `tile` columns laid out block-major, each block a run of 128-byte rows (MN-major SW128_32B operand)
+bool make_map_mn(CUtensorMap* map, const float* ptr, int rows, int width, int tile) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   const cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(width / 32)};
   const cuuint64_t strides[2] = {static_cast<cuuint64_t>(width) * 4, 128};
-  const cuuint32_t box[3] = {32, static_cast<cuuint32_t>(kWgRows), static_cast<cuuint32_t>(width / 32)};
+  const cuuint32_t box[3] = {32, static_cast<cuuint32_t>(kWgRows), static_cast<cuuint32_t>(tile / 32)};
   const cuuint32_t estr[3] = {1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename OT, int BK, int KIN, int NOUT>
-cudaError_t launch_variant(const float* x, const float* w_hi, const float* w_lo, const float* bias,
-                           const uint8_t* row_mask, int mask_mode, void* y, int rows, cudaStream_t st) {
+template <typename OT, int BK, int KIN, int NT>
+cudaError_t launch_variant(const float* x, const float* w_hi, const float* w_lo, const LinearEpilogue& ep,
+                           void* y, int rows, int n_total, cudaStream_t st) {
   CUtensorMap mx, mhi, mlo;
-  if (!make_map(&mx, x, rows, KIN, kBM, BK) || !make_map(&mhi, w_hi, NOUT, KIN, NOUT, BK) ||
-      !make_map(&mlo, w_lo, NOUT, KIN, NOUT, BK))
+  if (!make_map(&mx, x, rows, KIN, kBM, BK) || !make_map(&mhi, w_hi, n_total, KIN, NT, BK) ||
+      !make_map(&mlo, w_lo, n_total, KIN, NT, BK))
     return cudaErrorNotSupported;
-  constexpr uint32_t smem = Cfg<BK, KIN, NOUT>::kSmemBytes;
-  const cudaError_t e = cudaFuncSetAttribute(linear256_tf32x3_kernel<OT, BK, KIN, NOUT>,
+  constexpr uint32_t smem = Cfg<BK, KIN, NT>::kSmemBytes;
+  const cudaError_t e = cudaFuncSetAttribute(linear256_tf32x3_kernel<OT, BK, KIN, NT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  const unsigned grid = (rows + kBM - 1) / kBM;
-  linear256_tf32x3_kernel<OT, BK, KIN, NOUT><<<grid, kThreads, smem, st>>>(
-      mx, mhi, mlo, bias, row_mask, mask_mode, static_cast<OT*>(y), rows);
+  const unsigned grid = static_cast<unsigned>((rows + kBM - 1) / kBM) * (n_total / NT);
+  linear256_tf32x3_kernel<OT, BK, KIN, NT><<<grid, kThreads, smem, st>>>(
+      mx, mhi, mlo, ep, static_cast<OT*>(y), rows, n_total);
   return cudaGetLastError();
 }
 
-template <int KIN, int NOUT>
-cudaError_t launch_shape(const float* x, const float* w_hi, const float* w_lo, const float* bias,
-                         const uint8_t* row_mask, int mask_mode, void* y, int rows, int out_dtype,
-                         cudaStream_t st) {
-  const bool bk32 = tuning().linear_bk == 32;
+template <int KIN, int NT>
+cudaError_t launch_shape(const float* x, const float* w_hi, const float* w_lo, const LinearEpilogue& ep,
+                         void* y, int rows, int n_total, int out_dtype, cudaStream_t st) {
+  // the 32-float K-chunk variant exists for the 256-wide projections only (tuning knob)
+  if (KIN == 256 && tuning().linear_bk == 32) {
+    if (out_dtype == MSDA_BF16)
+      return launch_variant<__nv_bfloat16, 32, 256, NT>(x, w_hi, w_lo, ep, y, rows, n_total, st);
+    return launch_variant<float, 32, 256, NT>(x, w_hi, w_lo, ep, y, rows, n_total, st);
+  }
   if (out_dtype == MSDA_BF16)
-    return bk32 ? launch_variant<__nv_bfloat16, 32, KIN, NOUT>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st)
-                : launch_variant<__nv_bfloat16, 16, KIN, NOUT>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st);
-  return bk32 ? launch_variant<float, 32, KIN, NOUT>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st)
-              : launch_variant<float, 16, KIN, NOUT>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, st);
+    return launch_variant<__nv_bfloat16, 16, KIN, NT>(x, w_hi, w_lo, ep, y, rows, n_total, st);
+  return launch_variant<float, 16, KIN, NT>(x, w_hi, w_lo, ep, y, rows, n_total, st);
 }
 
-template <int MOUT, int NIN>
+template <int MT, int NT>
 cudaError_t launch_wgrad_shape(const float* dy, const float* x, const uint8_t* row_mask, int mask_mode,
-                               float* dw, int rows, int sm_count, cudaStream_t st) {
+                               float* dw, int rows, int in_total, int out_total, int sm_count,
+                               cudaStream_t st) {
   CUtensorMap mdy, mx;
-  if (!make_map_mn(&mdy, dy, rows, MOUT) || !make_map_mn(&mx, x, rows, NIN)) return cudaErrorNotSupported;
-  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * MOUT * NIN, st);
+  if (!make_map_mn(&mdy, dy, rows, out_total, MT) || !make_map_mn(&mx, x, rows, in_total, NT))
+    return cudaErrorNotSupported;
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * out_total * in_total, st);
   if (e != cudaSuccess) return e;
-  constexpr uint32_t smem = WgCfg<MOUT, NIN>::kSmemBytes;
-  e = cudaFuncSetAttribute(linear256_wgrad_kernel<MOUT, NIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  constexpr uint32_t smem = WgCfg<MT, NT>::kSmemBytes;
+  e = cudaFuncSetAttribute(linear256_wgrad_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  int rows_per_cta = (rows + sm_count - 1) / sm_count;
+  const int n_tiles = in_total / NT, tiles = (out_total / MT) * n_tiles;
+  // split-K CTAs per tile: one per SM whatever the tile count -- the tensor core accumulates with
+  // truncation, so the error grows with the length of a CTA's chain; short chains keep it at 3e-6
+  const int splits = sm_count;
+  int rows_per_cta = (rows + splits - 1) / splits;
   rows_per_cta = (rows_per_cta + kWgRows - 1) / kWgRows * kWgRows;
-  const unsigned grid = (rows + rows_per_cta - 1) / rows_per_cta;
-  linear256_wgrad_kernel<MOUT, NIN><<<grid, kThreads, smem, st>>>(
-      mdy, mx, row_mask, mask_mode == 1, mask_mode == 2, dw, rows, rows_per_cta);
+  const dim3 grid((rows + rows_per_cta - 1) / rows_per_cta, tiles);
+  linear256_wgrad_kernel<MT, NT><<<grid, kThreads, smem, st>>>(
+      mdy, mx, row_mask, mask_mode == 1, mask_mode == 2, dw, rows, rows_per_cta, n_tiles, in_total);
   note_launches(1);
   return cudaGetLastError();
 }
 
 // bias gradient: out[c] = sum over rows of dy[r][c] (rows with row_mask != 0 skipped).
 // torch's reduction over dim 0 of a (rows, 256) tensor runs at ~0.8 TB/s; this streams it once.
+// With a dropout threshold the pass is also the backward of the epilogue's dropout: it
+// regenerates each keep decision, writes dy_out = dy * keep * scale and sums that instead.
 template <int WIDTH>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ row_mask, float* __restrict__ out,
-              int rows, int rows_per_block) {
-  constexpr int CG = WIDTH / 4, RL = 256 / CG;      // column groups of 4 floats, row lanes
-  __shared__ float4 s_part[RL][CG];
+              float* __restrict__ dy_out, uint32_t threshold, float scale, uint32_t seed_lo,
+              uint32_t seed_hi, int rows, int rows_per_block) {
+  constexpr int CG = WIDTH / 4;                        // column groups of 4 floats
+  constexpr int RL = CG >= 256 ? 1 : 256 / CG;         // row lanes per pass
+  constexpr int PASSES = CG > 256 ? CG / 256 : 1;      // column passes (WIDTH 1024: 1)
+  static_assert(PASSES == 1, "WIDTH up to 1024");
+  __shared__ float4 s_part[RL][CG < 256 ? CG : 256];
   const int cg = threadIdx.x % CG, lane_r = threadIdx.x / CG;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int r = r0 + lane_r; r < r1; r += RL) {
     if (row_mask != nullptr && row_mask[r]) continue;
-    const float4 v = __ldcs(reinterpret_cast<const float4*>(dy + static_cast<int64_t>(r) * WIDTH) + cg);
+    const int64_t off = static_cast<int64_t>(r) * WIDTH + 4 * cg;
+    float4 v = __ldcs(reinterpret_cast<const float4*>(dy + off));
+    if (threshold != 0u) {
+      const uint32_t i = static_cast<uint32_t>(off);
+      v.x = dropout_keep(i, seed_lo, seed_hi, threshold) ? v.x * scale : 0.f;
+      v.y = dropout_keep(i + 1, seed_lo, seed_hi, threshold) ? v.y * scale : 0.f;
+      v.z = dropout_keep(i + 2, seed_lo, seed_hi, threshold) ? v.z * scale : 0.f;
+      v.w = dropout_keep(i + 3, seed_lo, seed_hi, threshold) ? v.w * scale : 0.f;
+      *reinterpret_cast<float4*>(dy_out + off) = v;
+    }
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  s_part[lane_r][cg] = acc;
-  __syncthreads();
-  if (lane_r == 0) {
-    for (int k = 1; k < RL; ++k) {
-      const float4 v = s_part[k][cg];
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  if (out == nullptr) return;
+  if (RL > 1) {
+    s_part[lane_r][cg] = acc;
+    __syncthreads();
+    if (lane_r == 0) {
+      for (int k = 1; k < RL; ++k) {
+        const float4 v = s_part[k][cg];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
     }
+  }
+  if (lane_r == 0) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + 4 * cg), "f"(acc.x), "f"(acc.y),
                  "f"(acc.z), "f"(acc.w)
                  : "memory");
@@ -596,53 +677,74 @@ colsum_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ row_mask
 
 }  // namespace
 
+static bool width_ok(int n) { return n == 128 || n == 256 || n == 1024; }
+
 bool linear_shape_supported(int in_features, int out_features) {
-  return (in_features == 256 && (out_features == 256 || out_features == 128)) ||
-         (in_features == 128 && out_features == 256);
+  // every pair of {128, 256, 1024} except the square 128 and 1024 (nothing in the model uses them)
+  return width_ok(in_features) && width_ok(out_features) &&
+         !(in_features == out_features && in_features != 256);
 }
 
-// y = x w^T + bias; returns cudaSuccess, cudaErrorNotSupported (shape, or no driver entry point),
-// or the launch error
-cudaError_t launch_linear256(const float* x, const float* w, const float* bias,
-                             const uint8_t* row_mask, int mask_mode, void* y, int rows, int in_features,
-                             int out_features, int out_dtype, float* scratch, cudaStream_t st) {
+// y = epilogue(x w^T); returns cudaSuccess, cudaErrorNotSupported (shape, or no driver entry
+// point), or the launch error
+cudaError_t launch_linear256(const float* x, const float* w, const LinearEpilogue& ep, void* y, int rows,
+                             int in_features, int out_features, int out_dtype, float* scratch,
+                             cudaStream_t st) {
   if (!linear_shape_supported(in_features, out_features)) return cudaErrorNotSupported;
   const int n = in_features * out_features;
   float* w_hi = scratch;
   float* w_lo = scratch + n;
   split_weight_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, w_hi, w_lo, n);
   note_launches(2);
-  if (in_features == 256 && out_features == 256)
-    return launch_shape<256, 256>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, out_dtype, st);
-  if (in_features == 256)
-    return launch_shape<256, 128>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, out_dtype, st);
-  return launch_shape<128, 256>(x, w_hi, w_lo, bias, row_mask, mask_mode, y, rows, out_dtype, st);
+  const bool wide = out_features != 128;      // column tiles of 256, or one of 128
+  switch (in_features) {
+    case 128:
+      return launch_shape<128, 256>(x, w_hi, w_lo, ep, y, rows, out_features, out_dtype, st);
+    case 256:
+      return wide ? launch_shape<256, 256>(x, w_hi, w_lo, ep, y, rows, out_features, out_dtype, st)
+                  : launch_shape<256, 128>(x, w_hi, w_lo, ep, y, rows, out_features, out_dtype, st);
+    default:
+      return wide ? launch_shape<1024, 256>(x, w_hi, w_lo, ep, y, rows, out_features, out_dtype, st)
+                  : launch_shape<1024, 128>(x, w_hi, w_lo, ep, y, rows, out_features, out_dtype, st);
+  }
 }
 
 // dW (out x in, fp32) = dY^T X; dW is overwritten
 cudaError_t launch_linear256_wgrad(const float* dy, const float* x, const uint8_t* row_mask,
                                    int mask_mode, float* dw, int rows, int in_features, int out_features,
                                    int sm_count, cudaStream_t st) {
-  if (in_features == 256 && out_features == 256)
-    return launch_wgrad_shape<256, 256>(dy, x, row_mask, mask_mode, dw, rows, sm_count, st);
-  if (in_features == 256 && out_features == 128)
-    return launch_wgrad_shape<128, 256>(dy, x, row_mask, mask_mode, dw, rows, sm_count, st);
-  if (in_features == 128 && out_features == 256)
-    return launch_wgrad_shape<256, 128>(dy, x, row_mask, mask_mode, dw, rows, sm_count, st);
-  return cudaErrorNotSupported;
+  if (!linear_shape_supported(in_features, out_features)) return cudaErrorNotSupported;
+  const bool m128 = out_features == 128, n128 = in_features == 128;
+  if (m128)
+    return launch_wgrad_shape<128, 256>(dy, x, row_mask, mask_mode, dw, rows, in_features, out_features,
+                                        sm_count, st);
+  if (n128)
+    return launch_wgrad_shape<256, 128>(dy, x, row_mask, mask_mode, dw, rows, in_features, out_features,
+                                        sm_count, st);
+  return launch_wgrad_shape<256, 256>(dy, x, row_mask, mask_mode, dw, rows, in_features, out_features,
+                                      sm_count, st);
 }
 
-cudaError_t launch_colsum256(const float* dy, const uint8_t* row_mask, float* out, int rows, int width,
-                             int sm_count, cudaStream_t st) {
-  if (width != 256 && width != 128) return cudaErrorNotSupported;
-  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * width, st);
-  if (e != cudaSuccess) return e;
+// out[width] = column sums of dy (optionally of dropout-backward(dy), also written to dy_out)
+cudaError_t launch_colsum256(const float* dy, const uint8_t* row_mask, float* out, float* dy_out,
+                             uint32_t threshold, float scale, uint32_t seed_lo, uint32_t seed_hi, int rows,
+                             int width, int sm_count, cudaStream_t st) {
+  if (!width_ok(width)) return cudaErrorNotSupported;
+  if (out != nullptr) {
+    const cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * width, st);
+    if (e != cudaSuccess) return e;
+  }
   const int blocks_wanted = sm_count * 8;
   int rows_per_block = (rows + blocks_wanted - 1) / blocks_wanted;
   rows_per_block = (rows_per_block + 7) / 8 * 8;
   const unsigned grid = (rows + rows_per_block - 1) / rows_per_block;
-  if (width == 256) colsum_kernel<256><<<grid, 256, 0, st>>>(dy, row_mask, out, rows, rows_per_block);
-  else colsum_kernel<128><<<grid, 256, 0, st>>>(dy, row_mask, out, rows, rows_per_block);
+#define MSDA_COLSUM(W_) \
+  colsum_kernel<W_><<<grid, 256, 0, st>>>(dy, row_mask, out, dy_out, threshold, scale, seed_lo, seed_hi, rows, \
+                                          rows_per_block)
+  if (width == 128) MSDA_COLSUM(128);
+  else if (width == 256) MSDA_COLSUM(256);
+  else MSDA_COLSUM(1024);
+#undef MSDA_COLSUM
   note_launches(1);
   return cudaGetLastError();
 }

@@ -279,28 +279,62 @@ int msda_fused_backward(const void* d_value, const int64_t* d_spatial_shapes,
   return MSDA_OK;
 }
 
+namespace {
+// p in [0, 1) -> keep threshold on a 32-bit hash and the survivor scale
+int dropout_params(const char* who, float p, uint32_t* threshold, float* scale) {
+  if (!(p >= 0.f) || p >= 1.f)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "%s: dropout_p must be in [0, 1), got %g", who, p);
+  *threshold = static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0);
+  *scale = *threshold ? 1.f / (1.f - p) : 1.f;
+  return MSDA_OK;
+}
+}  // namespace
+
+int msda_linear_fused(const float* d_x, const float* d_weight, const float* d_bias,
+                      const uint8_t* d_row_mask, int mask_mode, int relu, const float* d_gate,
+                      float gate_scale, float dropout_p, uint64_t dropout_seed,
+                      const float* d_residual, void* d_y, int rows, int in_features, int out_features,
+                      int out_dtype, float* d_scratch, void* stream) {
+  if (!d_x || !d_weight || !d_y || !d_scratch)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear_fused: NULL pointer argument");
+  if (rows <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear_fused: rows must be positive");
+  if (!linear_shape_supported(in_features, out_features))
+    return fail(MSDA_ERR_UNSUPPORTED,
+                "msda_linear_fused: (in, out) = (%d, %d): widths must be 128, 256 or 1024 (and not 128x128 / "
+                "1024x1024)", in_features, out_features);
+  if (out_dtype != MSDA_F32 && out_dtype != MSDA_BF16)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear_fused: out_dtype must be MSDA_F32 or MSDA_BF16");
+  if (mask_mode < 0 || mask_mode > 2 || (mask_mode != 0 && !d_row_mask))
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear_fused: bad mask_mode / row_mask");
+  if (misaligned16(d_x) || misaligned16(d_weight) || misaligned16(d_y) || misaligned16(d_scratch) ||
+      misaligned16(d_gate) || misaligned16(d_residual))
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_linear_fused needs 16-byte aligned buffers");
+  LinearEpilogue ep;
+  ep.bias = d_bias;
+  ep.row_mask = mask_mode ? d_row_mask : nullptr;
+  ep.mask_mode = mask_mode;
+  ep.relu = relu != 0;
+  ep.gate = d_gate;
+  ep.gate_scale = gate_scale;
+  const int rc = dropout_params("msda_linear_fused", dropout_p, &ep.dropout_threshold, &ep.dropout_scale);
+  if (rc) return rc;
+  ep.seed_lo = static_cast<uint32_t>(dropout_seed);
+  ep.seed_hi = static_cast<uint32_t>(dropout_seed >> 32);
+  ep.residual = d_residual;
+  const cudaError_t e = launch_linear256(d_x, d_weight, ep, d_y, rows, in_features, out_features, out_dtype,
+                                         d_scratch, static_cast<cudaStream_t>(stream));
+  if (e == cudaErrorNotSupported)
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_linear_fused: cuTensorMapEncodeTiled unavailable or failed");
+  if (e != cudaSuccess)
+    return fail(MSDA_ERR_CUDA, "msda_linear_fused launch failed: %s", cudaGetErrorString(e));
+  return MSDA_OK;
+}
+
 int msda_linear256(const float* d_x, const float* d_weight, const float* d_bias,
                    const uint8_t* d_row_mask, int mask_mode, void* d_y, int rows, int in_features,
                    int out_features, int out_dtype, float* d_scratch, void* stream) {
-  if (!d_x || !d_weight || !d_y || !d_scratch)
-    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256: NULL pointer argument");
-  if (rows <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256: rows must be positive");
-  if (!linear_shape_supported(in_features, out_features))
-    return fail(MSDA_ERR_UNSUPPORTED, "msda_linear256: (in, out) = (%d, %d) is not one of (256,256), (256,128), (128,256)",
-                in_features, out_features);
-  if (out_dtype != MSDA_F32 && out_dtype != MSDA_BF16)
-    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256: out_dtype must be MSDA_F32 or MSDA_BF16");
-  if (mask_mode < 0 || mask_mode > 2 || (mask_mode != 0 && !d_row_mask))
-    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256: bad mask_mode / row_mask");
-  if (misaligned16(d_x) || misaligned16(d_weight) || misaligned16(d_y) || misaligned16(d_scratch))
-    return fail(MSDA_ERR_UNSUPPORTED, "msda_linear256 needs 16-byte aligned buffers");
-  const cudaError_t e = launch_linear256(d_x, d_weight, d_bias, d_row_mask, mask_mode, d_y, rows,
-                                         in_features, out_features, out_dtype, d_scratch, static_cast<cudaStream_t>(stream));
-  if (e == cudaErrorNotSupported)
-    return fail(MSDA_ERR_UNSUPPORTED, "msda_linear256: cuTensorMapEncodeTiled unavailable or failed");
-  if (e != cudaSuccess)
-    return fail(MSDA_ERR_CUDA, "msda_linear256 launch failed: %s", cudaGetErrorString(e));
-  return MSDA_OK;
+  return msda_linear_fused(d_x, d_weight, d_bias, d_row_mask, mask_mode, 0, nullptr, 1.f, 0.f, 0, nullptr,
+                           d_y, rows, in_features, out_features, out_dtype, d_scratch, stream);
 }
 
 int msda_linear256_wgrad(const float* d_grad_y, const float* d_x, const uint8_t* d_row_mask,
@@ -310,8 +344,9 @@ int msda_linear256_wgrad(const float* d_grad_y, const float* d_x, const uint8_t*
     return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256_wgrad: NULL pointer argument");
   if (rows <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256_wgrad: rows must be positive");
   if (!linear_shape_supported(in_features, out_features))
-    return fail(MSDA_ERR_UNSUPPORTED, "msda_linear256_wgrad: (in, out) = (%d, %d) is not one of (256,256), (256,128), (128,256)",
-                in_features, out_features);
+    return fail(MSDA_ERR_UNSUPPORTED,
+                "msda_linear256_wgrad: (in, out) = (%d, %d): widths must be 128, 256 or 1024 (and not 128x128 / "
+                "1024x1024)", in_features, out_features);
   if (mask_mode < 0 || mask_mode > 2 || (mask_mode != 0 && !d_row_mask))
     return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear256_wgrad: bad mask_mode / row_mask");
   if (misaligned16(d_grad_y) || misaligned16(d_x) || misaligned16(d_grad_weight))
@@ -320,7 +355,8 @@ int msda_linear256_wgrad(const float* d_grad_y, const float* d_x, const uint8_t*
   const int rc = current_sm_count(&sms);
   if (rc) return rc;
   const cudaError_t e = launch_linear256_wgrad(d_grad_y, d_x, d_row_mask, mask_mode, d_grad_weight, rows,
-                                               in_features, out_features, sms, static_cast<cudaStream_t>(stream));
+                                               in_features, out_features, sms,
+                                               static_cast<cudaStream_t>(stream));
   if (e == cudaErrorNotSupported)
     return fail(MSDA_ERR_UNSUPPORTED, "msda_linear256_wgrad: cuTensorMapEncodeTiled unavailable or failed");
   if (e != cudaSuccess)
@@ -333,17 +369,44 @@ int msda_colsum256(const float* d_grad_y, const uint8_t* d_row_mask, float* d_gr
   if (!d_grad_y || !d_grad_bias)
     return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_colsum256: NULL pointer argument");
   if (rows <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_colsum256: rows must be positive");
-  if (width != 128 && width != 256)
-    return fail(MSDA_ERR_UNSUPPORTED, "msda_colsum256: width must be 128 or 256, got %d", width);
+  if (width != 128 && width != 256 && width != 1024)
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_colsum256: width must be 128, 256 or 1024, got %d", width);
   if (misaligned16(d_grad_y) || misaligned16(d_grad_bias))
     return fail(MSDA_ERR_UNSUPPORTED, "msda_colsum256 needs 16-byte aligned buffers");
   int sms = 0;
   const int rc = current_sm_count(&sms);
   if (rc) return rc;
-  const cudaError_t e = launch_colsum256(d_grad_y, d_row_mask, d_grad_bias, rows, width, sms,
-                                         static_cast<cudaStream_t>(stream));
+  const cudaError_t e = launch_colsum256(d_grad_y, d_row_mask, d_grad_bias, nullptr, 0u, 1.f, 0u, 0u, rows,
+                                         width, sms, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess)
     return fail(MSDA_ERR_CUDA, "msda_colsum256 launch failed: %s", cudaGetErrorString(e));
+  return MSDA_OK;
+}
+
+int msda_dropout_backward(const float* d_grad_y, float* d_grad_out, float* d_grad_bias, int rows,
+                          int width, float dropout_p, uint64_t dropout_seed, void* stream) {
+  if (!d_grad_y || !d_grad_out)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_dropout_backward: NULL pointer argument");
+  if (rows <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_dropout_backward: rows must be positive");
+  if (width != 128 && width != 256 && width != 1024)
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_dropout_backward: width must be 128, 256 or 1024, got %d", width);
+  if (misaligned16(d_grad_y) || misaligned16(d_grad_out) || misaligned16(d_grad_bias))
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_dropout_backward needs 16-byte aligned buffers");
+  uint32_t threshold = 0;
+  float scale = 1.f;
+  int rc = dropout_params("msda_dropout_backward", dropout_p, &threshold, &scale);
+  if (rc) return rc;
+  if (threshold == 0)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_dropout_backward: dropout_p rounds to zero; nothing to undo");
+  int sms = 0;
+  rc = current_sm_count(&sms);
+  if (rc) return rc;
+  const cudaError_t e = launch_colsum256(d_grad_y, nullptr, d_grad_bias, d_grad_out, threshold, scale,
+                                         static_cast<uint32_t>(dropout_seed),
+                                         static_cast<uint32_t>(dropout_seed >> 32), rows, width, sms,
+                                         static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess)
+    return fail(MSDA_ERR_CUDA, "msda_dropout_backward launch failed: %s", cudaGetErrorString(e));
   return MSDA_OK;
 }
 

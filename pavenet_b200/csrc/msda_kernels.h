@@ -41,17 +41,31 @@ cudaError_t launch_backward_fused(const void* value, const int64_t* shapes, cons
                                   float* grad_off, float* grad_logit, float* grad_loc,
                                   const Dims& d, int value_dtype, int sm_count, cudaStream_t st);
 
-// Y = X W^T + bias, dW = dY^T X and the bias gradient for the 128/256-wide projections of the
-// attention modules on tcgen05 (3xTF32), linear256_tc.cu
+// Y = epilogue(X W^T), dW = dY^T X and the bias gradient for the Linear layers of the
+// attention modules and transformer layers on tcgen05 (3xTF32), linear256_tc.cu.
+// What the GEMM epilogue does to the accumulator, in this order:
+struct LinearEpilogue {
+  const float* bias = nullptr;        // [out] added first
+  const uint8_t* row_mask = nullptr;  // [rows]; mask_mode 1: masked rows = 0, 2: masked rows = bias
+  int mask_mode = 0;
+  int relu = 0;                       // max(v, 0)
+  const float* gate = nullptr;        // [rows, out]: v = gate > 0 ? v * gate_scale : 0
+  float gate_scale = 1.f;
+  uint32_t dropout_threshold = 0;     // keep iff hash(index, seed) >= threshold; 0 = no dropout
+  float dropout_scale = 1.f;          // 1 / (1 - p)
+  uint32_t seed_lo = 0, seed_hi = 0;
+  const float* residual = nullptr;    // [rows, out] added last
+};
 bool linear_shape_supported(int in_features, int out_features);
-cudaError_t launch_linear256(const float* x, const float* w, const float* bias,
-                             const uint8_t* row_mask, int mask_mode, void* y, int rows, int in_features,
-                             int out_features, int out_dtype, float* scratch, cudaStream_t st);
+cudaError_t launch_linear256(const float* x, const float* w, const LinearEpilogue& ep, void* y, int rows,
+                             int in_features, int out_features, int out_dtype, float* scratch,
+                             cudaStream_t st);
 cudaError_t launch_linear256_wgrad(const float* dy, const float* x, const uint8_t* row_mask,
                                    int mask_mode, float* dw, int rows, int in_features, int out_features,
                                    int sm_count, cudaStream_t st);
-cudaError_t launch_colsum256(const float* dy, const uint8_t* row_mask, float* out, int rows, int width,
-                             int sm_count, cudaStream_t st);
+cudaError_t launch_colsum256(const float* dy, const uint8_t* row_mask, float* out, float* dy_out,
+                             uint32_t threshold, float scale, uint32_t seed_lo, uint32_t seed_hi, int rows,
+                             int width, int sm_count, cudaStream_t st);
 
 // adds n to the library-wide launch counter (msda_launch_count)
 void note_launches(int n);

@@ -20,6 +20,7 @@ __all__ = [
     'ms_deform_attn_backward', 'fuse_frames_as_levels', 'BF16_GRAD_VALUE_ATOMICS',
     'HostWorkspace', 'FusedMultiScaleDeformableAttnFunction', 'fused_supported',
     'Linear256Function', 'linear256', 'linear256_supported',
+    'FusedFFNFunction', 'fused_ffn', 'ffn_supported',
 ]
 
 #: When value is stored in bf16, accumulate grad_value in an fp32 scratch
@@ -434,49 +435,115 @@ class FusedMultiScaleDeformableAttnFunction(Function):
 
 
 # ---------------------------------------------------------------------------
-# the 128/256-wide projections on the tcgen05 tensor cores
+# fp32 Linear layers on the tcgen05 tensor cores
 # ---------------------------------------------------------------------------
-_LINEAR_SHAPES = ((256, 256), (128, 256), (256, 128))     # weight.shape = (out, in)
+_LINEAR_WIDTHS = (128, 256, 1024)
+
+
+def _linear_shape_ok(n_out, n_in):
+    return (n_out in _LINEAR_WIDTHS and n_in in _LINEAR_WIDTHS
+            and not (n_out == n_in and n_in != 256))
 
 
 def linear256_supported(x, weight):
     """True when `linear256` has kernels for these tensors: CUDA, fp32, weight
-    (out, in) one of (256,256), (128,256), (256,128) -- every projection of an
-    embed_dims = 256 attention module with num_heads*levels*points in {64, 128}
-    (offsets 128/256 wide, attention weights 128 wide)."""
+    (out, in) with both widths in {128, 256, 1024} (128x128 and 1024x1024
+    excluded) -- every projection of an embed_dims = 256 attention module whose
+    offsets / attention weights are 128 or 256 wide, and the 256 <-> 1024
+    feed-forward pair."""
     return (x.is_cuda and weight.is_cuda and x.dtype == torch.float32
-            and weight.dtype == torch.float32 and tuple(weight.shape) in _LINEAR_SHAPES
+            and weight.dtype == torch.float32 and weight.dim() == 2
+            and _linear_shape_ok(*weight.shape)
             and x.shape[-1] == weight.shape[1] and x.numel() > 0)
 
 
-def _linear256_raw(x2d, weight, bias, row_mask, mask_mode, out_dtype):
+def _next_dropout_seed():
+    # drawn from the CPU generator: follows torch.manual_seed, costs no GPU work or sync
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def _linear_fused_raw(x2d, weight, bias=None, row_mask=None, mask_mode=0, relu=False, gate=None,
+                      gate_scale=1.0, dropout_p=0.0, seed=0, residual=None, out_dtype=torch.float32):
+    """One call of msda_linear_fused on 2-D contiguous fp32 tensors (see include/pavenet_msda.h
+    for the order of the epilogue steps)."""
     lib = _capi.load()
     rows = x2d.shape[0]
     n_out, n_in = weight.shape
     with torch.cuda.device(x2d.device):
         y = torch.empty((rows, n_out), dtype=out_dtype, device=x2d.device)
         scratch = torch.empty(2 * n_out * n_in, dtype=torch.float32, device=x2d.device)
-        status = lib.msda_linear256(
+        status = lib.msda_linear_fused(
             x2d.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(),
-            None if row_mask is None else row_mask.data_ptr(), mask_mode, y.data_ptr(), rows,
+            None if row_mask is None else row_mask.data_ptr(), mask_mode, int(relu),
+            None if gate is None else gate.data_ptr(), gate_scale, dropout_p, seed,
+            None if residual is None else residual.data_ptr(), y.data_ptr(), rows,
             n_in, n_out, _DTYPE_CODE[out_dtype], scratch.data_ptr(),
             torch.cuda.current_stream().cuda_stream)
-    _capi.check(status, 'msda_linear256')
+    _capi.check(status, 'msda_linear_fused')
     return y
 
 
+def _wgrad_raw(g, x2d, row_mask, mask_mode, n_out, n_in):
+    """dW (out, in) = g^T x2d, split-K on the tensor cores."""
+    lib = _capi.load()
+    with torch.cuda.device(g.device):
+        grad_w = torch.empty((n_out, n_in), dtype=torch.float32, device=g.device)
+        status = lib.msda_linear256_wgrad(
+            g.data_ptr(), x2d.data_ptr(), None if row_mask is None else row_mask.data_ptr(),
+            mask_mode, grad_w.data_ptr(), g.shape[0], n_in, n_out,
+            torch.cuda.current_stream().cuda_stream)
+    _capi.check(status, 'msda_linear256_wgrad')
+    return grad_w
+
+
+def _colsum_raw(g, row_mask=None):
+    """Column sums of g (rows, width): the bias gradient, one streaming pass."""
+    lib = _capi.load()
+    with torch.cuda.device(g.device):
+        out = torch.empty(g.shape[1], dtype=torch.float32, device=g.device)
+        status = lib.msda_colsum256(g.data_ptr(), None if row_mask is None else row_mask.data_ptr(),
+                                    out.data_ptr(), g.shape[0], g.shape[1],
+                                    torch.cuda.current_stream().cuda_stream)
+    _capi.check(status, 'msda_colsum256')
+    return out
+
+
+def _dropout_backward_raw(g, dropout_p, seed, want_bias):
+    """g * keep / (1 - p) with the forward's keep decisions, and its column sums."""
+    lib = _capi.load()
+    with torch.cuda.device(g.device):
+        out = torch.empty_like(g)
+        bias = torch.empty(g.shape[1], dtype=torch.float32, device=g.device) if want_bias else None
+        status = lib.msda_dropout_backward(g.data_ptr(), out.data_ptr(),
+                                           None if bias is None else bias.data_ptr(), g.shape[0],
+                                           g.shape[1], dropout_p, seed,
+                                           torch.cuda.current_stream().cuda_stream)
+    _capi.check(status, 'msda_dropout_backward')
+    return out, bias
+
+
+def _as_f32_2d(t, width):
+    t = t.reshape(-1, width)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
 class Linear256Function(Function):
-    """y = x W^T + b with the forward, the input-gradient GEMM, the weight
-    gradient and the bias gradient on hand-written kernels: the three GEMMs on
-    the tcgen05 tensor cores (3xTF32 split, fp32 accumulation in tensor memory),
-    the padding mask and the storage dtype folded into the epilogue.
+    """y = residual + dropout(x W^T + b) with the forward, the input-gradient GEMM,
+    the weight gradient and the bias gradient on hand-written kernels: the three
+    GEMMs on the tcgen05 tensor cores (3xTF32 split, fp32 accumulation in tensor
+    memory), the padding mask, the storage dtype, dropout and the residual folded
+    into the epilogue.
 
     mask_mode 1: masked rows of y are zero (mask after the projection,
     multi_scale_deform_attn.py:369-371); 2: the input rows are treated as zero,
-    so y = bias there (mask before it, transformer.py:1706-1711)."""
+    so y = bias there (mask before it, transformer.py:1706-1711).
+    residual / dropout_p: `identity + dropout(output_proj(x))`,
+    multi_scale_deform_attn.py:406-412 (not combinable with a mask)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, row_mask, mask_mode, out_dtype):
+    def forward(ctx, x, weight, bias, row_mask, mask_mode, out_dtype, residual=None, dropout_p=0.0):
         shape = x.shape
         n_out, n_in = weight.shape
         x2d = x.reshape(-1, n_in).contiguous()
@@ -486,12 +553,23 @@ class Linear256Function(Function):
             mask_u8 = row_mask.reshape(-1).to(torch.uint8).contiguous()
             if mask_u8.numel() != x2d.shape[0]:
                 raise RuntimeError('row_mask has %d entries for %d rows' % (mask_u8.numel(), x2d.shape[0]))
-        y = _linear256_raw(x2d, weight, None if bias is None else bias.contiguous(), mask_u8,
-                           mask_mode if mask_u8 is not None else 0, out_dtype)
+        if mask_u8 is not None and (residual is not None or dropout_p > 0):
+            raise RuntimeError('linear256: row_mask cannot be combined with residual / dropout')
+        res2d = None
+        if residual is not None:
+            if residual.shape != shape[:-1] + (n_out,) or out_dtype != torch.float32:
+                raise RuntimeError('linear256: residual must have the output shape; fp32 output only')
+            res2d = _as_f32_2d(residual, n_out)
+        seed = _next_dropout_seed() if dropout_p > 0 else 0
+        y = _linear_fused_raw(x2d, weight, None if bias is None else bias.contiguous(), mask_u8,
+                              mask_mode if mask_u8 is not None else 0, dropout_p=dropout_p, seed=seed,
+                              residual=res2d, out_dtype=out_dtype)
         ctx.save_for_backward(x2d, weight, mask_u8)
         ctx.mask_mode = mask_mode if mask_u8 is not None else 0
         ctx.has_bias = bias is not None
         ctx.x_shape = shape
+        ctx.dropout = (dropout_p, seed)
+        ctx.has_residual = residual is not None
         return y.view(*shape[:-1], n_out)
 
     @staticmethod
@@ -499,39 +577,98 @@ class Linear256Function(Function):
     def backward(ctx, grad_y):
         x2d, weight, mask_u8 = ctx.saved_tensors
         n_out, n_in = weight.shape
-        g = grad_y.reshape(-1, n_out)
-        if g.dtype != torch.float32:
-            g = g.float()
-        g = g.contiguous()
-        grad_x = grad_w = grad_b = None
+        g = _as_f32_2d(grad_y, n_out)
+        grad_x = grad_w = grad_b = grad_res = None
+        if ctx.has_residual and ctx.needs_input_grad[6]:
+            grad_res = grad_y
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        dropout_p, seed = ctx.dropout
+        if dropout_p > 0:
+            # undo the epilogue's dropout (same keep decisions); the pass also sums the bias gradient
+            g, grad_b = _dropout_backward_raw(g, dropout_p, seed, want_b)
+        elif want_b:
+            # column sums of dY in one streaming pass (masked rows skipped in mode 1)
+            grad_b = _colsum_raw(g, mask_u8 if ctx.mask_mode == 1 else None)
         if ctx.needs_input_grad[0]:
             # dX = dY W: the same kernel with W^T as the weight; masked rows get no gradient
-            grad_x = _linear256_raw(g, weight.t().contiguous(), None, mask_u8,
-                                    1 if ctx.mask_mode else 0, torch.float32).view(ctx.x_shape)
+            grad_x = _linear_fused_raw(g, weight.t().contiguous(), None, mask_u8,
+                                       1 if ctx.mask_mode else 0).view(ctx.x_shape)
         if ctx.needs_input_grad[1]:
             # dW = dY^T X, split-K on the tensor cores; mode 1 drops the masked rows of dY
             # (their outputs were forced to zero), mode 2 those of X (their inputs were)
-            lib = _capi.load()
-            with torch.cuda.device(g.device):
-                grad_w = torch.empty((n_out, n_in), dtype=torch.float32, device=g.device)
-                status = lib.msda_linear256_wgrad(
-                    g.data_ptr(), x2d.data_ptr(), None if mask_u8 is None else mask_u8.data_ptr(),
-                    ctx.mask_mode, grad_w.data_ptr(), g.shape[0], n_in, n_out,
-                    torch.cuda.current_stream().cuda_stream)
-            _capi.check(status, 'msda_linear256_wgrad')
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            # column sums of dY in one streaming pass (masked rows skipped in mode 1)
-            lib = _capi.load()
-            with torch.cuda.device(g.device):
-                grad_b = torch.empty(n_out, dtype=torch.float32, device=g.device)
-                status = lib.msda_colsum256(
-                    g.data_ptr(),
-                    mask_u8.data_ptr() if (mask_u8 is not None and ctx.mask_mode == 1) else None,
-                    grad_b.data_ptr(), g.shape[0], n_out, torch.cuda.current_stream().cuda_stream)
-            _capi.check(status, 'msda_colsum256')
-        return grad_x, grad_w, grad_b, None, None, None
+            grad_w = _wgrad_raw(g, x2d, mask_u8, ctx.mask_mode, n_out, n_in)
+        return grad_x, grad_w, grad_b, None, None, None, grad_res, None
 
 
-def linear256(x, weight, bias=None, row_mask=None, mask_mode=0, out_dtype=torch.float32):
+def linear256(x, weight, bias=None, row_mask=None, mask_mode=0, out_dtype=torch.float32,
+              residual=None, dropout_p=0.0):
     """Functional front-end of `Linear256Function` (see there)."""
-    return Linear256Function.apply(x, weight, bias, row_mask, mask_mode, out_dtype)
+    return Linear256Function.apply(x, weight, bias, row_mask, mask_mode, out_dtype, residual, dropout_p)
+
+
+class FusedFFNFunction(Function):
+    """identity + dropout(fc2(dropout(relu(fc1(x))))) -- the feed-forward block of the
+    transformer layers (mmcv/cnn/bricks/transformer.py:1110-1120, 2 fcs, ReLU) -- as two
+    tensor-core GEMMs forward (bias + ReLU + dropout, and bias + dropout + residual, in
+    the epilogues) and four backward (the ReLU / dropout backward and the residual
+    gradient in the epilogues too), plus two streaming bias-gradient passes."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, dropout_p, identity, add_identity):
+        # identity None with add_identity: the residual is x itself
+        shape = x.shape
+        n_hidden, n_in = w1.shape
+        x2d = _as_f32_2d(x, n_in)
+        w1, w2 = w1.contiguous(), w2.contiguous()
+        res2d = None
+        if add_identity:
+            res2d = x2d if identity is None else _as_f32_2d(identity, w2.shape[0])
+        seed1 = _next_dropout_seed() if dropout_p > 0 else 0
+        seed2 = _next_dropout_seed() if dropout_p > 0 else 0
+        h = _linear_fused_raw(x2d, w1, None if b1 is None else b1.contiguous(), relu=True,
+                              dropout_p=dropout_p, seed=seed1)
+        y = _linear_fused_raw(h, w2, None if b2 is None else b2.contiguous(), dropout_p=dropout_p,
+                              seed=seed2, residual=res2d)
+        ctx.save_for_backward(x2d, h, w1, w2)
+        ctx.cfg = (shape, dropout_p, seed2, b1 is not None, b2 is not None,
+                   add_identity and identity is not None, add_identity and identity is None)
+        return y.view(*shape[:-1], w2.shape[0])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_y):
+        x2d, h, w1, w2 = ctx.saved_tensors
+        shape, p, seed2, has_b1, has_b2, has_identity, identity_is_x = ctx.cfg
+        n_hidden, n_in = w1.shape
+        n_out = w2.shape[0]
+        g = _as_f32_2d(grad_y, n_out)
+        # through dropout 2 (+ bias gradient of fc2 from the same pass)
+        if p > 0:
+            g2, grad_b2 = _dropout_backward_raw(g, p, seed2, has_b2)
+        else:
+            g2, grad_b2 = g, (_colsum_raw(g) if has_b2 else None)
+        grad_w2 = _wgrad_raw(g2, h, None, 0, n_out, n_hidden)
+        # dZ = (dY2 W2) * [h > 0] / (1 - p): h > 0 iff the ReLU passed and dropout 1 kept
+        dz = _linear_fused_raw(g2, w2.t().contiguous(), gate=h, gate_scale=1.0 / (1.0 - p))
+        grad_b1 = _colsum_raw(dz) if has_b1 else None
+        grad_w1 = _wgrad_raw(dz, x2d, None, 0, n_hidden, n_in)
+        grad_x = grad_identity = None
+        if ctx.needs_input_grad[0]:
+            # dX = dZ W1 (+ the identity branch's gradient when the identity is x itself)
+            grad_x = _linear_fused_raw(dz, w1.t().contiguous(),
+                                       residual=g if identity_is_x else None).view(shape)
+        if has_identity and not identity_is_x:
+            grad_identity = grad_y
+        return grad_x, grad_w1, grad_b1, grad_w2, grad_b2, None, grad_identity, None
+
+
+def ffn_supported(x, w1, w2):
+    """True when `fused_ffn` has kernels for these tensors (fp32 CUDA, widths 128 / 256 / 1024)."""
+    return (linear256_supported(x, w1) and w2.is_cuda and w2.dtype == torch.float32
+            and w2.dim() == 2 and w2.shape[1] == w1.shape[0] and _linear_shape_ok(*w2.shape))
+
+
+def fused_ffn(x, w1, b1, w2, b2, dropout_p=0.0, identity=None, add_identity=True):
+    """identity + dropout(fc2(dropout(relu(fc1(x))))); identity=None means x itself;
+    add_identity=False leaves the residual out."""
+    return FusedFFNFunction.apply(x, w1, b1, w2, b2, float(dropout_p), identity, bool(add_identity))

@@ -33,15 +33,16 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .functional import (FusedMultiScaleDeformableAttnFunction, MultiScaleDeformableAttnFunction,
-                         fuse_frames_as_levels, fused_supported, linear256, linear256_supported)
-from .registry import ATTENTION, OPERA_ATTENTION
+                         ffn_supported, fuse_frames_as_levels, fused_ffn, fused_supported, linear256,
+                         linear256_supported)
+from .registry import ATTENTION, FEEDFORWARD_NETWORK, OPERA_ATTENTION
 
 __all__ = [
     'MultiScaleDeformableAttention', 'MultiScaleDeformablePoseAttention',
     'MulFramesMultiScaleDeformablePoseAttentionNumFrames3',
     'MulFramesMultiScaleDeformablePoseAttentionNumFrames5',
     'MulFramesMultiScaleDeformableAttentionNumFrames3',
-    'MulFramesMultiScaleDeformableAttentionNumFrames5',
+    'MulFramesMultiScaleDeformableAttentionNumFrames5', 'FFN',
 ]
 
 _FRAME_PREFIXES = {3: ('pre_', '', 'next_'),
@@ -121,6 +122,21 @@ class _DeformAttnBase(nn.Module):
         if out_dtype is not None and y.dtype != out_dtype:
             y = y.to(out_dtype)
         return y
+
+    def _project_out(self, output, identity, seq_first):
+        """identity + dropout(output_proj(output)) for a batch-first `output`
+        (multi_scale_deform_attn.py:406-412); seq_first: identity and the result are
+        (Q, B, C).  Batch-first callers get dropout and the residual from the GEMM epilogue."""
+        layer = self.output_proj
+        if (not seq_first and self.tensor_core_linear and linear256_supported(output, layer.weight)
+                and identity.dtype == torch.float32 and identity.is_cuda
+                and identity.shape == output.shape[:-1] + (layer.out_features,)):
+            return linear256(output, layer.weight, layer.bias, residual=identity,
+                             dropout_p=self.dropout.p if self.training else 0.0)
+        output = self._project(layer, output)
+        if seq_first:
+            output = output.permute(1, 0, 2)
+        return self.dropout(output) + identity
 
     def __init__(self, embed_dims, num_heads, num_levels, num_points, im2col_step, dropout,
                  batch_first, norm_cfg, init_cfg, value_dtype):
@@ -219,10 +235,7 @@ class MultiScaleDeformableAttention(_DeformAttnBase):
                 scale = reference_points[..., 2:] * (0.5 / self.num_points)
             output = _run_fused(value, spatial_shapes, level_start_index, sampling_offsets,
                                 attention_weights, ref, scale)
-            output = self._project(self.output_proj, output)
-            if not self.batch_first:
-                output = output.permute(1, 0, 2)
-            return self.dropout(output) + identity
+            return self._project_out(output, identity, not self.batch_first)
         attention_weights = attention_weights.softmax(-1).view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points)
         if reference_points.shape[-1] == 2:
@@ -238,10 +251,15 @@ class MultiScaleDeformableAttention(_DeformAttnBase):
                              f'but get {reference_points.shape[-1]} instead.')
         output = _run_op(value, spatial_shapes, level_start_index, sampling_locations,
                          attention_weights, self.im2col_step)
-        output = self._project(self.output_proj, output)
-        if not self.batch_first:
-            output = output.permute(1, 0, 2)
-        return self.dropout(output) + identity
+        return self._project_out(output, identity, not self.batch_first)
+
+
+def _fold(t, sl):
+    """(G, Q, ...) -> rows sl of it as one batch entry (1, n*Q, ...); sl None: unchanged."""
+    if sl is None:
+        return t
+    t = t[sl]
+    return t.reshape((1, t.shape[0] * t.shape[1]) + tuple(t.shape[2:]))
 
 
 def _pose_box_wh(kpts):
@@ -491,10 +509,18 @@ class _MulFramesJointAttention(_MulFramesBase):
 
     def forward(self, query, key=None, value=None, identity=None, query_pos=None,
                 query_time_pos=None, key_padding_mask=None, reference_points=None,
-                spatial_shapes=None, level_start_index=None, **kwargs):
+                spatial_shapes=None, level_start_index=None, value_group_sizes=None, **kwargs):
         """query (num_query, G, C); value (num_key, G, T, C); key_padding_mask
         (G, T, num_key); reference_points (T*G, num_query, num_levels, 2)
-        frame-major, or (G, num_query, num_levels, 4) boxes shared by all frames."""
+        frame-major, or (G, num_query, num_levels, 4) boxes shared by all frames.
+
+        value_group_sizes (not in the reference): a list of ints, one per clip.  The
+        reference gathers the clip's memory once per person before calling this module
+        (`memory[:, img_inds]`), so value_proj and the sampling kernels see G copies of the
+        same tokens.  With this argument `value` and `key_padding_mask` hold ONE entry per
+        clip -- (num_key, clips, T, C) and (clips, T, num_key) -- and the G persons, ordered
+        by clip, share it: person g of clip b reads value[:, b].  Same result, 1/G-th of
+        the projection work and no gathered copy."""
         if 'residual' in kwargs:
             identity = kwargs.pop('residual')
         if value is None:
@@ -508,12 +534,37 @@ class _MulFramesJointAttention(_MulFramesBase):
             value = value.permute(1, 0, 2, 3)
         T, M, L, P = self.num_frames, self.num_heads, self.num_levels, self.num_points
         bs, num_query, _ = query.shape
-        bs, num_value, num_frames, _ = value.shape
+        num_value, num_frames = value.shape[1], value.shape[2]
         if num_frames != T:
             raise ValueError('value holds %d frames, module built for %d' % (num_frames, T))
-        value = self._project(self.value_proj, value,
-                              None if key_padding_mask is None else key_padding_mask.transpose(1, 2),
-                              2, self.value_dtype)  # (G, S, T, C)
+        groups = None
+        if value_group_sizes is not None:
+            groups = [int(n) for n in value_group_sizes]
+            if len(groups) != value.shape[0] or sum(groups) != bs or min(groups) < 0:
+                raise ValueError('value_group_sizes %r does not split %d queries over %d clips'
+                                 % (groups, bs, value.shape[0]))
+            if not self.fused:
+                # reference-style composition: materialise the gather the reference would have done
+                idx = torch.repeat_interleave(
+                    torch.arange(len(groups), device=value.device),
+                    torch.tensor(groups, device=value.device), output_size=bs)
+                value = value[idx]
+                if key_padding_mask is not None:
+                    key_padding_mask = key_padding_mask[idx]
+                groups = None
+        elif value.shape[0] != bs:
+            raise ValueError('value holds %d batch entries, query %d' % (value.shape[0], bs))
+        frame_major = value.permute(0, 2, 1, 3)              # (G, T, S, C)
+        if self.fused and frame_major.is_contiguous():
+            # tokens already frame-major (a batch-first encoder output viewed per clip): project in
+            # place, the result IS the T*L-level value the fused call needs -- no copy either side
+            value = self._project(self.value_proj, frame_major, key_padding_mask, 2,
+                                  self.value_dtype).permute(0, 2, 1, 3)             # (G, S, T, C) view
+        else:
+            value = self._project(
+                self.value_proj, value,
+                None if key_padding_mask is None else key_padding_mask.transpose(1, 2),
+                2, self.value_dtype)  # (G, S, T, C)
 
         ref_dim = reference_points.shape[-1]
         if ref_dim == 2:
@@ -532,9 +583,9 @@ class _MulFramesJointAttention(_MulFramesBase):
                 bs, num_query, M, T * L * P)
             shapes_f, starts_f = fuse_frames_as_levels(spatial_shapes, level_start_index, T,
                                                        num_value)
-            # frames are interleaved along dim 2 here, so this is one copy
-            # (the reference makes T `.contiguous()` copies of the same bytes)
-            value_f = value.permute(0, 2, 1, 3).reshape(bs, T * num_value, M, -1)
+            # frames are interleaved along dim 2 unless the tokens came frame-major: one copy
+            # at most (the reference makes T `.contiguous()` copies of the same bytes)
+            value_f = value.permute(0, 2, 1, 3).reshape(value.shape[0], T * num_value, M, -1)
             if ref_dim == 2:
                 ref_f = ref.permute(1, 2, 0, 3, 4).reshape(bs, num_query, T * L, 1, 2)
                 scale_f = None
@@ -543,7 +594,9 @@ class _MulFramesJointAttention(_MulFramesBase):
                 ref_f = boxes[..., :2].unsqueeze(3)
                 scale_f = boxes[..., 2:] * (0.5 / P)
             if self._can_fuse(value_f, offsets):
-                output = _run_fused(value_f, shapes_f, starts_f, offsets, logits, ref_f, scale_f)
+                def sample(v, sl):
+                    return _run_fused(v, shapes_f, starts_f, _fold(offsets, sl), _fold(logits, sl),
+                                      _fold(ref_f, sl), None if scale_f is None else _fold(scale_f, sl))
             else:
                 weights = logits.softmax(-1).view(bs, num_query, M, T * L, P)
                 if ref_dim == 2:
@@ -552,8 +605,20 @@ class _MulFramesJointAttention(_MulFramesBase):
                 else:
                     locations = ref_f.unsqueeze(2) \
                         + offsets / P * boxes[:, :, None, :, None, 2:] * 0.5
-                output = _run_op(value_f, shapes_f, starts_f, locations, weights,
-                                 self.im2col_step)
+
+                def sample(v, sl):
+                    return _run_op(v, shapes_f, starts_f, _fold(locations, sl), _fold(weights, sl),
+                                   self.im2col_step)
+            if groups is None:
+                output = sample(value_f, None)
+            else:
+                # the persons of one clip become extra queries of a single batch entry
+                outs, g0 = [], 0
+                for b, n in enumerate(groups):
+                    if n:
+                        outs.append(sample(value_f[b:b + 1], slice(g0, g0 + n)).view(n, num_query, -1))
+                    g0 += n
+                output = outs[0] if len(outs) == 1 else torch.cat(outs)
         else:
             outs, logits = [], []
             for t, pre in enumerate(self._prefixes):
@@ -574,10 +639,7 @@ class _MulFramesJointAttention(_MulFramesBase):
                                     self.im2col_step).reshape(bs, num_query, M, -1))
             output = self._fuse_reference_style(outs, logits).flatten(-2, -1)
 
-        output = self._project(self.output_proj, output)
-        if not self.batch_first:
-            output = output.permute(1, 0, 2)
-        return self.dropout(output) + identity
+        return self._project_out(output, identity, not self.batch_first)
 
 
 @ATTENTION.register_module()
@@ -611,3 +673,71 @@ MMCV_SCOPE_CLASSES = (MultiScaleDeformableAttention,
 OPERA_SCOPE_CLASSES = (MultiScaleDeformablePoseAttention,
                        MulFramesMultiScaleDeformablePoseAttentionNumFrames3,
                        MulFramesMultiScaleDeformablePoseAttentionNumFrames5)
+
+
+@FEEDFORWARD_NETWORK.register_module()
+class FFN(nn.Module):
+    """Mirrors mmcv/cnn/bricks/transformer.py:1046-1120 (same constructor kwargs,
+    `layers.0.0` / `layers.1` parameter names and `forward(x, identity=None)`): the
+    feed-forward block that follows every attention module of the reference's
+    transformer layers.  With two fcs, ReLU and 128/256/1024-wide layers on CUDA it
+    runs as `fused_ffn` (tensor-core GEMMs with bias, ReLU, dropout and the residual
+    in their epilogues); anything else is the op-by-op composition."""
+
+    #: False forces the op-by-op composition (nn.Linear / cuBLAS fp32)
+    tensor_core_linear = True
+
+    def __init__(self, embed_dims=256, feedforward_channels=1024, num_fcs=2,
+                 act_cfg=dict(type='ReLU', inplace=True), ffn_drop=0., dropout_layer=None,
+                 add_identity=True, init_cfg=None, **kwargs):
+        super().__init__()
+        if num_fcs < 2:
+            raise AssertionError(f'num_fcs should be no less than 2. got {num_fcs}.')
+        act_type = (act_cfg or {}).get('type', 'ReLU')
+        acts = {'ReLU': nn.ReLU, 'GELU': nn.GELU, 'LeakyReLU': nn.LeakyReLU, 'Tanh': nn.Tanh,
+                'Sigmoid': nn.Sigmoid, 'PReLU': nn.PReLU, 'ELU': nn.ELU, 'ReLU6': nn.ReLU6}
+        if act_type not in acts:
+            raise KeyError('%s is not in the activation layer registry' % act_type)
+        act_kwargs = {k: v for k, v in (act_cfg or {}).items() if k != 'type'}
+        if act_type in ('GELU', 'Tanh', 'Sigmoid', 'PReLU'):
+            act_kwargs.pop('inplace', None)
+        self.embed_dims, self.feedforward_channels = embed_dims, feedforward_channels
+        self.num_fcs, self.act_cfg = num_fcs, act_cfg
+        self.activate = acts[act_type](**act_kwargs)
+        layers, in_channels = [], embed_dims
+        for _ in range(num_fcs - 1):
+            layers.append(nn.Sequential(nn.Linear(in_channels, feedforward_channels), self.activate,
+                                        nn.Dropout(ffn_drop)))
+            in_channels = feedforward_channels
+        layers.append(nn.Linear(feedforward_channels, embed_dims))
+        layers.append(nn.Dropout(ffn_drop))
+        self.layers = nn.Sequential(*layers)
+        if dropout_layer:
+            kind = dropout_layer.get('type', 'Dropout')
+            if kind != 'Dropout':
+                raise KeyError('dropout_layer type %s is not supported here (Dropout only)' % kind)
+            self.dropout_layer = nn.Dropout(dropout_layer.get('drop_prob', 0.5))
+        else:
+            self.dropout_layer = nn.Identity()
+        self.add_identity = add_identity
+        self.ffn_drop = float(ffn_drop)
+
+    def _fusable(self, x):
+        return (self.tensor_core_linear and self.num_fcs == 2 and isinstance(self.activate, nn.ReLU)
+                and isinstance(self.dropout_layer, nn.Identity)
+                and ffn_supported(x, self.layers[0][0].weight, self.layers[1].weight))
+
+    def forward(self, x, identity=None):
+        if not x.is_cuda:
+            raise RuntimeError('pavenet_b200 modules run on CUDA tensors only (there is no CPU '
+                               'fallback); got x on %s' % x.device)
+        if self._fusable(x):
+            fc1, fc2 = self.layers[0][0], self.layers[1]
+            return fused_ffn(x, fc1.weight, fc1.bias, fc2.weight, fc2.bias,
+                             self.ffn_drop if self.training else 0.0, identity, self.add_identity)
+        out = self.layers(x)
+        if not self.add_identity:
+            return self.dropout_layer(out)
+        if identity is None:
+            identity = x
+        return identity + self.dropout_layer(out)

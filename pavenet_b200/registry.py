@@ -13,7 +13,8 @@ stand-in with the same `register_module` / `build` / `get` surface is used so
 configs written for the reference still build.
 """
 
-__all__ = ['ATTENTION', 'OPERA_ATTENTION', 'build_attention', 'install']
+__all__ = ['ATTENTION', 'OPERA_ATTENTION', 'FEEDFORWARD_NETWORK', 'build_attention',
+           'build_feedforward_network', 'install']
 
 
 class _MiniRegistry(object):
@@ -64,11 +65,17 @@ class _MiniRegistry(object):
 
 ATTENTION = _MiniRegistry('attention', scope='mmcv')
 OPERA_ATTENTION = _MiniRegistry('attention', scope='opera', parent=ATTENTION)
+FEEDFORWARD_NETWORK = _MiniRegistry('feed-forward Network', scope='mmcv')
 
 
 def build_attention(cfg, default_args=None):
     """`mmcv.cnn.bricks.transformer.build_attention` for the classes of this package."""
     return OPERA_ATTENTION.build(cfg, default_args)
+
+
+def build_feedforward_network(cfg, default_args=None):
+    """`mmcv.cnn.bricks.transformer.build_feedforward_network` for this package's FFN."""
+    return FEEDFORWARD_NETWORK.build(cfg, default_args)
 
 
 def install():
@@ -78,8 +85,8 @@ def install():
        are replaced, so every one of the reference's 18 attention classes (which
        all call `MultiScaleDeformableAttnFunction.apply`) runs on the new kernels
        unchanged.
-    2. The fused module classes of `pavenet_b200.modules` are registered over the
-       reference's registry names.
+    2. The fused module classes of `pavenet_b200.modules` (attention classes and
+       the transformer layers' `FFN`) are registered over the reference's registry names.
 
     Returns the list of things patched; raises ImportError if mmcv is absent.
     """
@@ -100,6 +107,9 @@ def install():
     for cls in modules.MMCV_SCOPE_CLASSES:
         MMCV_ATTENTION.register_module(name=cls.__name__, force=True, module=cls)
         patched.append('mmcv.' + cls.__name__)
+    from mmcv.cnn.bricks.registry import FEEDFORWARD_NETWORK as MMCV_FFN
+    MMCV_FFN.register_module(name='FFN', force=True, module=modules.FFN)
+    patched.append('mmcv.FFN')
     try:
         from opera.models.utils.builder import ATTENTION as OPERA_REG
         for cls in modules.OPERA_SCOPE_CLASSES:

@@ -33,3 +33,8 @@ for c, t in cat.most_common():
 print('total device time %.2f ms/step' % (tot / 3e3))
 others = [(e.self_device_time_total, e.key) for e in prof.key_averages() if classify(e.key) == 'other']
 for t, k in sorted(others, reverse=True)[:8]: print('   other:', round(t / 3e3, 3), k[:90])
+print('-- top kernels by device time per step')
+rows = sorted(((e.self_device_time_total, e.count, e.key) for e in prof.key_averages() if e.self_device_time_total > 0),
+              reverse=True)
+for t, c, k in rows[:32]:
+    print('  %8.3f ms  x%-5d %s' % (t / 3e3, c // 3, k[:110]))

@@ -11,7 +11,7 @@ from pavenet_b200 import _capi  # noqa: E402
 lib = _capi.load()
 torch.manual_seed(0)
 dev = 'cuda'
-SHAPES = ((256, 256), (256, 128), (128, 256))     # (in, out)
+SHAPES = ((256, 256), (256, 128), (128, 256), (256, 1024), (1024, 256))     # (in, out)
 
 
 def stream():
@@ -72,7 +72,7 @@ for n_in, n_out in SHAPES:
     t_ref = time_ms(lambda: dy.t() @ x)
     print('  rows %d: tcgen05 3xTF32 %.4f ms   torch fp32 (cuBLAS) %.4f ms' % (rows, t_ours, t_ref))
 
-for width in (128, 256):
+for width in (128, 256, 1024):
     print('== colsum width=%d' % width)
     rows = 66669
     dy = torch.randn(rows, width, device=dev)
