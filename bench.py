@@ -320,6 +320,8 @@ def run_model_step(args, world, rank, local):
     torch.manual_seed(0)
     vdt = None if args.value_dtype == 'f32' else torch.bfloat16
     model = clip_model.PaveNetR50(value_dtype=vdt).to(device).train()
+    if args.graphs:
+        model.enable_graphs()
     ddp = DDP(model, device_ids=[local], broadcast_buffers=False) if world > 1 else None
     opt = clip_model.build_optimizer(model)
     clips_per_gpu = 1
@@ -355,6 +357,7 @@ def run_model_step(args, world, rank, local):
             'config': {'workload': 'pavenet_step', 'description': 'PAVE-Net R-50, T=3 frames at 800x1333, '
                        '1 clip per GPU, forward + backward + DDP all-reduce + grad-clip + AdamW',
                        'trainable_params': n_params, 'parallelism': 'clip-sharded DDP x%d' % world,
+                       'cuda_graphs': bool(args.graphs),
                        'l2_policy': 'inputs larger than L2 (activations of a 3x800x1333 clip)'},
             'roofline': None, 'cpu_baseline': None, 'e2e': None,
             'clocks': clock_info, 'gpu_launches': int(_capi.launch_count() - launches0),
@@ -392,6 +395,7 @@ def main():
     ap.add_argument('--workload', default='encoder_cfg2',
                     choices=sorted(WORKLOADS) + list(MODEL_WORKLOADS))
     ap.add_argument('--value-dtype', default='f32', choices=['f32', 'bf16'])
+    ap.add_argument('--graphs', type=int, default=0, help='pavenet_step: run backbone, encoder and pose decoder as CUDA graphs (fwd + bwd)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--sets', type=int, default=4, help='distinct input sets rotated per step')

@@ -169,7 +169,9 @@ int msda_fused_backward(const void *d_value, const int64_t *d_spatial_shapes,
  *   d_gate != NULL ([rows,out] fp32): v = gate > 0 ? v * gate_scale : 0  (the
  *     backward of ReLU followed by dropout, with gate = the saved activation);
  *   dropout_p > 0: v = keep ? v / (1 - p) : 0, keep decided by a counter-based hash
- *     of (element index, dropout_seed) -- msda_dropout_backward regenerates it;
+ *     of (element index, seed) -- msda_dropout_backward regenerates it; seed =
+ *     dropout_seed, plus *d_dropout_seed when that device pointer is not NULL (a seed
+ *     in device memory lets a captured CUDA graph draw a new mask at every replay);
  *   mask_mode 1: rows with d_row_mask[r] != 0 are written as zeros (mask after the
  *     projection); 2: they are written as the bias (input masked before it);
  *   + d_residual ([rows,out] fp32, may be NULL);
@@ -179,7 +181,8 @@ int msda_fused_backward(const void *d_value, const int64_t *d_spatial_shapes,
 int msda_linear_fused(const float *d_x, const float *d_weight, const float *d_bias,
                       const uint8_t *d_row_mask, int mask_mode, int relu,
                       const float *d_gate, float gate_scale, float dropout_p,
-                      uint64_t dropout_seed, const float *d_residual, void *d_y,
+                      uint64_t dropout_seed, const uint64_t *d_dropout_seed,
+                      const float *d_residual, void *d_y,
                       int rows, int in_features, int out_features, int out_dtype,
                       float *d_scratch, void *stream);
 
@@ -205,12 +208,14 @@ int msda_colsum256(const float *d_grad_y, const uint8_t *d_row_mask,
                    float *d_grad_bias, int rows, int width, void *stream);
 
 /* Backward of msda_linear_fused's dropout: grad_out = grad_y * keep / (1 - p) with
- * the keep decisions regenerated from (dropout_p, dropout_seed); when d_grad_bias
+ * the keep decisions regenerated from (dropout_p, dropout_seed, d_dropout_seed) as
+ * given to the forward call; when d_grad_bias
  * is not NULL it also receives the column sums of grad_out (the bias gradient),
  * from the same pass. */
 int msda_dropout_backward(const float *d_grad_y, float *d_grad_out,
                           float *d_grad_bias, int rows, int width, float dropout_p,
-                          uint64_t dropout_seed, void *stream);
+                          uint64_t dropout_seed, const uint64_t *d_dropout_seed,
+                          void *stream);
 
 /*
  * Host-buffer convenience entry points (what a cgo / JNI / ctypes caller

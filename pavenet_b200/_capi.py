@@ -59,10 +59,11 @@ def _declare(lib):
     lib.msda_linear256_wgrad.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.msda_linear_fused.restype = c_int
     lib.msda_linear_fused.argtypes = ([c_void_p] * 4 + [c_int, c_int, c_void_p, ctypes.c_float, ctypes.c_float,
-                                      ctypes.c_uint64, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p, c_void_p])
+                                      ctypes.c_uint64, c_void_p, c_void_p, c_void_p] + [c_int] * 4 +
+                                     [c_void_p, c_void_p])
     lib.msda_dropout_backward.restype = c_int
     lib.msda_dropout_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_float,
-                                          ctypes.c_uint64, c_void_p]
+                                          ctypes.c_uint64, c_void_p, c_void_p]
     lib.msda_colsum256.restype = c_int
     lib.msda_colsum256.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
     lib.msda_workspace_create.restype = c_int

@@ -196,6 +196,7 @@ class PaveNetR50(nn.Module):
         self.refine_sigma = nn.ModuleList(mlp(256, 256, 2, n_hidden=1) for _ in range(2))
         self.flow = RealNVP()
         nn.init.constant_(self.cls_branches[0].bias, -4.6)
+        self._geo_cache, self._graphed = {}, None
 
     def train(self, mode=True):
         super().train(mode)
@@ -234,34 +235,57 @@ class PaveNetR50(nn.Module):
             pts.append(torch.stack([xx.reshape(-1), yy.reshape(-1)], -1))
         return torch.cat(pts)                          # (S, 2)
 
-    def forward_train(self, images, gt_kpts, gt_areas):
-        """images (Bc, T, 3, H, W); gt_kpts: per clip (G_i, T, K, 3) normalised x, y, visibility;
-        gt_areas: per clip (G_i,) normalised box areas.  Returns a dict of losses."""
-        T, K, Bc = self.T, self.K, images.shape[0]
+    # ---- constants of one input geometry (cached: nothing here depends on the data) ----
+    def _geometry(self, images):
+        Bc, T = images.shape[:2]
         H, W = images.shape[-2:]
-        feats = self.extract_feat(images)
-        self._mark('backbone+neck')
+        key = (Bc, T, H, W, images.device)
+        geo = self._geo_cache.get(key)
+        if geo is not None:
+            return geo
         dev = images.device
-        shapes_list = [tuple(f.shape[-2:]) for f in feats]
+
+        def down(n, times):
+            for _ in range(times):
+                n = (n - 1) // 2 + 1
+            return n
+        shapes_list = [(down(H, k), down(W, k)) for k in (3, 4, 5, 6)]      # strides 8 / 16 / 32 / 64
         shapes = torch.tensor(shapes_list, device=dev)
         lsi = torch.cat([shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]])
         masks = [torch.zeros((Bc * T, h, w), dtype=torch.bool, device=dev) for h, w in shapes_list]
-        pos = torch.cat([(self.pos_enc(m) + self.level_embeds[i].view(1, -1, 1, 1)).flatten(2)
-                         for i, m in enumerate(masks)], 2).transpose(1, 2).contiguous()  # (Bc*T, S, 256)
-        x = torch.cat([f.flatten(2) for f in feats], 2).transpose(1, 2).contiguous()   # (Bc*T, S, 256)
-        mask_flat = torch.cat([m.flatten(1) for m in masks], 1)                        # (Bc*T, S)
-        S = x.shape[1]
+        with torch.no_grad():
+            pos_sine = [self.pos_enc(m) for m in masks]                       # (Bc*T, 256, h, w) each
+        mask_flat = torch.cat([m.flatten(1) for m in masks], 1)               # (Bc*T, S)
+        S = mask_flat.shape[1]
         grid = self.reference_grid(shapes_list, dev)
-        ref_enc = grid[None, :, None, :].expand(Bc * T, S, 4, 2).contiguous()          # valid_ratios == 1
+        geo = dict(shapes_list=shapes_list, shapes=shapes, lsi=lsi, pos_sine=pos_sine, mask_flat=mask_flat,
+                   grid=grid, ref_enc=grid[None, :, None, :].expand(Bc * T, S, 4, 2).contiguous(),  # valid_ratios == 1
+                   proposals=inverse_sigmoid(grid)[None].expand(Bc, S, 2).contiguous(),
+                   wh=images.new_tensor([W, H]))
+        self._geo_cache[key] = geo
+        return geo
+
+    # ---- the three static-shape stages (eager, or one CUDA graph each: enable_graphs) ----
+    def _stage_backbone(self, images):
+        return tuple(self.extract_feat(images))
+
+    def _stage_encoder(self, f0, f1, f2, f3, p0, p1, p2, p3, mask_flat, ref_enc, shapes, lsi):
+        feats, pos_sine = (f0, f1, f2, f3), (p0, p1, p2, p3)
+        pos = torch.cat([(p + self.level_embeds[i].view(1, -1, 1, 1)).flatten(2)
+                         for i, p in enumerate(pos_sine)], 2).transpose(1, 2).contiguous()  # (Bc*T, S, 256)
+        x = torch.cat([f.flatten(2) for f in feats], 2).transpose(1, 2).contiguous()     # (Bc*T, S, 256)
         for layer in self.encoder:
             x = layer(x, pos, mask_flat, ref_enc, shapes, lsi)
-        memory = x.transpose(0, 1)             # (S, Bc*T, 256) view: what the decoders' modules take
-        self._mark('encoder')
+        return x
 
-        # two-stage proposals from the current frame
+    def _stage_decoder(self, x, proposals, mask_flat, shapes, lsi):
+        """two-stage proposals from the current frame + the pose decoder.
+        x (Bc*T, S, 256) -> enc_cls, enc_kpt, enc_sigma, then (cls, kpt, sigma) per decoder layer."""
+        T, K = self.T, self.K
+        Bc, S = x.shape[0] // T, x.shape[1]
+        memory = x.transpose(0, 1)             # (S, Bc*T, 256) view: what the decoders' modules take
         now = x[T // 2::T]                                                              # (Bc, S, 256)
         out_mem = self.enc_output_norm(self.enc_output(now))
-        proposals = inverse_sigmoid(grid)[None].expand(Bc, S, 2)
         enc_cls = self.cls_branches[3](out_mem)
         enc_kpt = self.kpt_branches[3](out_mem).view(Bc, S, K, 2) + proposals[:, :, None, :]
         enc_kpt = enc_kpt.flatten(2)
@@ -273,9 +297,7 @@ class PaveNetR50(nn.Module):
         q_pos, q = self.query_embedding.weight.split(256, 1)
         query = (tgt + q[None]).permute(1, 0, 2)                                        # (Q, Bc, 256)
         q_pos = q_pos[None].expand(Bc, -1, -1).permute(1, 0, 2)
-
-        # pose decoder
-        cls_out, kpt_out, sigma_out = [], [], []
+        outs = [enc_cls, enc_kpt, enc_sigma]
         for lid, layer in enumerate(self.decoder):
             ref_in = ref[:, :, None, :].expand(-1, -1, 4, -1)                           # (Bc, T*Q, L, 2K)
             query = layer(query, q_pos, value=memory, key_padding_mask=mask_flat, reference_points=ref_in,
@@ -284,42 +306,97 @@ class PaveNetR50(nn.Module):
             deltas = torch.cat([self.pre_kpt_branches[lid](o), self.kpt_branches[lid](o),
                                 self.next_kpt_branches[lid](o)], 1)
             ref = (deltas + inverse_sigmoid(ref)).sigmoid()                             # not detached
-            cls_out.append(self.cls_branches[lid](o))
-            kpt_out.append(ref.view(Bc, T, self.Qn, 2 * K))
-            sigma_out.append(self.sigma_branches[lid](o).sigmoid())
+            outs += [self.cls_branches[lid](o), ref.view(Bc, T, self.Qn, 2 * K),
+                     self.sigma_branches[lid](o).sigmoid()]
+        return tuple(outs)
+
+    def enable_graphs(self, enabled=True):
+        """Run the three static-shape stages (backbone + neck, encoder, two-stage + pose decoder) as
+        CUDA graphs, forward and backward (`graphs.GraphedStage`): the step issues ~6 300 kernels,
+        and on one B200 the host cannot launch them as fast as the GPU retires them.  The joint
+        decoder's shapes follow the number of matched persons, so it keeps one graph per count;
+        matching and the losses (host-side Hungarian assignment) stay eager."""
+        from . import graphs
+        if not enabled:
+            self._graphed = None
+            return self
+        mods_backbone = [self.stem, self.layer1, self.layer2, self.layer3, self.layer4, self.lateral, self.extra]
+        mods_decoder = [self.enc_output, self.enc_output_norm, self.cls_branches, self.kpt_branches,
+                        self.sigma_branches, self.pre_kpt_branches, self.next_kpt_branches, self.decoder,
+                        self.query_embedding]
+        self._graphed = dict(
+            backbone=graphs.GraphedStage(self._stage_backbone, mods_backbone),
+            encoder=graphs.GraphedStage(self._stage_encoder, [self.encoder], [self.level_embeds]),
+            decoder=graphs.GraphedStage(self._stage_decoder, mods_decoder),
+            joint=graphs.GraphedStage(self._stage_joint, [self.refine_decoder, self.refine_kpt, self.refine_sigma,
+                                                          self.refine_query_embedding]))
+        return self
+
+    def _run_stage(self, name, fn, *args):
+        graphed = getattr(self, '_graphed', None)
+        if graphed is not None and self.training and torch.is_grad_enabled():
+            return graphed[name](*args)
+        return fn(*args)
+
+    def forward_train(self, images, gt_kpts, gt_areas):
+        """images (Bc, T, 3, H, W); gt_kpts: per clip (G_i, T, K, 3) normalised x, y, visibility;
+        gt_areas: per clip (G_i,) normalised box areas.  Returns a dict of losses."""
+        T = self.T
+        geo = self._geometry(images)
+        shapes, lsi, mask_flat = geo['shapes'], geo['lsi'], geo['mask_flat']
+        feats = self._run_stage('backbone', self._stage_backbone, images)
+        if [tuple(f.shape[-2:]) for f in feats] != geo['shapes_list']:
+            raise RuntimeError('backbone produced %r, expected %r'
+                               % ([tuple(f.shape[-2:]) for f in feats], geo['shapes_list']))
+        self._mark('backbone+neck')
+        x = self._run_stage('encoder', self._stage_encoder, *feats, *geo['pos_sine'], mask_flat,
+                            geo['ref_enc'], shapes, lsi)
+        memory = x.transpose(0, 1)             # (S, Bc*T, 256) view: what the decoders' modules take
+        self._mark('encoder')
+        outs = self._run_stage('decoder', self._stage_decoder, x, geo['proposals'], mask_flat, shapes, lsi)
+        enc_cls, enc_kpt, enc_sigma = outs[:3]
+        cls_out, kpt_out, sigma_out = outs[3::3], outs[4::3], outs[5::3]
 
         self._mark('two-stage + pose decoder')
-        losses = {}
-        wh = images.new_tensor([W, H])
-        last_match = None
+        wh = geo['wh']
         stages = [(enc_cls, enc_kpt.sigmoid()[:, None].expand(-1, T, -1, -1), enc_sigma, 'enc')] + \
                  [(c, k, s, 'd%d' % i) for i, (c, k, s) in enumerate(zip(cls_out, kpt_out, sigma_out))]
-        for cls, kpt, sigma, tag in stages:
-            l_cls, l_kpt, match = self.stage_loss(cls, kpt, sigma, gt_kpts, gt_areas, wh)
-            losses[tag + '.loss_cls'], losses[tag + '.loss_kpt'] = l_cls, l_kpt
-            last_match = match
+        # every stage's Hungarian assignment behind ONE device->host synchronisation
+        matches = self.match_all(stages, gt_kpts, gt_areas, wh)
+        losses, rle_terms = {}, []
+        for (cls, kpt, sigma, tag), match in zip(stages, matches):
+            losses[tag + '.loss_cls'] = self.cls_loss(cls, match)
+            rle_terms.append((tag + '.loss_kpt',) + self.kpt_terms(kpt, sigma, match, gt_kpts))
         self._mark('matching + losses')
-        losses.update(self.refine(memory, mask_flat, shapes, lsi, kpt_out[-1], last_match, gt_kpts))
+        rle_terms += self.refine(memory, mask_flat, shapes, lsi, kpt_out[-1], matches[-1], gt_kpts)
         self._mark('joint decoder')
+        losses.update(self.rle_all(rle_terms))
+        self._mark('keypoint losses')
         return losses
 
     # ------------------------------------------------------------------ losses
-    def rle(self, pred, sigma, target, weight, num_valid):
-        """pred/sigma/target/weight (N, K, 2)."""
+    def rle_all(self, terms):
+        """All residual-log-likelihood keypoint losses of the step through ONE evaluation of the flow
+        prior: terms = [(name, pred, sigma, target, weight)], each (N_i, K, 2); loss_i is the sum over
+        its rows divided by its own number of valid coordinates (oks_loss.py:162-195)."""
+        sizes = [t[1].shape[0] for t in terms]
+        pred, sigma, target, weight = (torch.cat([t[i] for t in terms]) for i in (1, 2, 3, 4))
+        n_valid = torch.stack([t[4].sum() for t in terms]).detach()
+        n_valid = reduce_mean(n_valid).clamp(min=1)                                     # stays on the device
         bar_mu = (pred - target) / sigma
         log_phi = self.flow.log_prob(bar_mu.reshape(-1, 2)).reshape(pred.shape[0], -1, 1)
         nf = (torch.log(sigma) - log_phi) * weight[:, :, :1]
         amp = 1 / math.sqrt(2 * math.pi)
         logq = (torch.log(sigma / amp) + (target - pred).abs() / (math.sqrt(2) * sigma + 1e-9)) * weight
-        return (nf + logq).sum() / num_valid
+        per_row = (nf + logq).sum((1, 2))
+        seg = torch.repeat_interleave(torch.arange(len(sizes), device=pred.device),
+                                      torch.tensor(sizes, device=pred.device), output_size=sum(sizes))
+        totals = torch.zeros(len(sizes), device=pred.device).index_add(0, seg, per_row) / n_valid
+        return {t[0]: totals[i] for i, t in enumerate(terms)}
 
     @torch.no_grad()
-    def match(self, cls, kpt_now, gts, areas, wh):
-        """Hungarian assignment of one clip (cost: 2*focal + 70*L1 + 7*(1-OKS))."""
-        from scipy.optimize import linear_sum_assignment
-        G = gts.shape[0]
-        if G == 0:
-            return kpt_now.new_zeros(0, dtype=torch.long), kpt_now.new_zeros(0, dtype=torch.long)
+    def match_cost(self, cls, kpt_now, gts, areas, wh):
+        """Assignment cost of one clip and stage, (N, G): 2*focal + 70*L1 + 7*(1-OKS)."""
         p = cls.sigmoid()[:, 0]
         cost_cls = (0.25 * (1 - p) ** 2 * -(p + 1e-12).log() - 0.75 * p ** 2 * -(1 - p + 1e-12).log())
         pred = kpt_now.view(-1, 1, self.K, 2)
@@ -329,76 +406,124 @@ class PaveNetR50(nn.Module):
         var = (2 * POSETRACK_SIGMAS.to(pred.device)) ** 2
         oks = (torch.exp(-d2 / (2 * (areas[None, :, None] * wh.prod()).clamp(min=1) * var)) * vis).sum(-1)
         oks = oks / vis.sum(-1).clamp(min=1)
-        cost = 2.0 * cost_cls[:, None] + 70.0 * l1 + 7.0 * (1 - oks)
-        rows, cols = linear_sum_assignment(cost.cpu().numpy())
-        return (torch.as_tensor(rows, device=pred.device, dtype=torch.long),
-                torch.as_tensor(cols, device=pred.device, dtype=torch.long))
+        return 2.0 * cost_cls[:, None] + 70.0 * l1 + 7.0 * (1 - oks)
 
-    def stage_loss(self, cls, kpt, sigma, gt_kpts, gt_areas, wh):
-        """cls (Bc, N, 1); kpt (Bc, T, N, 2K); sigma (Bc, N, 2K)."""
-        Bc, K = cls.shape[0], self.K
+    @torch.no_grad()
+    def match_all(self, stages, gt_kpts, gt_areas, wh):
+        """Hungarian assignment for every stage and clip: the cost matrices are computed on the GPU,
+        copied to pinned host memory together, and solved after a single synchronisation.
+        Returns, per stage, a list over clips of (rows, cols) index tensors."""
+        from scipy.optimize import linear_sum_assignment
         now = self.T // 2
+        dev = stages[0][0].device
+        pending = []
+        for cls, kpt, _, _ in stages:
+            per_clip = []
+            for b in range(cls.shape[0]):
+                if gt_kpts[b].shape[0] == 0:
+                    per_clip.append(None)
+                    continue
+                cost = self.match_cost(cls[b], kpt[b, now], gt_kpts[b][:, now], gt_areas[b], wh)
+                host = torch.empty(cost.shape, dtype=cost.dtype, pin_memory=True)
+                host.copy_(cost, non_blocking=True)
+                per_clip.append(host)
+            pending.append(per_clip)
+        torch.cuda.current_stream(dev).synchronize()
+        solved, flat = [], []
+        for per_clip in pending:
+            out = []
+            for host in per_clip:
+                rows, cols = ([], []) if host is None else linear_sum_assignment(host.numpy())
+                out.append((len(flat), len(rows)))
+                flat.extend(rows)
+                flat.extend(cols)
+            solved.append(out)
+        # one host->device copy for all index lists
+        idx = torch.tensor(flat, dtype=torch.long).pin_memory().to(dev, non_blocking=True) if flat else \
+            torch.zeros(0, dtype=torch.long, device=dev)
+        return [[(idx[o:o + n], idx[o + n:o + 2 * n]) for o, n in out] for out in solved]
+
+    def cls_loss(self, cls, match):
+        """Focal classification loss of one stage; cls (Bc, N, 1)."""
         labels = torch.zeros_like(cls)
-        preds, sigmas, tgts, wts, matches = [], [], [], [], []
-        for b in range(Bc):
-            rows, cols = self.match(cls[b], kpt[b, now], gt_kpts[b][:, now], gt_areas[b], wh)
-            matches.append((rows, cols))
+        for b, (rows, _) in enumerate(match):
             labels[b, rows] = 1.0
+        n_pos = float(sum(int(r.shape[0]) for r, _ in match))
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            n_pos = reduce_mean(cls.new_tensor([n_pos])).clamp(min=1)
+        else:
+            n_pos = max(n_pos, 1.0)
+        p = cls.sigmoid()
+        focal = F.binary_cross_entropy_with_logits(cls, labels, reduction='none') * \
+            (labels * 0.25 * (1 - p) ** 2 + (1 - labels) * 0.75 * p ** 2)
+        return 0.5 * focal.sum() / n_pos
+
+    def kpt_terms(self, kpt, sigma, match, gt_kpts):
+        """(pred, sigma, target, weight) of one stage's matched poses, each (N, K, 2);
+        kpt (Bc, T, N, 2K), sigma (Bc, N, 2K)."""
+        K, now = self.K, self.T // 2
+        preds, sigmas, tgts, wts = [], [], [], []
+        for b, (rows, cols) in enumerate(match):
             preds.append(kpt[b, now, rows].view(-1, K, 2))
             sigmas.append(sigma[b, rows].view(-1, K, 2))
             tgts.append(gt_kpts[b][cols, now, :, :2])
             wts.append((gt_kpts[b][cols, now, :, 2:] > 0).float().expand(-1, -1, 2))
-        n_pos = reduce_mean(cls.new_tensor([float(sum(len(r) for r, _ in matches))])).clamp(min=1).item()
-        p = cls.sigmoid()
-        focal = F.binary_cross_entropy_with_logits(cls, labels, reduction='none') * \
-            (labels * 0.25 * (1 - p) ** 2 + (1 - labels) * 0.75 * p ** 2)
-        l_cls = 0.5 * focal.sum() / n_pos
-        pred, sig, tgt, wt = (torch.cat(t) for t in (preds, sigmas, tgts, wts))
-        n_valid = reduce_mean(wt.sum().detach()[None]).clamp(min=1).item()
-        l_kpt = self.rle(pred, sig, tgt, wt, n_valid) if pred.shape[0] else pred.sum() * 0
-        return l_cls, l_kpt, matches
+        return tuple(torch.cat(t) for t in (preds, sigmas, tgts, wts))
 
     def refine(self, memory, mask_flat, shapes, lsi, kpt_last, matches, gt_kpts):
-        """Joint decoder over the matched persons: K keypoint queries per person."""
+        """Joint decoder over the matched persons: K keypoint queries per person.
+        Returns the keypoint-loss terms of its layers for `rle_all`."""
         T, K = self.T, self.K
-        S = memory.shape[0]
-        poses, img_inds, tgts, wts = [], [], [], []
+        poses, tgts, wts = [], [], []
         for b, (rows, cols) in enumerate(matches):
             poses.append(kpt_last[b][:, rows])                                          # (T, g, 2K)
-            img_inds.append(rows.new_full(rows.shape, b))
             tgts.append(gt_kpts[b][cols, T // 2, :, :2])
             wts.append((gt_kpts[b][cols, T // 2, :, 2:] > 0).float().expand(-1, -1, 2))
-        poses, img_inds = torch.cat(poses, 1), torch.cat(img_inds)
+        poses = torch.cat(poses, 1)
         group_sizes = [int(rows.shape[0]) for rows, _ in matches]
-        G = img_inds.shape[0]
+        G = sum(group_sizes)
+        names = ['d%d.loss_kpt_refine' % lid for lid in range(len(self.refine_decoder))]
         if G == 0:
             zero = sum(p.sum() for p in self.refine_decoder.parameters()) * 0 + \
                 sum(p.sum() for p in self.refine_kpt.parameters()) * 0 + \
                 sum(p.sum() for p in self.refine_sigma.parameters()) * 0 + \
                 self.refine_query_embedding.weight.sum() * 0
-            return {'d0.loss_kpt_refine': zero, 'd1.loss_kpt_refine': zero}
-        ref = poses.detach().reshape(T * G, K, 2)                                       # frame-major (T*G, K, 2)
+            empty = zero.new_zeros(1, K, 2)
+            # one all-zero-weight row per layer keeps the parameters in the autograd graph (DDP)
+            return [(n, empty + zero, empty + 1, empty, empty) for n in names]
+        ref = poses.detach().reshape(T * G, K, 2).contiguous()                          # frame-major (T*G, K, 2)
+        tgt, wt = torch.cat(tgts), torch.cat(wts)
+        # the reference gathers memory[:, img_inds] -> (S, G, T, 256) here; the persons of a clip
+        # share its tokens instead (value_group_sizes), so nothing is gathered or re-projected
+        x = memory.transpose(0, 1)                                                      # (Bc*T, S, 256)
+        graphed = self._graphed
+        if graphed is not None and self.training and torch.is_grad_enabled():
+            outs = graphed['joint'](x, mask_flat, shapes, lsi, ref, static=tuple(group_sizes))
+        else:
+            outs = self._stage_joint(x, mask_flat, shapes, lsi, ref, static=tuple(group_sizes))
+        return [(n, outs[2 * lid][G:2 * G], outs[2 * lid + 1], tgt, wt) for lid, n in enumerate(names)]
+
+    def _stage_joint(self, x, mask_flat, shapes, lsi, ref, static):
+        """The joint decoder layers for G matched persons (static = persons per clip):
+        x (Bc*T, S, 256), ref (T*G, K, 2) -> (refined keypoints (T*G, K, 2), sigma (G, K, 2)) per layer.
+        Shapes follow G, so a graphed run keeps one graph per distinct `static`."""
+        T, K = self.T, self.K
+        S, G = x.shape[1], ref.shape[0] // T
         q_pos, q = self.refine_query_embedding.weight.split(256, 1)
         query = q[None].expand(G, -1, -1).permute(1, 0, 2)                              # (K, G, 256)
         q_pos = q_pos[None].expand(G, -1, -1).permute(1, 0, 2)
-        # the reference gathers memory[:, img_inds] -> (S, G, T, 256) here; the persons of a clip
-        # share its tokens instead (value_group_sizes), so nothing is gathered or re-projected
-        mem = memory.transpose(0, 1).reshape(-1, T, S, 256).permute(2, 0, 1, 3)         # (S, Bc, T, 256) view
+        mem = x.reshape(-1, T, S, 256).permute(2, 0, 1, 3)                              # (S, Bc, T, 256) view
         mask = mask_flat.view(-1, T, S)                                                 # (Bc, T, S)
-        tgt, wt = torch.cat(tgts), torch.cat(wts)
-        n_valid = reduce_mean(wt.sum().detach()[None]).clamp(min=1).item()
-        losses = {}
+        outs = []
         for lid, layer in enumerate(self.refine_decoder):
             ref_in = ref[:, :, None, :].expand(-1, -1, 4, -1)                           # (T*G, K, L, 2)
             query = layer(query, q_pos, value=mem, key_padding_mask=mask, reference_points=ref_in,
-                          spatial_shapes=shapes, level_start_index=lsi, value_group_sizes=group_sizes)
+                          spatial_shapes=shapes, level_start_index=lsi, value_group_sizes=list(static))
             o = query.permute(1, 0, 2)                                                  # (G, K, 256)
             deltas = torch.cat([self.refine_kpt[t][lid](o) for t in range(T)], 0)       # (T*G, K, 2)
-            new_ref = (deltas + inverse_sigmoid(ref)).sigmoid()
-            sigma = self.refine_sigma[lid](o).sigmoid()
-            losses['d%d.loss_kpt_refine' % lid] = self.rle(new_ref[G:2 * G], sigma, tgt, wt, n_valid)
-            ref = new_ref
-        return losses
+            ref = (deltas + inverse_sigmoid(ref)).sigmoid()
+            outs += [ref, self.refine_sigma[lid](o).sigmoid()]
+        return tuple(outs)
 
 
 def build_optimizer(model):
@@ -436,6 +561,9 @@ def synthetic_clip_batch(clips, device, seed, height=800, width=1333, num_frames
 def train_step(model, optimizer, images, gt_kpts, gt_areas, ddp_model=None):
     """forward + backward (+ DDP gradient all-reduce) + grad-clip 0.1 + AdamW step."""
     net = ddp_model if ddp_model is not None else model
+    if getattr(model, '_graphed', None) is not None:
+        from . import graphs
+        graphs.refresh_seed(images.device)        # new epilogue-dropout masks for this step's replays
     losses = net(images, gt_kpts, gt_areas)
     loss = sum(losses.values())
     optimizer.zero_grad(set_to_none=True)

@@ -136,6 +136,15 @@ __device__ __forceinline__ bool dropout_keep(uint32_t idx, uint32_t seed_lo, uin
   return x >= threshold;
 }
 
+// seed = host part + optional device part
+__device__ __forceinline__ void resolve_seed(uint32_t lo, uint32_t hi, const unsigned long long* ptr,
+                                             uint32_t* out_lo, uint32_t* out_hi) {
+  unsigned long long s = (static_cast<unsigned long long>(hi) << 32) | lo;
+  if (ptr != nullptr) s += *ptr;
+  *out_lo = static_cast<uint32_t>(s);
+  *out_hi = static_cast<uint32_t>(s >> 32);
+}
+
 template <typename OT>
 __device__ __forceinline__ void store_chunk(OT* row_ptr, const float (&v)[32]);
 template <>
@@ -279,6 +288,8 @@ linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
     const float* gate = ep.gate ? ep.gate + row_off : nullptr;
     const float* res = ep.residual ? ep.residual + row_off : nullptr;
     const uint32_t drop_idx0 = static_cast<uint32_t>(row_off);
+    uint32_t seed_lo = 0, seed_hi = 0;
+    if (ep.dropout_threshold != 0u) resolve_seed(ep.seed_lo, ep.seed_hi, ep.seed_ptr, &seed_lo, &seed_hi);
   #pragma unroll 1
     for (int c0 = 0; c0 < NT; c0 += 32) {
       uint32_t u[32];
@@ -318,7 +329,7 @@ linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
       if (ep.dropout_threshold != 0u) {
   #pragma unroll
         for (int j = 0; j < 32; ++j)
-          v[j] = dropout_keep(drop_idx0 + c0 + j, ep.seed_lo, ep.seed_hi, ep.dropout_threshold)
+          v[j] = dropout_keep(drop_idx0 + c0 + j, seed_lo, seed_hi, ep.dropout_threshold)
                      ? v[j] * ep.dropout_scale : 0.f;
       }
       if (res != nullptr && in_range) {
@@ -543,6 +554,22 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// cudaFuncSetAttribute once per kernel and device (later launches may be inside a stream capture,
+// where the fewer host-side driver calls the better)
+struct SmemOptIn {
+  unsigned long long done = 0;   // bit d: set on device d
+  template <typename K>
+  cudaError_t ensure(K kernel, uint32_t smem) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && ((done >> dev) & 1ull)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess && dev < 64) done |= 1ull << dev;
+    return e;
+  }
+};
+
 // (rows x width) fp32 row-major matrix, boxes of bk floats x box_rows rows, swizzle span = bk floats
 bool make_map(CUtensorMap* map, const float* ptr, int rows, int width, int box_rows, int bk) {
   EncodeTiledFn fn = encode_fn();
@@ -578,8 +605,8 @@ cudaError_t launch_variant(const float* x, const float* w_hi, const float* w_lo,
       !make_map(&mlo, w_lo, n_total, KIN, NT, BK))
     return cudaErrorNotSupported;
   constexpr uint32_t smem = Cfg<BK, KIN, NT>::kSmemBytes;
-  const cudaError_t e = cudaFuncSetAttribute(linear256_tf32x3_kernel<OT, BK, KIN, NT>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static SmemOptIn opt_in;
+  const cudaError_t e = opt_in.ensure(linear256_tf32x3_kernel<OT, BK, KIN, NT>, smem);
   if (e != cudaSuccess) return e;
   const unsigned grid = static_cast<unsigned>((rows + kBM - 1) / kBM) * (n_total / NT);
   linear256_tf32x3_kernel<OT, BK, KIN, NT><<<grid, kThreads, smem, st>>>(
@@ -611,7 +638,8 @@ cudaError_t launch_wgrad_shape(const float* dy, const float* x, const uint8_t* r
   cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * out_total * in_total, st);
   if (e != cudaSuccess) return e;
   constexpr uint32_t smem = WgCfg<MT, NT>::kSmemBytes;
-  e = cudaFuncSetAttribute(linear256_wgrad_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static SmemOptIn opt_in;
+  e = opt_in.ensure(linear256_wgrad_kernel<MT, NT>, smem);
   if (e != cudaSuccess) return e;
   const int n_tiles = in_total / NT, tiles = (out_total / MT) * n_tiles;
   // split-K CTAs per tile: one per SM whatever the tile count -- the tensor core accumulates with
@@ -633,8 +661,9 @@ cudaError_t launch_wgrad_shape(const float* dy, const float* x, const uint8_t* r
 template <int WIDTH>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ row_mask, float* __restrict__ out,
-              float* __restrict__ dy_out, uint32_t threshold, float scale, uint32_t seed_lo,
-              uint32_t seed_hi, int rows, int rows_per_block) {
+              float* __restrict__ dy_out, uint32_t threshold, float scale, uint32_t seed_lo_host,
+              uint32_t seed_hi_host, const unsigned long long* __restrict__ seed_ptr, int rows,
+              int rows_per_block) {
   constexpr int CG = WIDTH / 4;                        // column groups of 4 floats
   constexpr int RL = CG >= 256 ? 1 : 256 / CG;         // row lanes per pass
   constexpr int PASSES = CG > 256 ? CG / 256 : 1;      // column passes (WIDTH 1024: 1)
@@ -643,6 +672,8 @@ colsum_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ row_mask
   const int cg = threadIdx.x % CG, lane_r = threadIdx.x / CG;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t seed_lo = 0, seed_hi = 0;
+  if (threshold != 0u) resolve_seed(seed_lo_host, seed_hi_host, seed_ptr, &seed_lo, &seed_hi);
   for (int r = r0 + lane_r; r < r1; r += RL) {
     if (row_mask != nullptr && row_mask[r]) continue;
     const int64_t off = static_cast<int64_t>(r) * WIDTH + 4 * cg;
@@ -727,8 +758,9 @@ cudaError_t launch_linear256_wgrad(const float* dy, const float* x, const uint8_
 
 // out[width] = column sums of dy (optionally of dropout-backward(dy), also written to dy_out)
 cudaError_t launch_colsum256(const float* dy, const uint8_t* row_mask, float* out, float* dy_out,
-                             uint32_t threshold, float scale, uint32_t seed_lo, uint32_t seed_hi, int rows,
-                             int width, int sm_count, cudaStream_t st) {
+                             uint32_t threshold, float scale, uint32_t seed_lo, uint32_t seed_hi,
+                             const unsigned long long* seed_ptr, int rows, int width, int sm_count,
+                             cudaStream_t st) {
   if (!width_ok(width)) return cudaErrorNotSupported;
   if (out != nullptr) {
     const cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * width, st);
@@ -739,8 +771,8 @@ cudaError_t launch_colsum256(const float* dy, const uint8_t* row_mask, float* ou
   rows_per_block = (rows_per_block + 7) / 8 * 8;
   const unsigned grid = (rows + rows_per_block - 1) / rows_per_block;
 #define MSDA_COLSUM(W_) \
-  colsum_kernel<W_><<<grid, 256, 0, st>>>(dy, row_mask, out, dy_out, threshold, scale, seed_lo, seed_hi, rows, \
-                                          rows_per_block)
+  colsum_kernel<W_><<<grid, 256, 0, st>>>(dy, row_mask, out, dy_out, threshold, scale, seed_lo, seed_hi, \
+                                          seed_ptr, rows, rows_per_block)
   if (width == 128) MSDA_COLSUM(128);
   else if (width == 256) MSDA_COLSUM(256);
   else MSDA_COLSUM(1024);

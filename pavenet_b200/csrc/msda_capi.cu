@@ -293,7 +293,7 @@ int dropout_params(const char* who, float p, uint32_t* threshold, float* scale) 
 int msda_linear_fused(const float* d_x, const float* d_weight, const float* d_bias,
                       const uint8_t* d_row_mask, int mask_mode, int relu, const float* d_gate,
                       float gate_scale, float dropout_p, uint64_t dropout_seed,
-                      const float* d_residual, void* d_y, int rows, int in_features, int out_features,
+                      const uint64_t* d_dropout_seed, const float* d_residual, void* d_y, int rows, int in_features, int out_features,
                       int out_dtype, float* d_scratch, void* stream) {
   if (!d_x || !d_weight || !d_y || !d_scratch)
     return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_linear_fused: NULL pointer argument");
@@ -320,6 +320,7 @@ int msda_linear_fused(const float* d_x, const float* d_weight, const float* d_bi
   if (rc) return rc;
   ep.seed_lo = static_cast<uint32_t>(dropout_seed);
   ep.seed_hi = static_cast<uint32_t>(dropout_seed >> 32);
+  ep.seed_ptr = reinterpret_cast<const unsigned long long*>(d_dropout_seed);
   ep.residual = d_residual;
   const cudaError_t e = launch_linear256(d_x, d_weight, ep, d_y, rows, in_features, out_features, out_dtype,
                                          d_scratch, static_cast<cudaStream_t>(stream));
@@ -334,7 +335,7 @@ int msda_linear256(const float* d_x, const float* d_weight, const float* d_bias,
                    const uint8_t* d_row_mask, int mask_mode, void* d_y, int rows, int in_features,
                    int out_features, int out_dtype, float* d_scratch, void* stream) {
   return msda_linear_fused(d_x, d_weight, d_bias, d_row_mask, mask_mode, 0, nullptr, 1.f, 0.f, 0, nullptr,
-                           d_y, rows, in_features, out_features, out_dtype, d_scratch, stream);
+                           nullptr, d_y, rows, in_features, out_features, out_dtype, d_scratch, stream);
 }
 
 int msda_linear256_wgrad(const float* d_grad_y, const float* d_x, const uint8_t* d_row_mask,
@@ -376,15 +377,16 @@ int msda_colsum256(const float* d_grad_y, const uint8_t* d_row_mask, float* d_gr
   int sms = 0;
   const int rc = current_sm_count(&sms);
   if (rc) return rc;
-  const cudaError_t e = launch_colsum256(d_grad_y, d_row_mask, d_grad_bias, nullptr, 0u, 1.f, 0u, 0u, rows,
-                                         width, sms, static_cast<cudaStream_t>(stream));
+  const cudaError_t e = launch_colsum256(d_grad_y, d_row_mask, d_grad_bias, nullptr, 0u, 1.f, 0u, 0u, nullptr,
+                                         rows, width, sms, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess)
     return fail(MSDA_ERR_CUDA, "msda_colsum256 launch failed: %s", cudaGetErrorString(e));
   return MSDA_OK;
 }
 
 int msda_dropout_backward(const float* d_grad_y, float* d_grad_out, float* d_grad_bias, int rows,
-                          int width, float dropout_p, uint64_t dropout_seed, void* stream) {
+                          int width, float dropout_p, uint64_t dropout_seed,
+                          const uint64_t* d_dropout_seed, void* stream) {
   if (!d_grad_y || !d_grad_out)
     return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_dropout_backward: NULL pointer argument");
   if (rows <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_dropout_backward: rows must be positive");
@@ -403,7 +405,9 @@ int msda_dropout_backward(const float* d_grad_y, float* d_grad_out, float* d_gra
   if (rc) return rc;
   const cudaError_t e = launch_colsum256(d_grad_y, nullptr, d_grad_bias, d_grad_out, threshold, scale,
                                          static_cast<uint32_t>(dropout_seed),
-                                         static_cast<uint32_t>(dropout_seed >> 32), rows, width, sms,
+                                         static_cast<uint32_t>(dropout_seed >> 32),
+                                         reinterpret_cast<const unsigned long long*>(d_dropout_seed), rows,
+                                         width, sms,
                                          static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess)
     return fail(MSDA_ERR_CUDA, "msda_dropout_backward launch failed: %s", cudaGetErrorString(e));

@@ -53,7 +53,9 @@ struct LinearEpilogue {
   float gate_scale = 1.f;
   uint32_t dropout_threshold = 0;     // keep iff hash(index, seed) >= threshold; 0 = no dropout
   float dropout_scale = 1.f;          // 1 / (1 - p)
-  uint32_t seed_lo = 0, seed_hi = 0;
+  uint32_t seed_lo = 0, seed_hi = 0;  // the 64-bit seed ...
+  const unsigned long long* seed_ptr = nullptr;  // ... plus *seed_ptr when set (device memory: lets a
+                                                 // captured CUDA graph draw new masks at every replay)
   const float* residual = nullptr;    // [rows, out] added last
 };
 bool linear_shape_supported(int in_features, int out_features);
@@ -64,8 +66,9 @@ cudaError_t launch_linear256_wgrad(const float* dy, const float* x, const uint8_
                                    int mask_mode, float* dw, int rows, int in_features, int out_features,
                                    int sm_count, cudaStream_t st);
 cudaError_t launch_colsum256(const float* dy, const uint8_t* row_mask, float* out, float* dy_out,
-                             uint32_t threshold, float scale, uint32_t seed_lo, uint32_t seed_hi, int rows,
-                             int width, int sm_count, cudaStream_t st);
+                             uint32_t threshold, float scale, uint32_t seed_lo, uint32_t seed_hi,
+                             const unsigned long long* seed_ptr, int rows, int width, int sm_count,
+                             cudaStream_t st);
 
 // adds n to the library-wide launch counter (msda_launch_count)
 void note_launches(int n);

@@ -20,7 +20,7 @@ __all__ = [
     'ms_deform_attn_backward', 'fuse_frames_as_levels', 'BF16_GRAD_VALUE_ATOMICS',
     'HostWorkspace', 'FusedMultiScaleDeformableAttnFunction', 'fused_supported',
     'Linear256Function', 'linear256', 'linear256_supported',
-    'FusedFFNFunction', 'fused_ffn', 'ffn_supported',
+    'FusedFFNFunction', 'fused_ffn', 'ffn_supported', 'device_dropout_seed',
 ]
 
 #: When value is stored in bf16, accumulate grad_value in an fp32 scratch
@@ -462,8 +462,44 @@ def _next_dropout_seed():
     return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
 
 
+class _DeviceSeed(object):
+    """Dropout seeds for code that will be captured into a CUDA graph.
+
+    A seed passed by value is baked into the captured kernel arguments, so every replay
+    would drop the same elements.  Inside `device_dropout_seed(t)` each dropout site gets a
+    fixed small offset instead and the kernels add `t[0]` (a 1-element int64 CUDA tensor)
+    to it on the device; refresh `t` between replays (`t.random_()`) for new masks."""
+    tensor = None
+    next_offset = 0
+
+
+class device_dropout_seed(object):
+    def __init__(self, seed_tensor):
+        if not (seed_tensor.is_cuda and seed_tensor.dtype == torch.int64 and seed_tensor.numel() == 1):
+            raise ValueError('device_dropout_seed needs a 1-element int64 CUDA tensor')
+        self.tensor = seed_tensor
+
+    def __enter__(self):
+        self.saved = (_DeviceSeed.tensor, _DeviceSeed.next_offset)
+        _DeviceSeed.tensor, _DeviceSeed.next_offset = self.tensor, 0
+        return self
+
+    def __exit__(self, *exc):
+        _DeviceSeed.tensor, _DeviceSeed.next_offset = self.saved
+        return False
+
+
+def _draw_seed():
+    """-> (host seed, device seed tensor or None) for one dropout site."""
+    if _DeviceSeed.tensor is not None:
+        _DeviceSeed.next_offset += 0x9E3779B97F4A7C15 % (2 ** 40)      # sites far apart in seed space
+        return _DeviceSeed.next_offset % (2 ** 62), _DeviceSeed.tensor
+    return _next_dropout_seed(), None
+
+
 def _linear_fused_raw(x2d, weight, bias=None, row_mask=None, mask_mode=0, relu=False, gate=None,
-                      gate_scale=1.0, dropout_p=0.0, seed=0, residual=None, out_dtype=torch.float32):
+                      gate_scale=1.0, dropout_p=0.0, seed=0, residual=None, out_dtype=torch.float32,
+                      seed_tensor=None):
     """One call of msda_linear_fused on 2-D contiguous fp32 tensors (see include/pavenet_msda.h
     for the order of the epilogue steps)."""
     lib = _capi.load()
@@ -476,6 +512,7 @@ def _linear_fused_raw(x2d, weight, bias=None, row_mask=None, mask_mode=0, relu=F
             x2d.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(),
             None if row_mask is None else row_mask.data_ptr(), mask_mode, int(relu),
             None if gate is None else gate.data_ptr(), gate_scale, dropout_p, seed,
+            None if seed_tensor is None else seed_tensor.data_ptr(),
             None if residual is None else residual.data_ptr(), y.data_ptr(), rows,
             n_in, n_out, _DTYPE_CODE[out_dtype], scratch.data_ptr(),
             torch.cuda.current_stream().cuda_stream)
@@ -508,7 +545,7 @@ def _colsum_raw(g, row_mask=None):
     return out
 
 
-def _dropout_backward_raw(g, dropout_p, seed, want_bias):
+def _dropout_backward_raw(g, dropout_p, seed, want_bias, seed_tensor=None):
     """g * keep / (1 - p) with the forward's keep decisions, and its column sums."""
     lib = _capi.load()
     with torch.cuda.device(g.device):
@@ -517,6 +554,7 @@ def _dropout_backward_raw(g, dropout_p, seed, want_bias):
         status = lib.msda_dropout_backward(g.data_ptr(), out.data_ptr(),
                                            None if bias is None else bias.data_ptr(), g.shape[0],
                                            g.shape[1], dropout_p, seed,
+                                           None if seed_tensor is None else seed_tensor.data_ptr(),
                                            torch.cuda.current_stream().cuda_stream)
     _capi.check(status, 'msda_dropout_backward')
     return out, bias
@@ -560,15 +598,15 @@ class Linear256Function(Function):
             if residual.shape != shape[:-1] + (n_out,) or out_dtype != torch.float32:
                 raise RuntimeError('linear256: residual must have the output shape; fp32 output only')
             res2d = _as_f32_2d(residual, n_out)
-        seed = _next_dropout_seed() if dropout_p > 0 else 0
+        seed, seed_t = _draw_seed() if dropout_p > 0 else (0, None)
         y = _linear_fused_raw(x2d, weight, None if bias is None else bias.contiguous(), mask_u8,
                               mask_mode if mask_u8 is not None else 0, dropout_p=dropout_p, seed=seed,
-                              residual=res2d, out_dtype=out_dtype)
+                              residual=res2d, out_dtype=out_dtype, seed_tensor=seed_t)
         ctx.save_for_backward(x2d, weight, mask_u8)
         ctx.mask_mode = mask_mode if mask_u8 is not None else 0
         ctx.has_bias = bias is not None
         ctx.x_shape = shape
-        ctx.dropout = (dropout_p, seed)
+        ctx.dropout = (dropout_p, seed, seed_t)
         ctx.has_residual = residual is not None
         return y.view(*shape[:-1], n_out)
 
@@ -582,10 +620,10 @@ class Linear256Function(Function):
         if ctx.has_residual and ctx.needs_input_grad[6]:
             grad_res = grad_y
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
-        dropout_p, seed = ctx.dropout
+        dropout_p, seed, seed_t = ctx.dropout
         if dropout_p > 0:
             # undo the epilogue's dropout (same keep decisions); the pass also sums the bias gradient
-            g, grad_b = _dropout_backward_raw(g, dropout_p, seed, want_b)
+            g, grad_b = _dropout_backward_raw(g, dropout_p, seed, want_b, seed_t)
         elif want_b:
             # column sums of dY in one streaming pass (masked rows skipped in mode 1)
             grad_b = _colsum_raw(g, mask_u8 if ctx.mask_mode == 1 else None)
@@ -623,13 +661,14 @@ class FusedFFNFunction(Function):
         res2d = None
         if add_identity:
             res2d = x2d if identity is None else _as_f32_2d(identity, w2.shape[0])
-        seed1 = _next_dropout_seed() if dropout_p > 0 else 0
-        seed2 = _next_dropout_seed() if dropout_p > 0 else 0
+        seed1, seed_t = _draw_seed() if dropout_p > 0 else (0, None)
+        seed2, _ = _draw_seed() if dropout_p > 0 else (0, None)
         h = _linear_fused_raw(x2d, w1, None if b1 is None else b1.contiguous(), relu=True,
-                              dropout_p=dropout_p, seed=seed1)
+                              dropout_p=dropout_p, seed=seed1, seed_tensor=seed_t)
         y = _linear_fused_raw(h, w2, None if b2 is None else b2.contiguous(), dropout_p=dropout_p,
-                              seed=seed2, residual=res2d)
+                              seed=seed2, residual=res2d, seed_tensor=seed_t)
         ctx.save_for_backward(x2d, h, w1, w2)
+        ctx.seed_tensor = seed_t
         ctx.cfg = (shape, dropout_p, seed2, b1 is not None, b2 is not None,
                    add_identity and identity is not None, add_identity and identity is None)
         return y.view(*shape[:-1], w2.shape[0])
@@ -644,7 +683,7 @@ class FusedFFNFunction(Function):
         g = _as_f32_2d(grad_y, n_out)
         # through dropout 2 (+ bias gradient of fc2 from the same pass)
         if p > 0:
-            g2, grad_b2 = _dropout_backward_raw(g, p, seed2, has_b2)
+            g2, grad_b2 = _dropout_backward_raw(g, p, seed2, has_b2, ctx.seed_tensor)
         else:
             g2, grad_b2 = g, (_colsum_raw(g) if has_b2 else None)
         grad_w2 = _wgrad_raw(g2, h, None, 0, n_out, n_hidden)

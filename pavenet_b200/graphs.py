@@ -1,0 +1,109 @@
+"""CUDA-graph capture of static-shape stages, forward and backward
+("CUDA-graph capture of a whole decoder layer").
+
+A transformer layer around the sampling op is ~100 small kernels forward and
+~200 backward; at 300 pose queries or 15 keypoint queries per person each of them
+runs for a few microseconds, so the layer's time is the host's launch rate, not the
+GPU's.  `GraphedStage` wraps a function of tensors (plus the modules / parameters
+it uses) and runs it through `torch.cuda.make_graphed_callables`: one graph launch
+for the forward, one for the backward, per distinct input signature.
+
+What makes the attention modules of this package capturable:
+  * the C-ABI launchers make no synchronising call (shapes and level starts are
+    read on the device, SM count and function attributes are host-side queries);
+  * every scratch buffer comes from torch's caching allocator (graph-private pool);
+  * dropout inside the GEMM epilogues takes its seed from device memory
+    (`functional.device_dropout_seed`), so replays draw new masks; torch's own
+    dropout is graph-safe already (Philox offset registered with the graph).
+
+Call `refresh_seed()` once per step before the first graphed stage.
+"""
+import torch
+import torch.nn as nn
+
+from .functional import device_dropout_seed
+
+# capture runs on a side stream, so the parameters' AccumulateGrad nodes (created earlier on the
+# default stream) see gradients produced on another stream; autograd inserts the event wait it
+# needs and warns once per process -- the wait is intended here
+if hasattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch'):
+    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+
+__all__ = ['GraphedStage', 'refresh_seed']
+
+_SEED = {}
+
+
+def _seed_tensor(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    t = _SEED.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int64, device='cuda:%d' % key)
+        t.random_()
+        _SEED[key] = t
+    return t
+
+
+def refresh_seed(device=None):
+    """New dropout masks for the next replay of every graphed stage on `device` (one tiny
+    kernel, outside the graphs)."""
+    _seed_tensor(device if device is not None else torch.cuda.current_device()).random_()
+
+
+class _Stage(nn.Module):
+    """fn(*tensors) with the modules / parameters it touches registered, so the capture
+    sees their parameters as graph inputs and returns their gradients."""
+
+    def __init__(self, fn, modules, params, seed, static):
+        super().__init__()
+        self.mods = nn.ModuleList(modules)
+        self.extra = nn.ParameterList(params)
+        self._fn, self._seed, self._static = fn, seed, static
+
+    def forward(self, *args):
+        with device_dropout_seed(self._seed):
+            if self._static is not None:
+                return self._fn(*args, static=self._static)
+            return self._fn(*args)
+
+
+class GraphedStage(object):
+    """stage = GraphedStage(fn, modules, params); out = stage(*tensors, static=None)
+
+    `static`: an optional hashable passed through to `fn(..., static=static)` for the parts of
+    the computation that are Python values (e.g. how many persons each clip holds); it is part
+    of the signature, so each distinct value gets its own graph.
+    `fn` takes and returns tensors (or tuples of tensors) of fixed shapes for a given
+    signature of its inputs, calls nothing that synchronises with the host, and uses only
+    the listed modules / parameters.  The first call with a new signature (shapes, dtypes,
+    requires_grad, training mode) runs warm-up iterations and captures; later calls replay.
+    Not an nn.Module on purpose: it must not re-register the wrapped modules in the model's
+    own module tree."""
+
+    def __init__(self, fn, modules=(), params=(), warmup_iters=3):
+        self.fn, self.modules, self.params = fn, list(modules), list(params)
+        self.warmup_iters = warmup_iters
+        self._graphs = {}
+
+    def _signature(self, args, static):
+        training = tuple(m.training for m in self.modules)
+        return (static,) + training + tuple((tuple(a.shape), a.dtype, a.requires_grad, a.device.index) for a in args)
+
+    def captured_signatures(self):
+        return list(self._graphs)
+
+    def __call__(self, *args, static=None):
+        for a in args:
+            if not (isinstance(a, torch.Tensor) and a.is_cuda):
+                raise RuntimeError('GraphedStage takes CUDA tensors only, got %r' % (type(a),))
+        key = self._signature(args, static)
+        graphed = self._graphs.get(key)
+        if graphed is None:
+            stage = _Stage(self.fn, self.modules, self.params, _seed_tensor(args[0].device), static)
+            # make_graphed_callables keys its replay on the wrapper's training flag; the wrapped
+            # modules keep their own modes (frozen BatchNorm stays in eval)
+            sample = tuple(a.detach().clone().requires_grad_(a.requires_grad) for a in args)
+            graphed = torch.cuda.make_graphed_callables(stage, sample, num_warmup_iters=self.warmup_iters,
+                                                        allow_unused_input=True)
+            self._graphs[key] = graphed
+        return graphed(*args)

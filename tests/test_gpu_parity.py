@@ -887,10 +887,10 @@ def test_ffn_module_variants():
     assert sorted(ffn.state_dict()) == ['layers.0.0.bias', 'layers.0.0.weight', 'layers.1.bias',
                                         'layers.1.weight']
     core = ffn.layers[1](torch.relu(ffn.layers[0][0](x)))
-    assert rel_err(ffn(x), x + core) < 1e-5
-    assert rel_err(ffn(x, identity=ident), ident + core) < 1e-5
+    assert rel_err(ffn(x), x + core) < 3e-5
+    assert rel_err(ffn(x, identity=ident), ident + core) < 3e-5
     ffn.add_identity = False
-    assert rel_err(ffn(x), core) < 1e-5
+    assert rel_err(ffn(x), core) < 3e-5
     ffn.add_identity, ffn.tensor_core_linear = True, False
     assert rel_err(ffn(x), x + core) < 1e-6
     gelu = pavenet_b200.build_feedforward_network(
@@ -966,6 +966,41 @@ def test_clip_model_training_step_small():
     assert not torch.equal(before, model.encoder[0].attn.value_proj.weight)
 
 
+def test_clip_model_graphed_step_equals_eager():
+    """Backbone, encoder, pose decoder and joint decoder replayed from CUDA graphs give the
+    eager step's losses and gradients (dropout off so the two runs are comparable)."""
+    from pavenet_b200 import clip_model
+    torch.manual_seed(0)
+    model = clip_model.PaveNetR50(num_query=50).cuda().train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+        if hasattr(m, 'ffn_drop'):
+            m.ffn_drop = 0.0
+    batch = clip_model.synthetic_clip_batch(2, 'cuda', seed=3, height=256, width=352)
+    params = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+
+    def run():
+        for _, p in params:
+            p.grad = None
+        losses = model(*batch)
+        sum(losses.values()).backward()
+        return {k: v.detach().clone() for k, v in losses.items()}, {n: p.grad.clone() for n, p in params}
+
+    l_eager, g_eager = run()
+    model.enable_graphs()
+    run()                                                   # captures
+    l_graph, g_graph = run()                                # replays
+    assert set(l_graph) == set(l_eager)
+    for k in l_eager:
+        assert rel_err(l_graph[k], l_eager[k]) < 1e-4, k
+    for n in g_eager:
+        assert rel_err(g_graph[n], g_eager[n]) < 2e-3, n
+    assert all(len(st.captured_signatures()) == 1 for st in model._graphed.values())
+
+
 @pytest.mark.parametrize('pinned', [True, False])
 def test_host_buffer_entry_points(pinned):
     """msda_forward_host / msda_forward_backward_host (pipelined over batch
@@ -1000,3 +1035,89 @@ def test_loaded_library_is_in_tree():
     assert pavenet_b200._capi.launch_count() == before + 1
     assert os.path.dirname(pavenet_b200._build.LIB_PATH).endswith(os.path.join('pavenet_b200', 'lib'))
     assert lib.msda_abi_version() == 1
+
+
+# --------------------------------------------------------------------------
+# CUDA-graph capture of a transformer layer around the op (forward + backward)
+# --------------------------------------------------------------------------
+def _encoder_layer(drop):
+    import pavenet_b200
+    torch.manual_seed(3)
+    attn = pavenet_b200.MultiScaleDeformableAttention(embed_dims=256, batch_first=True, dropout=drop).cuda()
+    ffn = pavenet_b200.FFN(256, 1024, ffn_drop=drop).cuda()
+    norm = torch.nn.LayerNorm(256).cuda()
+    with torch.no_grad():
+        for name, p in attn.named_parameters():
+            if 'sampling_offsets' in name or 'attention_weights' in name:
+                p.add_(torch.randn_like(p) * 0.05)
+
+    def layer(x, pos, ref, shapes, lsi):
+        return ffn(norm(attn(x, query_pos=pos, reference_points=ref, spatial_shapes=shapes,
+                             level_start_index=lsi)))
+    return layer, [attn, ffn, norm]
+
+
+def test_graphed_stage_matches_eager():
+    """One encoder layer (attention module with fused prologue and tensor-core projections,
+    LayerNorm, fused FFN) replayed from a CUDA graph: same output and gradients as eager."""
+    from pavenet_b200 import graphs
+    g = torch.Generator().manual_seed(21)
+    shapes = torch.tensor(MID_LEVELS).cuda()
+    lsi = O.level_start_index(shapes.cpu()).cuda()
+    S, B = int(shapes.prod(1).sum()), 2
+    layer, mods = _encoder_layer(0.0)
+    params = [p for m in mods for p in m.parameters()]
+    x0 = torch.randn(B, S, 256, generator=g).cuda()
+    pos = torch.randn(B, S, 256, generator=g).cuda()
+    ref = torch.rand(B, S, 4, 2, generator=g).cuda()
+    go = torch.randn(B, S, 256, generator=g).cuda()
+
+    def run(fn, x_in):
+        for p in params:
+            p.grad = None
+        x = x_in.clone().requires_grad_()
+        out = fn(x, pos, ref, shapes, lsi)
+        out.backward(go)
+        return out.detach().clone(), x.grad.clone(), [p.grad.clone() for p in params]
+
+    eager = run(layer, x0)
+    stage = graphs.GraphedStage(layer, mods)
+    run(stage, x0)                                     # captures
+    assert len(stage.captured_signatures()) == 1
+    for x_in, want in ((x0, eager), (x0 * 0.5, run(layer, x0 * 0.5))):     # replays, second with new data
+        got = run(stage, x_in)
+        assert rel_err(got[0], want[0]) < 1e-5
+        assert rel_err(got[1], want[1]) < 2e-4
+        for a, b_ in zip(got[2], want[2]):
+            assert rel_err(a, b_) < 2e-4
+    assert len(stage.captured_signatures()) == 1
+
+
+def test_graphed_stage_redraws_epilogue_dropout():
+    """Dropout inside the GEMM epilogues reads its seed from device memory, so a replayed graph
+    draws new masks after refresh_seed() and the same ones without it; the backward uses the
+    forward's masks."""
+    from pavenet_b200 import graphs
+    g = torch.Generator().manual_seed(22)
+    shapes = torch.tensor(MID_LEVELS).cuda()
+    lsi = O.level_start_index(shapes.cpu()).cuda()
+    S, B = int(shapes.prod(1).sum()), 1
+    layer, mods = _encoder_layer(0.1)
+    for m in mods:
+        m.train()
+    x = torch.randn(B, S, 256, generator=g).cuda().requires_grad_()
+    pos = torch.randn(B, S, 256, generator=g).cuda()
+    ref = torch.rand(B, S, 4, 2, generator=g).cuda()
+    stage = graphs.GraphedStage(layer, mods)
+    stage(x, pos, ref, shapes, lsi)                    # captures
+    graphs.refresh_seed()
+    a = stage(x, pos, ref, shapes, lsi).detach().clone()
+    b = stage(x, pos, ref, shapes, lsi).detach().clone()
+    assert torch.equal(a, b)                           # same seed, same masks
+    graphs.refresh_seed()
+    out = stage(x, pos, ref, shapes, lsi)
+    assert (out.detach() != a).float().mean() > 0.5    # new masks
+    # gradient of sum(out) wrt x under the replayed masks == finite-difference-free check: the
+    # dropped FFN-output elements contribute exactly the identity path
+    out.sum().backward()
+    assert torch.isfinite(x.grad).all() and x.grad.abs().max() > 0

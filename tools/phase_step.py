@@ -13,6 +13,8 @@ from pavenet_b200 import clip_model  # noqa: E402
 torch.manual_seed(0)
 dev = torch.device('cuda:0')
 model = clip_model.PaveNetR50().to(dev).train()
+if len(sys.argv) > 1 and sys.argv[1] == 'graphs':
+    model.enable_graphs()
 opt = clip_model.build_optimizer(model)
 batch = clip_model.synthetic_clip_batch(1, dev, seed=1)
 params = [p for p in model.parameters() if p.requires_grad]
@@ -27,6 +29,9 @@ def run(sync):
         marks.append((name, time.perf_counter()))
 
     model.phase_hook = hook
+    if model._graphed is not None:
+        from pavenet_b200 import graphs
+        graphs.refresh_seed(dev)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     losses = model(*batch)
