@@ -322,13 +322,20 @@ def run_model_step(args, world, rank, local):
     model = clip_model.PaveNetR50(value_dtype=vdt).to(device).train()
     if args.graphs:
         model.enable_graphs()
-    ddp = DDP(model, device_ids=[local], broadcast_buffers=False) if world > 1 else None
+    ddp = flat = None
+    if args.grad_exchange == 'ddp':
+        ddp = DDP(model, device_ids=[local], broadcast_buffers=False) if world > 1 else None
+    else:
+        if world > 1:                                  # same initial weights on every rank
+            for p in model.parameters():
+                dist.broadcast(p.data, 0)
+        flat = clip_model.FlatGradients(model)
     opt = clip_model.build_optimizer(model)
     clips_per_gpu = 1
     batches = [clip_model.synthetic_clip_batch(clips_per_gpu, device, seed=100 * rank + i)
                for i in range(2)]
     for i in range(args.warmup):
-        clip_model.train_step(model, opt, *batches[i % 2], ddp_model=ddp)
+        clip_model.train_step(model, opt, *batches[i % 2], ddp_model=ddp, flat_grads=flat)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -338,7 +345,7 @@ def run_model_step(args, world, rank, local):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        loss = clip_model.train_step(model, opt, *batches[i % 2], ddp_model=ddp)
+        loss = clip_model.train_step(model, opt, *batches[i % 2], ddp_model=ddp, flat_grads=flat)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -355,9 +362,9 @@ def run_model_step(args, world, rank, local):
             'dtype': 'f32 (TF32 convolutions, fp32 GEMMs)' + ('' if vdt is None else ', bf16 value storage'),
             'data': 'synthetic',
             'config': {'workload': 'pavenet_step', 'description': 'PAVE-Net R-50, T=3 frames at 800x1333, '
-                       '1 clip per GPU, forward + backward + DDP all-reduce + grad-clip + AdamW',
+                       '1 clip per GPU, forward + backward + gradient all-reduce (NCCL) + grad-clip + AdamW',
                        'trainable_params': n_params, 'parallelism': 'clip-sharded DDP x%d' % world,
-                       'cuda_graphs': bool(args.graphs),
+                       'cuda_graphs': bool(args.graphs), 'grad_exchange': args.grad_exchange,
                        'l2_policy': 'inputs larger than L2 (activations of a 3x800x1333 clip)'},
             'roofline': None, 'cpu_baseline': None, 'e2e': None,
             'clocks': clock_info, 'gpu_launches': int(_capi.launch_count() - launches0),
@@ -395,7 +402,8 @@ def main():
     ap.add_argument('--workload', default='encoder_cfg2',
                     choices=sorted(WORKLOADS) + list(MODEL_WORKLOADS))
     ap.add_argument('--value-dtype', default='f32', choices=['f32', 'bf16'])
-    ap.add_argument('--graphs', type=int, default=0, help='pavenet_step: run backbone, encoder and pose decoder as CUDA graphs (fwd + bwd)')
+    ap.add_argument('--grad-exchange', default='flat', choices=['flat', 'ddp'], help='pavenet_step: one all-reduce of a flat gradient bucket, or torch DDP')
+    ap.add_argument('--graphs', type=int, default=1, help='pavenet_step: run backbone, encoder and pose decoder as CUDA graphs (fwd + bwd)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--sets', type=int, default=4, help='distinct input sets rotated per step')

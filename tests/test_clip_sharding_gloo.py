@@ -78,3 +78,39 @@ def test_world_size_2_gloo(tmp_path):
     # every clip was produced by exactly one rank
     assert ((g != 0).sum(0) == 1).all()
     assert torch.equal(g.sum(0), torch.arange(1, clips + 1, dtype=torch.float64) ** 2)
+
+
+def _flat_worker(rank, world, port, out_dir):
+    """The gradient exchange of the clip-sharded training step: every .grad is a view into one
+    flat bucket, one all-reduce averages it (clip_model.FlatGradients)."""
+    from pavenet_b200 import clip_model
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port),
+                      RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)                               # same weights on every rank
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+        net[0].bias.requires_grad_(False)                  # frozen parameters stay out of the bucket
+        flat = clip_model.FlatGradients(net)
+        x = torch.full((3, 6), float(rank + 1))            # each rank sees its own clip
+        for _ in range(2):                                 # second pass: zero() really clears the views
+            flat.zero()
+            net(x).square().sum().backward()
+            local = flat.flat.clone()
+            flat.all_reduce_mean()
+        views_ok = all(p.grad.data_ptr() >= flat.flat.data_ptr() for p in flat.params)
+        torch.save(dict(local=local, reduced=flat.flat.clone(), views_ok=views_ok,
+                        n=sum(p.numel() for p in flat.params)), os.path.join(out_dir, 'f%d.pt' % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_bucket_all_reduce_gloo(tmp_path):
+    world = 2
+    mp.spawn(_flat_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(os.path.join(str(tmp_path), 'f%d.pt' % r)) for r in range(world)]
+    mean = (res[0]['local'] + res[1]['local']) / 2
+    for r in res:
+        assert r['views_ok'] and r['n'] == 6 * 5 + 5 * 2 + 2 == r['reduced'].numel()
+        assert torch.allclose(r['reduced'], mean, rtol=1e-6, atol=1e-7)
+    assert not torch.allclose(res[0]['local'], res[1]['local'])
