@@ -255,6 +255,26 @@ def measure_cpu_baseline(wl, budget_s=20.0):
 
 
 # ---------------------------------------------------------------------------
+_JSON_OUT = None
+
+
+def protect_stdout():
+    """The caller reads ONE JSON line from stdout; native libraries write there too (NCCL prints
+    its version banner to fd 1 at NCCL_DEBUG >= VERSION).  Keep a private duplicate of stdout for
+    the JSON line and point fd 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(text):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(text + '\n')
+    out.flush()
+
+
 def dist_setup(gpus):
     # NCCL announces its version on STDOUT at NCCL_DEBUG=VERSION, which would precede the
     # one JSON line this script owes its caller
@@ -303,7 +323,7 @@ def run_reference_arm(args, world, rank):
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def run_model_step(args, world, rank, local):
@@ -355,7 +375,7 @@ def run_model_step(args, world, rank, local):
     clips = clip_sharding.sum_over_ranks(clips_per_gpu * args.steps, device)
     if rank == 0:
         n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
-        print(json.dumps({
+        emit(json.dumps({
             'metric': 'PAVE-Net R-50 training clips/s', 'value': clips / (ms * 1e-3), 'unit': 'clips/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -363,12 +383,12 @@ def run_model_step(args, world, rank, local):
             'data': 'synthetic',
             'config': {'workload': 'pavenet_step', 'description': 'PAVE-Net R-50, T=3 frames at 800x1333, '
                        '1 clip per GPU, forward + backward + gradient all-reduce (NCCL) + grad-clip + AdamW',
-                       'trainable_params': n_params, 'parallelism': 'clip-sharded DDP x%d' % world,
+                       'trainable_params': n_params, 'parallelism': 'clip-sharded data parallel x%d' % world,
                        'cuda_graphs': bool(args.graphs), 'grad_exchange': args.grad_exchange,
                        'l2_policy': 'inputs larger than L2 (activations of a 3x800x1333 clip)'},
             'roofline': None, 'cpu_baseline': None, 'e2e': None,
             'clocks': clock_info, 'gpu_launches': int(_capi.launch_count() - launches0),
-            'final_loss': float(loss)}), flush=True)
+            'final_loss': float(loss)}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -394,6 +414,7 @@ def load_traffic(workload, kernel_key):
 
 
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)
@@ -416,7 +437,7 @@ def main():
     if args.workload in MODEL_WORKLOADS:
         if args.impl == 'reference':
             if rank == 0:
-                print(json.dumps({'impl': 'reference', 'unavailable':
+                emit(json.dumps({'impl': 'reference', 'unavailable':
                                   'the reference model cannot be imported here (mmcv/mmdet/opera '
                                   'dependencies absent); only the op has a CPU reference arm'}))
             return
@@ -647,7 +668,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N = 1 only
             line['cpu_baseline'] = measure_cpu_baseline(wl)
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
