@@ -218,6 +218,23 @@ int msda_dropout_backward(const float *d_grad_y, float *d_grad_out,
                           void *stream);
 
 /*
+ * LayerNorm over the channel dimension, the `norm` step after every attention
+ * module and feed-forward block of the reference's transformer layers
+ * (operation_order ('self_attn', 'norm', 'ffn', 'norm'); mmcv builds nn.LayerNorm(256)).
+ * width must be 256.  Forward writes y and the per-row mean / 1/sqrt(var + eps) the
+ * backward needs; backward makes one pass over (x, grad_y) and overwrites grad_x,
+ * grad_gamma[width] and grad_beta[width].  Biased variance, as torch.
+ */
+int msda_layernorm_forward(const float *d_x, const float *d_gamma, const float *d_beta,
+                           float *d_y, float *d_mean, float *d_rstd, int rows,
+                           int width, float eps, void *stream);
+
+int msda_layernorm_backward(const float *d_x, const float *d_grad_y,
+                            const float *d_gamma, const float *d_mean,
+                            const float *d_rstd, float *d_grad_x, float *d_grad_gamma,
+                            float *d_grad_beta, int rows, int width, void *stream);
+
+/*
  * Host-buffer convenience entry points (what a cgo / JNI / ctypes caller
  * without its own device memory management binds).  All pointers are HOST
  * pointers (pinned memory gives asynchronous copies; pageable memory works

@@ -15,12 +15,12 @@ There is no CPU path: ops raise if the CUDA library is missing or a tensor is
 not on a CUDA device.
 """
 from . import _capi
-from .functional import (FusedFFNFunction, FusedMultiScaleDeformableAttnFunction, HostWorkspace,
+from .functional import (LayerNorm256Function, layer_norm256, FusedFFNFunction, FusedMultiScaleDeformableAttnFunction, HostWorkspace,
                          Linear256Function, MultiScaleDeformableAttnFunction, ext_module,
                          ffn_supported, fused_ffn, fused_supported, linear256, linear256_supported,
                          fuse_frames_as_levels, ms_deform_attn_backward,
                          ms_deform_attn_forward)
-from .modules import (FFN, MulFramesMultiScaleDeformableAttentionNumFrames3,
+from .modules import (FFN, LayerNorm, MulFramesMultiScaleDeformableAttentionNumFrames3,
                       MulFramesMultiScaleDeformableAttentionNumFrames5,
                       MulFramesMultiScaleDeformablePoseAttentionNumFrames3,
                       MulFramesMultiScaleDeformablePoseAttentionNumFrames5,
@@ -36,7 +36,7 @@ __all__ = [
     'ms_deform_attn_backward', 'fuse_frames_as_levels', 'HostWorkspace',
     'FusedMultiScaleDeformableAttnFunction', 'fused_supported', 'Linear256Function',
     'linear256', 'linear256_supported', 'FusedFFNFunction', 'fused_ffn', 'ffn_supported', 'FFN',
-    'FEEDFORWARD_NETWORK', 'build_feedforward_network',
+    'FEEDFORWARD_NETWORK', 'build_feedforward_network', 'LayerNorm', 'LayerNorm256Function', 'layer_norm256',
     'MultiScaleDeformableAttention', 'MultiScaleDeformablePoseAttention',
     'MulFramesMultiScaleDeformablePoseAttentionNumFrames3',
     'MulFramesMultiScaleDeformablePoseAttentionNumFrames5',

@@ -18,6 +18,7 @@ EXPORTED_SYMBOLS = (
     'msda_kernel_name', 'msda_forward', 'msda_backward', 'msda_fused_forward',
     'msda_fused_backward', 'msda_linear256', 'msda_linear256_wgrad',
     'msda_colsum256', 'msda_linear_fused', 'msda_dropout_backward',
+    'msda_layernorm_forward', 'msda_layernorm_backward',
     'msda_workspace_create', 'msda_workspace_destroy', 'msda_workspace_set_piece_bytes',
     'msda_host_alloc',
     'msda_host_free', 'msda_forward_host',
@@ -64,6 +65,10 @@ def _declare(lib):
     lib.msda_dropout_backward.restype = c_int
     lib.msda_dropout_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_float,
                                           ctypes.c_uint64, c_void_p, c_void_p]
+    lib.msda_layernorm_forward.restype = c_int
+    lib.msda_layernorm_forward.argtypes = [c_void_p] * 6 + [c_int, c_int, ctypes.c_float, c_void_p]
+    lib.msda_layernorm_backward.restype = c_int
+    lib.msda_layernorm_backward.argtypes = [c_void_p] * 8 + [c_int, c_int, c_void_p]
     lib.msda_colsum256.restype = c_int
     lib.msda_colsum256.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
     lib.msda_workspace_create.restype = c_int

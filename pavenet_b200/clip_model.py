@@ -104,7 +104,7 @@ class EncoderLayer(nn.Module):
         # batch_first: tokens stay (frames, S, 256) through the encoder, so no projection needs a
         # transposing copy (a constructor option of the reference class, multi_scale_deform_attn.py:244)
         self.attn = MultiScaleDeformableAttention(embed_dims=256, value_dtype=value_dtype, batch_first=True)
-        self.norm1, self.ffn, self.norm2 = nn.LayerNorm(256), FFN(), nn.LayerNorm(256)
+        self.norm1, self.ffn, self.norm2 = modules.LayerNorm(256), FFN(), modules.LayerNorm(256)
 
     def forward(self, x, pos, mask, ref, shapes, lsi):
         x = self.norm1(self.attn(x, query_pos=pos, key_padding_mask=mask, reference_points=ref,
@@ -116,8 +116,8 @@ class DecoderLayer(nn.Module):
     def __init__(self, cross):
         super().__init__()
         self.self_attn, self.cross = SelfAttention(), cross
-        self.norm1, self.norm2, self.ffn, self.norm3 = (nn.LayerNorm(256), nn.LayerNorm(256), FFN(),
-                                                        nn.LayerNorm(256))
+        self.norm1, self.norm2, self.ffn, self.norm3 = (modules.LayerNorm(256), modules.LayerNorm(256), FFN(),
+                                                        modules.LayerNorm(256))
 
     def forward(self, x, pos, **cross_kw):
         x = self.norm1(self.self_attn(x, pos))
@@ -177,7 +177,7 @@ class PaveNetR50(nn.Module):
         self.pos_enc = SinePositionalEncoding()
         self.level_embeds = nn.Parameter(torch.randn(4, 256))
         self.encoder = nn.ModuleList(EncoderLayer(value_dtype) for _ in range(6))
-        self.enc_output, self.enc_output_norm = nn.Linear(256, 256), nn.LayerNorm(256)
+        self.enc_output, self.enc_output_norm = nn.Linear(256, 256), modules.LayerNorm(256)
         K = num_keypoints
         self.decoder = nn.ModuleList(
             DecoderLayer(MulFramesMultiScaleDeformablePoseAttentionNumFrames3(

@@ -414,6 +414,47 @@ int msda_dropout_backward(const float* d_grad_y, float* d_grad_out, float* d_gra
   return MSDA_OK;
 }
 
+int msda_layernorm_forward(const float* d_x, const float* d_gamma, const float* d_beta, float* d_y,
+                           float* d_mean, float* d_rstd, int rows, int width, float eps, void* stream) {
+  if (!d_x || !d_gamma || !d_beta || !d_y || !d_mean || !d_rstd)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_layernorm_forward: NULL pointer argument");
+  if (rows <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_layernorm_forward: rows must be positive");
+  if (!layernorm_width_supported(width))
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_layernorm_forward: width must be 256, got %d", width);
+  if (misaligned16(d_x) || misaligned16(d_gamma) || misaligned16(d_beta) || misaligned16(d_y))
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_layernorm_forward needs 16-byte aligned buffers");
+  int sms = 0;
+  const int rc = current_sm_count(&sms);
+  if (rc) return rc;
+  const cudaError_t e = launch_layernorm_forward(d_x, d_gamma, d_beta, d_y, d_mean, d_rstd, rows, eps, sms,
+                                                 static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess)
+    return fail(MSDA_ERR_CUDA, "msda_layernorm_forward launch failed: %s", cudaGetErrorString(e));
+  return MSDA_OK;
+}
+
+int msda_layernorm_backward(const float* d_x, const float* d_grad_y, const float* d_gamma,
+                            const float* d_mean, const float* d_rstd, float* d_grad_x,
+                            float* d_grad_gamma, float* d_grad_beta, int rows, int width, void* stream) {
+  if (!d_x || !d_grad_y || !d_gamma || !d_mean || !d_rstd || !d_grad_x || !d_grad_gamma || !d_grad_beta)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_layernorm_backward: NULL pointer argument");
+  if (rows <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_layernorm_backward: rows must be positive");
+  if (!layernorm_width_supported(width))
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_layernorm_backward: width must be 256, got %d", width);
+  if (misaligned16(d_x) || misaligned16(d_grad_y) || misaligned16(d_gamma) || misaligned16(d_grad_x) ||
+      misaligned16(d_grad_gamma) || misaligned16(d_grad_beta))
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_layernorm_backward needs 16-byte aligned buffers");
+  int sms = 0;
+  const int rc = current_sm_count(&sms);
+  if (rc) return rc;
+  const cudaError_t e = launch_layernorm_backward(d_x, d_grad_y, d_gamma, d_mean, d_rstd, d_grad_x,
+                                                  d_grad_gamma, d_grad_beta, rows, sms,
+                                                  static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess)
+    return fail(MSDA_ERR_CUDA, "msda_layernorm_backward launch failed: %s", cudaGetErrorString(e));
+  return MSDA_OK;
+}
+
 // ---------------------------------------------------------------------------
 // host-buffer entry points
 //

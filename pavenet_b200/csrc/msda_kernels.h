@@ -70,6 +70,15 @@ cudaError_t launch_colsum256(const float* dy, const uint8_t* row_mask, float* ou
                              const unsigned long long* seed_ptr, int rows, int width, int sm_count,
                              cudaStream_t st);
 
+// LayerNorm over 256 channels, layernorm.cu
+bool layernorm_width_supported(int width);
+cudaError_t launch_layernorm_forward(const float* x, const float* gamma, const float* beta, float* y,
+                                     float* mean, float* rstd, int rows, float eps, int sm_count,
+                                     cudaStream_t st);
+cudaError_t launch_layernorm_backward(const float* x, const float* dy, const float* gamma, const float* mean,
+                                      const float* rstd, float* dx, float* dgamma, float* dbeta, int rows,
+                                      int sm_count, cudaStream_t st);
+
 // adds n to the library-wide launch counter (msda_launch_count)
 void note_launches(int n);
 

@@ -21,6 +21,7 @@ __all__ = [
     'HostWorkspace', 'FusedMultiScaleDeformableAttnFunction', 'fused_supported',
     'Linear256Function', 'linear256', 'linear256_supported',
     'FusedFFNFunction', 'fused_ffn', 'ffn_supported', 'device_dropout_seed',
+    'LayerNorm256Function', 'layer_norm256', 'layer_norm_supported',
 ]
 
 #: When value is stored in bf16, accumulate grad_value in an fp32 scratch
@@ -711,3 +712,56 @@ def fused_ffn(x, w1, b1, w2, b2, dropout_p=0.0, identity=None, add_identity=True
     """identity + dropout(fc2(dropout(relu(fc1(x))))); identity=None means x itself;
     add_identity=False leaves the residual out."""
     return FusedFFNFunction.apply(x, w1, b1, w2, b2, float(dropout_p), identity, bool(add_identity))
+
+
+# ---------------------------------------------------------------------------
+# LayerNorm(256): the `norm` step after every attention module / feed-forward block
+# ---------------------------------------------------------------------------
+def layer_norm_supported(x, weight, bias):
+    """True when `layer_norm256` has kernels: fp32 CUDA, 256 channels, affine."""
+    return (x.is_cuda and x.dtype == torch.float32 and x.shape[-1] == 256 and x.numel() > 0
+            and weight is not None and bias is not None and weight.dtype == torch.float32
+            and weight.numel() == 256 and bias.numel() == 256)
+
+
+class LayerNorm256Function(Function):
+    """nn.LayerNorm(256) forward / backward as two streaming kernels (layernorm.cu): the
+    backward writes grad_x and both parameter gradients in one pass over (x, grad_y)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        lib = _capi.load()
+        x2d = _as_f32_2d(x, 256)
+        weight, bias = weight.contiguous(), bias.contiguous()
+        rows = x2d.shape[0]
+        with torch.cuda.device(x2d.device):
+            y = torch.empty_like(x2d)
+            stats = torch.empty((2, rows), dtype=torch.float32, device=x2d.device)
+            status = lib.msda_layernorm_forward(
+                x2d.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(), stats[0].data_ptr(),
+                stats[1].data_ptr(), rows, 256, eps, torch.cuda.current_stream().cuda_stream)
+        _capi.check(status, 'msda_layernorm_forward')
+        ctx.save_for_backward(x2d, weight, stats)
+        ctx.x_shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_y):
+        lib = _capi.load()
+        x2d, weight, stats = ctx.saved_tensors
+        g = _as_f32_2d(grad_y, 256)
+        with torch.cuda.device(g.device):
+            grad_x = torch.empty_like(x2d)
+            grad_wb = torch.empty((2, 256), dtype=torch.float32, device=g.device)
+            status = lib.msda_layernorm_backward(
+                x2d.data_ptr(), g.data_ptr(), weight.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
+                grad_x.data_ptr(), grad_wb[0].data_ptr(), grad_wb[1].data_ptr(), x2d.shape[0], 256,
+                torch.cuda.current_stream().cuda_stream)
+        _capi.check(status, 'msda_layernorm_backward')
+        return grad_x.view(ctx.x_shape), grad_wb[0], grad_wb[1], None
+
+
+def layer_norm256(x, weight, bias, eps=1e-5):
+    """Functional front-end of `LayerNorm256Function`."""
+    return LayerNorm256Function.apply(x, weight, bias, float(eps))

@@ -33,8 +33,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .functional import (FusedMultiScaleDeformableAttnFunction, MultiScaleDeformableAttnFunction,
-                         ffn_supported, fuse_frames_as_levels, fused_ffn, fused_supported, linear256,
-                         linear256_supported)
+                         ffn_supported, fuse_frames_as_levels, fused_ffn, fused_supported, layer_norm256,
+                         layer_norm_supported, linear256, linear256_supported)
 from .registry import ATTENTION, FEEDFORWARD_NETWORK, OPERA_ATTENTION
 
 __all__ = [
@@ -42,7 +42,7 @@ __all__ = [
     'MulFramesMultiScaleDeformablePoseAttentionNumFrames3',
     'MulFramesMultiScaleDeformablePoseAttentionNumFrames5',
     'MulFramesMultiScaleDeformableAttentionNumFrames3',
-    'MulFramesMultiScaleDeformableAttentionNumFrames5', 'FFN',
+    'MulFramesMultiScaleDeformableAttentionNumFrames5', 'FFN', 'LayerNorm',
 ]
 
 _FRAME_PREFIXES = {3: ('pre_', '', 'next_'),
@@ -741,3 +741,17 @@ class FFN(nn.Module):
         if identity is None:
             identity = x
         return identity + self.dropout_layer(out)
+
+
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm (what mmcv's `build_norm_layer(dict(type='LN'), 256)` returns for the `norm`
+    steps of the transformer layers; same parameters and state-dict names) running on the
+    streaming kernels of layernorm.cu when the input is fp32 CUDA with 256 channels."""
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError('pavenet_b200 modules run on CUDA tensors only (there is no CPU '
+                               'fallback); got x on %s' % x.device)
+        if tuple(self.normalized_shape) == (256,) and layer_norm_supported(x, self.weight, self.bias):
+            return layer_norm256(x, self.weight, self.bias, self.eps)
+        return super().forward(x)

@@ -1037,6 +1037,38 @@ def test_loaded_library_is_in_tree():
     assert lib.msda_abi_version() == 1
 
 
+@pytest.mark.parametrize('shape', [(1, 256), (7, 3, 256), (3, 22223, 256), (300, 1, 256)])
+def test_layer_norm_matches_torch(shape):
+    """LayerNorm(256) forward / backward kernels against torch (fp64 reference for the bound)."""
+    import pavenet_b200
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.randn(*shape, generator=g) * 3 + 1.5).cuda().requires_grad_()
+    ln = pavenet_b200.LayerNorm(256).cuda()
+    with torch.no_grad():
+        ln.weight.copy_(torch.randn(256, generator=g))
+        ln.bias.copy_(torch.randn(256, generator=g))
+    assert sorted(ln.state_dict()) == ['bias', 'weight']
+    go = torch.randn(*shape, generator=g).cuda()
+    y = ln(x)
+    y.backward(go)
+    got = (y.detach(), x.grad.clone(), ln.weight.grad.clone(), ln.bias.grad.clone())
+    x64 = x.detach().double().requires_grad_()
+    w64, b64 = ln.weight.detach().double().requires_grad_(), ln.bias.detach().double().requires_grad_()
+    y64 = torch.nn.functional.layer_norm(x64, (256,), w64, b64, ln.eps)
+    y64.backward(go.double())
+    ref = (y64.detach(), x64.grad, w64.grad, b64.grad)
+    for t in (x, ln.weight, ln.bias):
+        t.grad = None
+    yt = torch.nn.functional.layer_norm(x, (256,), ln.weight, ln.bias, ln.eps)
+    yt.backward(go)
+    torch_err = [rel_err(a, b_) for a, b_ in zip((yt.detach(), x.grad, ln.weight.grad, ln.bias.grad), ref)]
+    for a, b_, te, name in zip(got, ref, torch_err, ('y', 'grad_x', 'grad_weight', 'grad_bias')):
+        assert rel_err(a, b_) < max(2e-6, 4 * te), (shape, name, rel_err(a, b_), te)
+    with pytest.raises(RuntimeError):
+        ln(x.detach().cpu())
+    assert pavenet_b200.LayerNorm(128).cuda()(torch.randn(4, 128).cuda()).shape == (4, 128)   # other widths: torch
+
+
 # --------------------------------------------------------------------------
 # CUDA-graph capture of a transformer layer around the op (forward + backward)
 # --------------------------------------------------------------------------
