@@ -15,6 +15,9 @@ Prints ONE JSON line on stdout (rank 0).  Keys beyond the base contract:
                 duration against the measured HBM copy peak
   roofline_fwd / roofline_step   the same for the forward kernel and for the
                 whole step (fwd + grad_value zero-fill + bwd)
+  roofline_onchip   the limiter that actually binds: 128-byte value rows gathered through
+                L1 (forward) / reduced into L2 (backward) per second against the
+                micro-benchmarked peak of that instruction stream
   cpu_baseline  the reference's CPU path (per-level grid_sample + autograd),
                 restated in oracle/msda_oracle.py, timed on this host's cores
   e2e           the same metric through the C-ABI host-buffer call
@@ -647,6 +650,20 @@ def main():
                     'algorithmic_bytes': nbytes, 'kernel_ms': ms, 'peak_source': peak_src,
                     'frac_of_8TBs_nominal': gbs / 8000.0}
 
+        # Secondary, on-chip rooflines (SURVEY.md section 8d asks for the L1 / L2 limiter next to HBM):
+        # the op gathers / reduces 4*L*P value rows per output row, all of them L2-resident, so what
+        # bounds the kernels is the rate at which an SM can gather 128-byte rows through L1 (forward)
+        # and reduce them into L2 (backward).  Peaks: tools/microbench_red.cu on this pool's B200
+        # (profiles/r01_microbench_scatter_rows.txt): ld.v4.f32 134 G rows/s, red.add.v4.f32 54 G rows/s
+        # (red.add.v4.bf16x2 89 G rows/s and half-size ld rows were not used as peaks: fp32 figures).
+        corner_rows = 4.0 * dims['B'] * dims['Q'] * dims['M'] * dims['L'] * dims['P']
+
+        def onchip(ms, peak_rows, what):
+            rate = corner_rows / (ms * 1e-3) / 1e9
+            return {'bound': what, 'achieved': rate, 'peak': peak_rows, 'unit': 'G rows/s (128-byte value rows)',
+                    'frac': rate / peak_rows, 'rows_per_launch': corner_rows,
+                    'peak_source': 'micro-benchmark, profiles/r01_microbench_scatter_rows.txt'}
+
         kname = _capi.kernel_name(dims['D'], 0, 0 if vdt == torch.float32 else 2)
         line = {
             'metric': 'deform-attn fwd+bwd queries/s', 'value': value, 'unit': 'queries/s',
@@ -662,6 +679,8 @@ def main():
             'roofline': roof(ab['bwd'], bwd_ms, 'msda_bwd_rows_kernel'),
             'roofline_fwd': roof(ab['fwd'], fwd_ms, 'msda_fwd_rows_kernel'),
             'roofline_step': roof(ab['fwd'] + ab['bwd'], fwd_ms + zero_ms + bwd_ms, 'step'),
+            'roofline_onchip': {'bwd': onchip(bwd_ms, 53.97, 'sm_to_l2_reduction'),
+                                'fwd': onchip(fwd_ms, 133.93, 'l1_gather')},
             'kernel_ms': {'fwd': fwd_ms, 'grad_value_zero_fill': zero_ms, 'bwd': bwd_ms},
             'clocks': clock_info, 'gpu_launches': int(launches), 'e2e': e2e,
             'e2e_autograd': e2e_autograd,

@@ -148,12 +148,6 @@ __device__ __forceinline__ void resolve_seed(uint32_t lo, uint32_t hi, const uns
 template <typename OT>
 __device__ __forceinline__ void store_chunk(OT* row_ptr, const float (&v)[32]);
 template <>
-__device__ __forceinline__ void store_chunk<float>(float* p, const float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 32; j += 4)
-    *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-}
-template <>
 __device__ __forceinline__ void store_chunk<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
@@ -167,6 +161,107 @@ __device__ __forceinline__ void store_chunk<__nv_bfloat16>(__nv_bfloat16* p, con
   }
 }
 
+// One thread = one output row: reads its NT accumulator columns from tensor memory 32 at a
+// time (taddr = the row's lane quarter + the accumulator's first column) and applies the epilogue.
+//
+// fp32 outputs leave through TMA: a thread writing its own 1 KB row with 16-byte stores touches 32
+// different lines per warp instruction (32 L1 wavefronts each; measured: the store phase cost as
+// much as the MMAs).  Instead each warp parks its 32 x 32 chunk in a 4 KB shared-memory tile laid
+// out in the 128-byte swizzle (16-byte unit j of row r at position j ^ (r & 7): conflict-free for
+// row-per-lane writes, and exactly what a SWIZZLE_128B tensor map expects) and lane 0 issues one
+// cp.async.bulk.tensor store per chunk, double-buffered; rows past the end are clipped by the map.
+template <typename OT, int NT>
+__device__ __forceinline__ void epilogue_row(uint32_t taddr_row, int r, int rows, int n0, int n_total,
+                                             const LinearEpilogue& ep, OT* __restrict__ y,
+                                             const CUtensorMap* map_y, uint8_t* warp_tiles, int warp_row0) {
+  constexpr bool kTmaStore = sizeof(OT) == 4;
+  const int lane = threadIdx.x & 31;
+  const bool in_range = r < rows;
+  const bool masked = in_range && ep.row_mask != nullptr && ep.mask_mode != 0 && ep.row_mask[r] != 0;
+  const int64_t row_off = static_cast<int64_t>(in_range ? r : 0) * n_total + n0;
+  OT* yrow = y + row_off;
+  const float* gate = ep.gate ? ep.gate + row_off : nullptr;
+  const float* res = ep.residual ? ep.residual + row_off : nullptr;
+  const uint32_t drop_idx0 = static_cast<uint32_t>(row_off);
+  uint32_t seed_lo = 0, seed_hi = 0;
+  if (ep.dropout_threshold != 0u) resolve_seed(ep.seed_lo, ep.seed_hi, ep.seed_ptr, &seed_lo, &seed_hi);
+#pragma unroll 1
+  for (int c0 = 0; c0 < NT; c0 += 32) {
+    uint32_t u[32];
+    const uint32_t taddr = taddr_row + c0;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+        "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]),
+          "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]),
+          "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]),
+          "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float b = ep.bias ? __ldg(ep.bias + n0 + c0 + j) : 0.f;
+      float acc = __uint_as_float(u[j]) + b;
+      if (masked) acc = (ep.mask_mode == 1) ? 0.f : b;
+      v[j] = acc;
+    }
+    if (ep.relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (gate != nullptr && in_range) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 g = __ldcs(reinterpret_cast<const float4*>(gate + c0 + j));
+        v[j] = g.x > 0.f ? v[j] * ep.gate_scale : 0.f;
+        v[j + 1] = g.y > 0.f ? v[j + 1] * ep.gate_scale : 0.f;
+        v[j + 2] = g.z > 0.f ? v[j + 2] * ep.gate_scale : 0.f;
+        v[j + 3] = g.w > 0.f ? v[j + 3] * ep.gate_scale : 0.f;
+      }
+    }
+    if (ep.dropout_threshold != 0u) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        v[j] = dropout_keep(drop_idx0 + c0 + j, seed_lo, seed_hi, ep.dropout_threshold)
+                   ? v[j] * ep.dropout_scale : 0.f;
+    }
+    if (res != nullptr && in_range) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 g = __ldcs(reinterpret_cast<const float4*>(res + c0 + j));
+        v[j] += g.x; v[j + 1] += g.y; v[j + 2] += g.z; v[j + 3] += g.w;
+      }
+    }
+    if constexpr (kTmaStore) {
+      const int buf = (c0 >> 5) & 1;
+      if (c0 >= 64) {                      // the store issued two chunks ago must have read this tile
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+      }
+      float4* tile = reinterpret_cast<float4*>(warp_tiles + buf * 4096);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        tile[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(map_y), "r"(smem_u32(tile)), "r"(n0 + c0), "r"(warp_row0)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else {
+      if (in_range) store_chunk<OT>(yrow + c0, v);
+    }
+  }
+  if constexpr (kTmaStore) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // before the tiles go away
+    __syncwarp();
+  }
+}
+
 // mask_mode: 0 none; 1 masked rows are written as zeros (mask applied after the
 // projection, multi_scale_deform_attn.py:369-371); 2 masked rows are written as
 // the bias (mask applied to the input before it, transformer.py:1706-1711).
@@ -177,7 +272,8 @@ template <typename OT, int BK, int KIN, int NT>
 __global__ void __launch_bounds__(kThreads, BK == 32 ? 1 : 2)
 linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
                         const __grid_constant__ CUtensorMap map_whi,
-                        const __grid_constant__ CUtensorMap map_wlo, const LinearEpilogue ep,
+                        const __grid_constant__ CUtensorMap map_wlo,
+                        const __grid_constant__ CUtensorMap map_y, const LinearEpilogue ep,
                         OT* __restrict__ y, int rows, int n_total) {
   using C = Cfg<BK, KIN, NT>;
   constexpr int kBK = C::kBK, kChunks = C::kChunks;
@@ -212,6 +308,7 @@ linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_whi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wlo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -280,72 +377,149 @@ linear256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
 
   if (warp < 4) {
     // epilogue: warp w owns TMEM lanes 32w .. 32w+31 = rows of the tile
-    const int r = row0 + tid;
-    const bool in_range = r < rows;
-    const bool masked = in_range && ep.row_mask != nullptr && ep.mask_mode != 0 && ep.row_mask[r] != 0;
-    const int64_t row_off = static_cast<int64_t>(in_range ? r : 0) * n_total + n0;
-    OT* yrow = y + row_off;
-    const float* gate = ep.gate ? ep.gate + row_off : nullptr;
-    const float* res = ep.residual ? ep.residual + row_off : nullptr;
-    const uint32_t drop_idx0 = static_cast<uint32_t>(row_off);
-    uint32_t seed_lo = 0, seed_hi = 0;
-    if (ep.dropout_threshold != 0u) resolve_seed(ep.seed_lo, ep.seed_hi, ep.seed_ptr, &seed_lo, &seed_hi);
-  #pragma unroll 1
-    for (int c0 = 0; c0 < NT; c0 += 32) {
-      uint32_t u[32];
-      const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
-          "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
-            "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]),
-            "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]),
-            "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]),
-            "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float v[32];
-  #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float b = ep.bias ? __ldg(ep.bias + n0 + c0 + j) : 0.f;
-        float acc = __uint_as_float(u[j]) + b;
-        if (masked) acc = (ep.mask_mode == 1) ? 0.f : b;
-        v[j] = acc;
-      }
-      if (ep.relu) {
-  #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
-      if (gate != nullptr && in_range) {
-  #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 g = __ldcs(reinterpret_cast<const float4*>(gate + c0 + j));
-          v[j] = g.x > 0.f ? v[j] * ep.gate_scale : 0.f;
-          v[j + 1] = g.y > 0.f ? v[j + 1] * ep.gate_scale : 0.f;
-          v[j + 2] = g.z > 0.f ? v[j + 2] * ep.gate_scale : 0.f;
-          v[j + 3] = g.w > 0.f ? v[j + 3] * ep.gate_scale : 0.f;
-        }
-      }
-      if (ep.dropout_threshold != 0u) {
-  #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          v[j] = dropout_keep(drop_idx0 + c0 + j, seed_lo, seed_hi, ep.dropout_threshold)
-                     ? v[j] * ep.dropout_scale : 0.f;
-      }
-      if (res != nullptr && in_range) {
-  #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 g = __ldcs(reinterpret_cast<const float4*>(res + c0 + j));
-          v[j] += g.x; v[j + 1] += g.y; v[j + 2] += g.z; v[j + 3] += g.w;
-        }
-      }
-      if (in_range) store_chunk<OT>(yrow + c0, v);
-    }
+    // (the pipeline stages are free by now: every load was consumed and every MMA has retired)
+    epilogue_row<OT, NT>(tmem_d + (static_cast<uint32_t>(warp * 32) << 16), row0 + tid, rows, n0, n_total, ep, y,
+                         &map_y, base_ptr + warp * 8192, row0 + warp * 32);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(NT));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The same product with 256 rows per CTA (tuning knob, off by default).
+//
+// The 128-row kernel above streams the split weight (hi + lo: 2 * NT * KIN * 4 bytes, 512 KB at
+// 256 x 256) from L2 into shared memory once per 128-row tile; at 66 669 rows that is 333 MB of
+// L2 -> SM traffic for 68 MB of input, and the kernel runs at the rate the L2 delivers it
+// (measured: 5.6 TB/s, 0.072 ms before the TMA-store epilogue).  Here one CTA owns 256 rows: two M = 128 accumulators side
+// by side in tensor memory (2 * NT columns, all 512 at NT = 256), so every weight chunk feeds
+// twice the MMAs -- 200 MB for the same problem.  One CTA per SM (192 KB: three 64 KB stages of
+// A_hi, A_lo (256 x 16 floats each), B_hi, B_lo), 8 consumer warps (split, epilogue: warps
+// 0-3 rows 0..127, warps 4-7 rows 128..255), thread 0 issues, warp 8 is the TMA producer.
+constexpr int kBM2 = 256, kStages2 = 3, kBK2 = 16, kConsumers2 = 256, kThreads2 = kConsumers2 + 32;
+
+template <int NT>
+struct Cfg2 {
+  static constexpr uint32_t kABytes = kBM2 * kBK2 * 4;                 // 16 KB (hi or lo)
+  static constexpr uint32_t kBBytes = NT * kBK2 * 4;
+  static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr uint32_t kTxBytes = kABytes + 2 * kBBytes;
+  static constexpr uint32_t kSmemBytes = kStages2 * kStageBytes + 1024 + 128;
+};
+
+template <typename OT, int KIN, int NT>
+__global__ void __launch_bounds__(kThreads2, 1)
+linear_m256_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x,
+                          const __grid_constant__ CUtensorMap map_whi,
+                          const __grid_constant__ CUtensorMap map_wlo,
+                          const __grid_constant__ CUtensorMap map_y, const LinearEpilogue ep,
+                          OT* __restrict__ y, int rows, int n_total) {
+  using C = Cfg<kBK2, KIN, NT>;          // swizzle / descriptor constants of the 16-float chunk
+  using C2 = Cfg2<NT>;
+  constexpr int kChunks = KIN / kBK2;
+  constexpr uint32_t kIdesc = idesc_tf32(NT, false);
+  constexpr uint32_t kABytes = C2::kABytes, kBBytes = C2::kBBytes, kStageBytes = C2::kStageBytes;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t bars = base + kStages2 * kStageBytes;   // full[3], mma_done[3], tmem slot
+  const uint32_t full0 = bars, done0 = bars + 32, tmem_slot = bars + 64;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + kStages2 * kStageBytes + 64);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_tiles = n_total / NT;
+  const int row0 = (blockIdx.x / n_tiles) * kBM2;
+  const int n0 = (blockIdx.x % n_tiles) * NT;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(2 * NT));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kStages2; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(done0 + 8 * s, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_whi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wlo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp == kConsumers2 / 32) {
+    if (tid == kConsumers2) {
+      for (int c = 0; c < kChunks; ++c) {
+        const int s = c % kStages2;
+        if (c >= kStages2) mbar_wait(done0 + 8 * s, ((c / kStages2) - 1) & 1);
+        const uint32_t bar = full0 + 8 * s, a = base + s * kStageBytes;
+        mbar_expect_tx(bar, C2::kTxBytes);
+        tma_load_2d(a, &map_x, bar, c * kBK2, row0);                           // A: 256 rows (hi, split in place)
+        tma_load_2d(a + 2 * kABytes, &map_whi, bar, c * kBK2, n0);             // B_hi
+        tma_load_2d(a + 2 * kABytes + kBBytes, &map_wlo, bar, c * kBK2, n0);   // B_lo
+      }
+    }
+  } else {
+    for (int kc = 0; kc < kChunks; ++kc) {
+      const int s = kc % kStages2;
+      mbar_wait(full0 + 8 * s, (kc / kStages2) & 1);
+      {
+        float4* a_hi = reinterpret_cast<float4*>(base_ptr + s * kStageBytes);
+        float4* a_lo = reinterpret_cast<float4*>(base_ptr + s * kStageBytes + kABytes);
+#pragma unroll
+        for (int i = tid; i < static_cast<int>(kABytes / 16); i += kConsumers2) {
+          const float4 x = a_hi[i];
+          const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+          a_hi[i] = h;
+          a_lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a = base + s * kStageBytes;
+#pragma unroll
+        for (int k = 0; k < kBK2 / kUmmaK; ++k) {
+          const uint32_t koff = k * kUmmaK * 4;
+          const uint64_t b_hi = umma_desc<C>(a + 2 * kABytes + koff);
+          const uint64_t b_lo = umma_desc<C>(a + 2 * kABytes + kBBytes + koff);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {                       // rows 128h .. 128h+127 of the tile
+            const uint32_t aoff = h * (kABytes / 2) + koff;
+            const uint64_t a_hi = umma_desc<C>(a + aoff), a_lo = umma_desc<C>(a + kABytes + aoff);
+            const uint32_t d = tmem_d + h * NT;
+            umma_tf32(d, a_lo, b_hi, kIdesc, (kc | k) != 0);
+            umma_tf32(d, a_hi, b_lo, kIdesc, 1);
+            umma_tf32(d, a_hi, b_hi, kIdesc, 1);
+          }
+        }
+        umma_commit(done0 + 8 * s);
+      }
+    }
+    constexpr int last = kChunks - 1;
+    mbar_wait(done0 + 8 * (last % kStages2), (last / kStages2) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int h = warp >> 2, q = warp & 3;                    // accumulator, TMEM lane quarter
+    epilogue_row<OT, NT>(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + h * NT,
+                         row0 + h * 128 + q * 32 + (tid & 31), rows, n0, n_total, ep, y,
+                         &map_y, base_ptr + warp * 8192, row0 + h * 128 + q * 32);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(2 * NT));
   }
 }
 
@@ -583,6 +757,22 @@ bool make_map(CUtensorMap* map, const float* ptr, int rows, int width, int box_r
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// the fp32 output (rows x width) for the epilogue's TMA stores: 32 x 32 boxes, 128-byte swizzle
+// (bf16 outputs are stored directly; they still get a valid map so the kernel signature is one)
+bool make_map_y(CUtensorMap* map, const void* ptr, int rows, int width, bool is_f32) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t elt = is_f32 ? 4 : 2;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(width) * elt};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+            const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            is_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // (rows x width) fp32 viewed as {32 floats, rows, width/32 column blocks}: one box = a 16-row slab of
 // `tile` columns laid out block-major, each block a run of 128-byte rows (MN-major SW128_32B operand)
 bool make_map_mn(CUtensorMap* map, const float* ptr, int rows, int width, int tile) {
@@ -600,9 +790,9 @@ bool make_map_mn(CUtensorMap* map, const float* ptr, int rows, int width, int ti
 template <typename OT, int BK, int KIN, int NT>
 cudaError_t launch_variant(const float* x, const float* w_hi, const float* w_lo, const LinearEpilogue& ep,
                            void* y, int rows, int n_total, cudaStream_t st) {
-  CUtensorMap mx, mhi, mlo;
+  CUtensorMap mx, mhi, mlo, my;
   if (!make_map(&mx, x, rows, KIN, kBM, BK) || !make_map(&mhi, w_hi, n_total, KIN, NT, BK) ||
-      !make_map(&mlo, w_lo, n_total, KIN, NT, BK))
+      !make_map(&mlo, w_lo, n_total, KIN, NT, BK) || !make_map_y(&my, y, rows, n_total, sizeof(OT) == 4))
     return cudaErrorNotSupported;
   constexpr uint32_t smem = Cfg<BK, KIN, NT>::kSmemBytes;
   static SmemOptIn opt_in;
@@ -610,13 +800,37 @@ cudaError_t launch_variant(const float* x, const float* w_hi, const float* w_lo,
   if (e != cudaSuccess) return e;
   const unsigned grid = static_cast<unsigned>((rows + kBM - 1) / kBM) * (n_total / NT);
   linear256_tf32x3_kernel<OT, BK, KIN, NT><<<grid, kThreads, smem, st>>>(
-      mx, mhi, mlo, ep, static_cast<OT*>(y), rows, n_total);
+      mx, mhi, mlo, my, ep, static_cast<OT*>(y), rows, n_total);
+  return cudaGetLastError();
+}
+
+template <typename OT, int KIN, int NT>
+cudaError_t launch_m256(const float* x, const float* w_hi, const float* w_lo, const LinearEpilogue& ep,
+                        void* y, int rows, int n_total, cudaStream_t st) {
+  CUtensorMap mx, mhi, mlo, my;
+  if (!make_map(&mx, x, rows, KIN, kBM2, kBK2) || !make_map(&mhi, w_hi, n_total, KIN, NT, kBK2) ||
+      !make_map(&mlo, w_lo, n_total, KIN, NT, kBK2) || !make_map_y(&my, y, rows, n_total, sizeof(OT) == 4))
+    return cudaErrorNotSupported;
+  constexpr uint32_t smem = Cfg2<NT>::kSmemBytes;
+  static SmemOptIn opt_in;
+  const cudaError_t e = opt_in.ensure(linear_m256_tf32x3_kernel<OT, KIN, NT>, smem);
+  if (e != cudaSuccess) return e;
+  const unsigned grid = static_cast<unsigned>((rows + kBM2 - 1) / kBM2) * (n_total / NT);
+  linear_m256_tf32x3_kernel<OT, KIN, NT><<<grid, kThreads2, smem, st>>>(
+      mx, mhi, mlo, my, ep, static_cast<OT*>(y), rows, n_total);
   return cudaGetLastError();
 }
 
 template <int KIN, int NT>
 cudaError_t launch_shape(const float* x, const float* w_hi, const float* w_lo, const LinearEpilogue& ep,
                          void* y, int rows, int n_total, int out_dtype, cudaStream_t st) {
+  // 256 rows per CTA: a tuning knob (PAVENET_MSDA_LINEAR_BM=256).  Measured on B200 it does not beat
+  // two resident 128-row CTAs per SM (66 669 x 256 x 256: 0.062 vs 0.058 ms; 256 -> 1024: 0.211 vs 0.189 ms).
+  if (tuning().linear_bm == 256) {
+    if (out_dtype == MSDA_BF16)
+      return launch_m256<__nv_bfloat16, KIN, NT>(x, w_hi, w_lo, ep, y, rows, n_total, st);
+    return launch_m256<float, KIN, NT>(x, w_hi, w_lo, ep, y, rows, n_total, st);
+  }
   // the 32-float K-chunk variant exists for the 256-wide projections only (tuning knob)
   if (KIN == 256 && tuning().linear_bk == 32) {
     if (out_dtype == MSDA_BF16)

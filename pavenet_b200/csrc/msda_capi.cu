@@ -38,6 +38,8 @@ const Tuning& tuning() {
     x.fwd_split = env_int("PAVENET_MSDA_FWD_SPLIT", 0);
     x.bwd_split = env_int("PAVENET_MSDA_BWD_SPLIT", 0);
     x.linear_bk = env_int("PAVENET_MSDA_LINEAR_BK", 16) == 32 ? 32 : 16;
+    x.linear_bm = env_int("PAVENET_MSDA_LINEAR_BM", 0);
+    if (x.linear_bm != 128 && x.linear_bm != 256) x.linear_bm = 0;
     return x;
   }();
   return t;

@@ -16,6 +16,7 @@ struct Tuning {
   int fwd_split = 0;  // 0 = heuristic
   int bwd_split = 0;  // 0 = heuristic
   int linear_bk = 16; // linear256 K-chunk: 16 (two CTAs per SM) or 32 (one)
+  int linear_bm = 0;  // rows per CTA: 128 (default, also 0) or 256
 };
 const Tuning& tuning();
 
