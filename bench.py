@@ -113,6 +113,19 @@ def make_problem(wl, seed, device, value_dtype=torch.float32, frames=None):
         loc = ref[None, :, None, None, None, :] + (
             off[None, None] + randn(B, Q, M, L, P, 2)) / norm[None, None, None, :, None, :]
         Lk = L
+        # experiment: hand the queries to the op in patch order (PW x PH pixel patches inside each
+        # level) instead of raster order, to measure what a patch-shaped block would gain in L1 hits
+        order = os.environ.get('PAVENET_BENCH_QUERY_ORDER', '')
+        if order.startswith('patch'):
+            pw, ph = (int(v) for v in order[5:].split('x'))
+            perm, base = [], 0
+            for h, w in levels:
+                yy, xx = torch.meshgrid(torch.arange(h, device=device), torch.arange(w, device=device),
+                                        indexing='ij')
+                key = (((yy // ph) * ((w + pw - 1) // pw) + xx // pw) * ph + yy % ph) * pw + xx % pw
+                perm.append(base + key.reshape(-1).argsort())
+                base += h * w
+            loc = loc[:, torch.cat(perm)]
     else:
         Q = cfg['Q']
         Lk = T * L

@@ -29,30 +29,23 @@ __device__ __forceinline__ void red_add_row(float* p, const float (&v)[4]) {
                "f"(v[2]), "f"(v[3])
                : "memory");
 }
-__device__ __forceinline__ void red_add_row(float* p, const float (&v)[8]) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]),
-               "f"(v[2]), "f"(v[3])
-               : "memory");
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + 4), "f"(v[4]),
-               "f"(v[5]), "f"(v[6]), "f"(v[7])
-               : "memory");
-}
-// fp32 gradient rows under bf16 value storage: a lane's 8 value channels are 32
-// bytes of fp32 gradient.  Reducing them as [8*gl, 8*gl+8) would touch half of
-// each 32-byte sector twice; instead the G lanes cover the row as two
-// contiguous halves, lane gl taking channels [4*gl, 4*gl+4) and
-// [D/2 + 4*gl, D/2 + 4*gl + 4): every reduction fills whole sectors.
-__device__ __forceinline__ void red_add_halves(float* row, int gl, int half_d, const float (&v)[8]) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + 4 * gl), "f"(v[0]),
-               "f"(v[1]), "f"(v[2]), "f"(v[3])
-               : "memory");
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + half_d + 4 * gl),
-               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-               : "memory");
-}
-__device__ __forceinline__ void red_add_halves(float*, int, int, const float (&)[4]) {}
-__device__ __forceinline__ void red_add_halves(__nv_bfloat16*, int, int, const float (&)[4]) {}
-__device__ __forceinline__ void red_add_halves(__nv_bfloat16*, int, int, const float (&)[8]) {}
+// How the lanes of a group cover a row in the backward: the width of the GRADIENT element
+// decides.  Under bf16 value storage with fp32 gradients a lane takes 4 channels - an 8-byte
+// value load and ONE 16-byte reduction - so a row leaves the SM as one 128-byte request, like
+// the fp32 kernel.  (Measured on B200: reductions cost ~3.9 ps per request + 0.114 ps per byte;
+// covering the row with 4 lanes x two 64-byte halves ran config 2 in 0.786 ms against 0.642 ms
+// for fp32 values.)
+template <typename VT, typename GT>
+struct BwdVec : Vec16<VT> {};
+template <>
+struct BwdVec<__nv_bfloat16, float> {
+  static constexpr int VEC = 4;
+  __device__ __forceinline__ static void load(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+  }
+};
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
@@ -191,7 +184,8 @@ __global__ void __launch_bounds__(kRowsThreads, IO::kFused ? 2 : 0)
 msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, IO io, const float* __restrict__ grad_out,
                      GT* __restrict__ grad_value, Dims d, int nsplit) {
-  constexpr int VEC = Vec16<VT>::VEC;
+  using VL = BwdVec<VT, GT>;
+  constexpr int VEC = VL::VEC;
   constexpr int G = D / VEC;
   static_assert(D % VEC == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0, "bad D");
 
@@ -225,10 +219,9 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   if (!live) q_idx = d.Q - 1;
   const int64_t unit = (b * d.Q + q_idx) * d.M + m;
 
-  constexpr bool kHalves = std::is_same<GT, float>::value && VEC == 8;
   const int64_t boff = b * d.S * MD + m * D + gl * VEC;
   const VT* vbase = value + boff;
-  GT* gvbase = grad_value + boff - (kHalves ? gl * VEC : 0);  // kHalves: row start, lanes add their own slots
+  GT* gvbase = grad_value + boff;
   const int LP = d.L * d.P;
   io.bind(unit, LP, d.M, b * d.Q + q_idx);
   io.src.template prepass<G>(LP, gl, false);   // fused: row max and 1/sum saved by the forward
@@ -241,18 +234,6 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
       const float4 t = __ldcs(reinterpret_cast<const float4*>(gp + c));
       g[c] = t.x; g[c + 1] = t.y; g[c + 2] = t.z; g[c + 3] = t.w;
     }
-  }
-
-  // grad_out channels this lane scatters (== g unless the row is covered in halves)
-  float gs[VEC];
-#pragma unroll
-  for (int c = 0; c < VEC; ++c) gs[c] = g[c];
-  if (kHalves) {
-    const float* gp = grad_out + unit * D;
-    const float4 lo = __ldcs(reinterpret_cast<const float4*>(gp + 4 * gl));
-    const float4 hi = __ldcs(reinterpret_cast<const float4*>(gp + D / 2 + 4 * gl));
-    gs[0] = lo.x; gs[1] = lo.y; gs[2] = lo.z; gs[3] = lo.w;
-    gs[VEC - 4] = hi.x; gs[VEC - 3] = hi.y; gs[VEC - 2] = hi.z; gs[VEC - 1] = hi.w;
   }
 
   const int per = ((LP + nsplit - 1) / nsplit + G - 1) / G * G;
@@ -314,10 +295,10 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
         float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
 #pragma unroll
         for (int c = 0; c < VEC; ++c) v1[c] = v2[c] = v3[c] = v4[c] = 0.f;
-        if (meta & 1) Vec16<VT>::load(p, v1);
-        if (meta & 2) Vec16<VT>::load(p + MD, v2);
-        if (meta & 4) Vec16<VT>::load(p + rs, v3);
-        if (meta & 8) Vec16<VT>::load(p + rs + MD, v4);
+        if (meta & 1) VL::load(p, v1);
+        if (meta & 2) VL::load(p + MD, v2);
+        if (meta & 4) VL::load(p + rs, v3);
+        if (meta & 8) VL::load(p + rs + MD, v4);
         const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
         float tg[VEC];
         float sw = 0.f, sx = 0.f, sy = 0.f;
@@ -335,9 +316,8 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
         float t[VEC];
 #define MSDA_SCATTER(BIT, WK, PTR)                                   \
   if (meta & BIT) {                                                  \
-    _Pragma("unroll") for (int c = 0; c < VEC; ++c) t[c] = (WK) * a * gs[c]; \
-    if (kHalves) red_add_halves(PTR, gl, D / 2, t);                  \
-    else red_add_row(PTR, t);                                        \
+    _Pragma("unroll") for (int c = 0; c < VEC; ++c) t[c] = (WK) * a * g[c]; \
+    red_add_row(PTR, t);                                             \
   }
         MSDA_SCATTER(1, w1, gp)
         MSDA_SCATTER(2, w2, gp + MD)
@@ -459,7 +439,7 @@ template <int D, typename VT, typename GT, class IO>
 static cudaError_t launch_bwd_rows(const void* value, const int64_t* shapes, const int64_t* lsi,
                                    const IO& io, const float* go, void* gv, const Dims& d,
                                    int nsplit, cudaStream_t st) {
-  constexpr int G = D / Vec16<VT>::VEC;
+  constexpr int G = D / BwdVec<VT, GT>::VEC;
   constexpr int GPB = kRowsThreads / G;
   if (nsplit > GPB) nsplit = GPB;   // (a power of two, so it divides GPB)
   const int qpb = GPB / nsplit;
@@ -506,7 +486,7 @@ cudaError_t launch_backward(const void* value, const int64_t* shapes, const int6
           value, shapes, lsi, io, gof, grad_value, d, choose_bwd_split(d, DD / 4, sm_count), st); \
     } else if (grad_value_dtype == MSDA_F32) {                                                    \
       return launch_bwd_rows<DD, __nv_bfloat16, float, PlainIO>(                                  \
-          value, shapes, lsi, io, gof, grad_value, d, choose_bwd_split(d, DD / 8, sm_count), st); \
+          value, shapes, lsi, io, gof, grad_value, d, choose_bwd_split(d, DD / 4, sm_count), st); \
     } else {                                                                                      \
       return launch_bwd_rows<DD, __nv_bfloat16, __nv_bfloat16, PlainIO>(                          \
           value, shapes, lsi, io, gof, grad_value, d, choose_bwd_split(d, DD / 8, sm_count), st); \
@@ -560,7 +540,7 @@ cudaError_t launch_backward_fused(const void* value, const int64_t* shapes, cons
                                                       d, choose_bwd_split(d, 8, sm_count), st);
   if (value_dtype == MSDA_BF16)
     return launch_bwd_rows<32, __nv_bfloat16, float, FusedIO>(
-        value, shapes, lsi, io, grad_out, grad_value, d, choose_bwd_split(d, 4, sm_count), st);
+        value, shapes, lsi, io, grad_out, grad_value, d, choose_bwd_split(d, 8, sm_count), st);
   return cudaErrorNotSupported;
 }
 
