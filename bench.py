@@ -666,16 +666,20 @@ def main():
         # Secondary, on-chip rooflines (SURVEY.md section 8d asks for the L1 / L2 limiter next to HBM):
         # the op gathers / reduces 4*L*P value rows per output row, all of them L2-resident, so what
         # bounds the kernels is the rate at which an SM can gather 128-byte rows through L1 (forward)
-        # and reduce them into L2 (backward).  Peaks: tools/microbench_red.cu on this pool's B200
-        # (profiles/r01_microbench_scatter_rows.txt): ld.v4.f32 134 G rows/s, red.add.v4.f32 54 G rows/s
-        # (red.add.v4.bf16x2 89 G rows/s and half-size ld rows were not used as peaks: fp32 figures).
+        # and push reductions into L2 (backward).  Peaks: micro-benchmarks on this pool's B200 --
+        # tools/microbench_gather.cu (profiles/r01_microbench_gather_rows.txt): ld.v4.f32 of random
+        # L2-resident rows 157.6 G rows/s (1.84 clocks per row and SM; 259.6 when the rows sit in L1);
+        # tools/microbench_red.cu (profiles/r01_microbench_scatter_rows.txt): red.add.v4.f32 54.0 G rows/s
+        # = the SM -> L2 write path (st.v4 peaks at 8.6 TB/s, ~30 bytes per clock and SM).
         corner_rows = 4.0 * dims['B'] * dims['Q'] * dims['M'] * dims['L'] * dims['P']
 
-        def onchip(ms, peak_rows, what):
+        def onchip(ms, peak_rows, what, source, **extra):
             rate = corner_rows / (ms * 1e-3) / 1e9
-            return {'bound': what, 'achieved': rate, 'peak': peak_rows, 'unit': 'G rows/s (128-byte value rows)',
-                    'frac': rate / peak_rows, 'rows_per_launch': corner_rows,
-                    'peak_source': 'micro-benchmark, profiles/r01_microbench_scatter_rows.txt'}
+            out = {'bound': what, 'achieved': rate, 'peak': peak_rows, 'unit': 'G rows/s (128-byte value rows)',
+                   'frac': rate / peak_rows, 'rows_per_launch': corner_rows,
+                   'peak_source': 'micro-benchmark, ' + source}
+            out.update(extra)
+            return out
 
         kname = _capi.kernel_name(dims['D'], 0, 0 if vdt == torch.float32 else 2)
         line = {
@@ -692,8 +696,10 @@ def main():
             'roofline': roof(ab['bwd'], bwd_ms, 'msda_bwd_rows_kernel'),
             'roofline_fwd': roof(ab['fwd'], fwd_ms, 'msda_fwd_rows_kernel'),
             'roofline_step': roof(ab['fwd'] + ab['bwd'], fwd_ms + zero_ms + bwd_ms, 'step'),
-            'roofline_onchip': {'bwd': onchip(bwd_ms, 53.97, 'sm_to_l2_reduction'),
-                                'fwd': onchip(fwd_ms, 133.93, 'l1_gather')},
+            'roofline_onchip': None if vdt != torch.float32 else {   # the peaks are fp32-row figures
+                'bwd': onchip(bwd_ms, 53.97, 'sm_to_l2_reduction', 'profiles/r01_microbench_scatter_rows.txt'),
+                'fwd': onchip(fwd_ms, 157.63, 'l1_gather', 'profiles/r01_microbench_gather_rows.txt',
+                              peak_if_l1_resident=259.55)},
             'kernel_ms': {'fwd': fwd_ms, 'grad_value_zero_fill': zero_ms, 'bwd': bwd_ms},
             'clocks': clock_info, 'gpu_launches': int(launches), 'e2e': e2e,
             'e2e_autograd': e2e_autograd,
