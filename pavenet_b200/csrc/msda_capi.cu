@@ -40,6 +40,9 @@ const Tuning& tuning() {
     x.linear_bk = env_int("PAVENET_MSDA_LINEAR_BK", 16) == 32 ? 32 : 16;
     x.linear_bm = env_int("PAVENET_MSDA_LINEAR_BM", 0);
     if (x.linear_bm != 128 && x.linear_bm != 256) x.linear_bm = 0;
+    x.copy_streams = env_int("PAVENET_MSDA_COPY_STREAMS", 1);
+    if (x.copy_streams < 1) x.copy_streams = 1;
+    if (x.copy_streams > 4) x.copy_streams = 4;
     return x;
   }();
   return t;
@@ -461,14 +464,20 @@ int msda_layernorm_backward(const float* d_x, const float* d_grad_y, const float
 // host-buffer entry points
 //
 // The staged call is pipelined: work is cut into (batch entry, query chunk)
-// pieces; piece k+1 is copied host->device on one stream while piece k runs
-// forward + backward on a second and piece k-1's results return on a third.
-// PCIe is full duplex, so with pinned host memory the call costs about
-// max(bytes up, bytes down) / link bandwidth instead of their sum plus the
-// kernels.
+// pieces; piece k+1 is copied host->device on an upload stream while piece k
+// runs forward + backward on the compute stream and piece k-1's results return
+// on a download stream.  PCIe is full duplex, so with pinned host memory the
+// call costs about max(bytes up, bytes down) / link bandwidth instead of their
+// sum plus the kernels.  One stream per direction by default: alternating the
+// pieces between two or more streams per direction (PAVENET_MSDA_COPY_STREAMS)
+// was measured on B200 and is slower (7.8 vs 6.4 ms on config 2) -- concurrent
+// copies in the same direction take turns on the link instead of hiding each
+// other's start-up cost.
 // ---------------------------------------------------------------------------
+constexpr int kMaxCopyStreams = 4;
 struct msda_workspace {
-  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+  cudaStream_t s_in[kMaxCopyStreams] = {}, s_cmp = nullptr, s_out[kMaxCopyStreams] = {};
+  int n_copy = 1;
   void* buf = nullptr;   // one grow-only device arena
   size_t cap = 0;
   std::vector<cudaEvent_t> events;  // grow-only pool, reused across calls
@@ -479,7 +488,12 @@ struct msda_workspace {
 int msda_workspace_create(msda_workspace** out_ws) {
   if (!out_ws) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_workspace_create: NULL out pointer");
   msda_workspace* ws = new msda_workspace();
-  cudaStream_t* st[3] = {&ws->s_in, &ws->s_cmp, &ws->s_out};
+  ws->n_copy = msda::tuning().copy_streams;
+  std::vector<cudaStream_t*> st = {&ws->s_cmp};
+  for (int i = 0; i < ws->n_copy; ++i) {
+    st.push_back(&ws->s_in[i]);
+    st.push_back(&ws->s_out[i]);
+  }
   for (auto* p : st) {
     const cudaError_t e = cudaStreamCreateWithFlags(p, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -495,9 +509,11 @@ void msda_workspace_destroy(msda_workspace* ws) {
   if (!ws) return;
   for (cudaEvent_t e : ws->events) cudaEventDestroy(e);
   if (ws->buf) cudaFree(ws->buf);
-  if (ws->s_in) cudaStreamDestroy(ws->s_in);
+  for (int i = 0; i < kMaxCopyStreams; ++i) {
+    if (ws->s_in[i]) cudaStreamDestroy(ws->s_in[i]);
+    if (ws->s_out[i]) cudaStreamDestroy(ws->s_out[i]);
+  }
   if (ws->s_cmp) cudaStreamDestroy(ws->s_cmp);
-  if (ws->s_out) cudaStreamDestroy(ws->s_out);
   delete ws;
 }
 
@@ -608,14 +624,15 @@ int msda_forward_backward_host(msda_workspace* ws, const void* h_value,
   Arena ar{static_cast<char*>(ws->buf)};
   int64_t* d_shp = static_cast<int64_t*>(ar.take(b_shp));
   int64_t* d_lsi = static_cast<int64_t*>(ar.take(b_lsi));
-  MSDA_CU(cudaMemcpyAsync(d_shp, h_spatial_shapes, b_shp, cudaMemcpyHostToDevice, ws->s_in));
-  MSDA_CU(cudaMemcpyAsync(d_lsi, h_level_start_index, b_lsi, cudaMemcpyHostToDevice, ws->s_in));
+  MSDA_CU(cudaMemcpyAsync(d_shp, h_spatial_shapes, b_shp, cudaMemcpyHostToDevice, ws->s_in[0]));
+  MSDA_CU(cudaMemcpyAsync(d_lsi, h_level_start_index, b_lsi, cudaMemcpyHostToDevice, ws->s_in[0]));
 
   const size_t up_q = (smp_q * 3 + (do_bwd ? out_q : 0)) * es;
   const int chunk = pick_chunk(num_query, up_q, ws->piece_bytes);
   auto hoff = [](const void* p, size_t bytes) { return static_cast<const char*>(p) + bytes; };
   auto hoffw = [](void* p, size_t bytes) { return static_cast<char*>(p) + bytes; };
 
+  int piece = 0;  // global piece counter: piece k uploads on s_in[k % n], downloads on s_out[k % n]
   for (int b = 0; b < batch; ++b) {
     char* d_val = static_cast<char*>(ar.take(b_val));
     char* d_loc = static_cast<char*>(ar.take(b_loc));
@@ -629,22 +646,29 @@ int msda_forward_backward_host(msda_workspace* ws, const void* h_value,
       d_gaw = static_cast<char*>(ar.take(b_aw));
       MSDA_CU(cudaMemsetAsync(d_gval, 0, b_gval, ws->s_cmp));
     }
-    MSDA_CU(cudaMemcpyAsync(d_val, hoff(h_value, b * b_val), b_val, cudaMemcpyHostToDevice, ws->s_in));
+    // the entry's value (and, for the first entry, the level tables queued on s_in[0] above) must be
+    // resident before any of its pieces runs
+    MSDA_CU(cudaMemcpyAsync(d_val, hoff(h_value, b * b_val), b_val, cudaMemcpyHostToDevice, ws->s_in[0]));
+    cudaEvent_t ev_val;
+    MSDA_RC(ws_event(ws, &ev_val));
+    MSDA_CU(cudaEventRecord(ev_val, ws->s_in[0]));
+    MSDA_CU(cudaStreamWaitEvent(ws->s_cmp, ev_val, 0));
     cudaEvent_t ev_done = nullptr;
-    for (int q0 = 0; q0 < num_query; q0 += chunk) {
+    for (int q0 = 0; q0 < num_query; q0 += chunk, ++piece) {
+      cudaStream_t s_in = ws->s_in[piece % ws->n_copy], s_out = ws->s_out[piece % ws->n_copy];
       const int nq = (num_query - q0 < chunk) ? num_query - q0 : chunk;
       const size_t o_loc = smp_q * 2 * es * q0, o_aw = smp_q * es * q0, o_out = out_q * es * q0;
       const size_t n_loc = smp_q * 2 * es * nq, n_aw = smp_q * es * nq, n_out = out_q * es * nq;
       MSDA_CU(cudaMemcpyAsync(d_loc + o_loc, hoff(h_sampling_loc, b * b_loc + o_loc), n_loc,
-                              cudaMemcpyHostToDevice, ws->s_in));
+                              cudaMemcpyHostToDevice, s_in));
       MSDA_CU(cudaMemcpyAsync(d_aw + o_aw, hoff(h_attn_weight, b * b_aw + o_aw), n_aw,
-                              cudaMemcpyHostToDevice, ws->s_in));
+                              cudaMemcpyHostToDevice, s_in));
       if (do_bwd)
         MSDA_CU(cudaMemcpyAsync(d_go + o_out, hoff(h_grad_output, b * b_out + o_out), n_out,
-                                cudaMemcpyHostToDevice, ws->s_in));
+                                cudaMemcpyHostToDevice, s_in));
       cudaEvent_t ev_in;
       MSDA_RC(ws_event(ws, &ev_in));
-      MSDA_CU(cudaEventRecord(ev_in, ws->s_in));
+      MSDA_CU(cudaEventRecord(ev_in, s_in));
       MSDA_CU(cudaStreamWaitEvent(ws->s_cmp, ev_in, 0));
       if (h_output)
         MSDA_RC(msda_forward(d_val, d_shp, d_lsi, d_loc + o_loc, d_aw + o_aw, d_out + o_out, 1,
@@ -656,24 +680,28 @@ int msda_forward_backward_host(msda_workspace* ws, const void* h_value,
                               num_levels, nq, num_point, dtype, value_dtype, dtype, ws->s_cmp));
       MSDA_RC(ws_event(ws, &ev_done));
       MSDA_CU(cudaEventRecord(ev_done, ws->s_cmp));
-      MSDA_CU(cudaStreamWaitEvent(ws->s_out, ev_done, 0));
+      MSDA_CU(cudaStreamWaitEvent(s_out, ev_done, 0));
       if (h_output)
         MSDA_CU(cudaMemcpyAsync(hoffw(h_output, b * b_out + o_out), d_out + o_out, n_out,
-                                cudaMemcpyDeviceToHost, ws->s_out));
+                                cudaMemcpyDeviceToHost, s_out));
       if (do_bwd) {
         MSDA_CU(cudaMemcpyAsync(hoffw(h_grad_sampling_loc, b * b_loc + o_loc), d_gloc + o_loc, n_loc,
-                                cudaMemcpyDeviceToHost, ws->s_out));
+                                cudaMemcpyDeviceToHost, s_out));
         MSDA_CU(cudaMemcpyAsync(hoffw(h_grad_attn_weight, b * b_aw + o_aw), d_gaw + o_aw, n_aw,
-                                cudaMemcpyDeviceToHost, ws->s_out));
+                                cudaMemcpyDeviceToHost, s_out));
       }
     }
-    if (do_bwd)  // all pieces of this batch entry have been scattered (s_out waited on the last one)
+    if (do_bwd) {
+      // every piece of this batch entry has been scattered once the last one's backward is done
+      cudaStream_t s_out = ws->s_out[piece % ws->n_copy];
+      MSDA_CU(cudaStreamWaitEvent(s_out, ev_done, 0));
       MSDA_CU(cudaMemcpyAsync(hoffw(h_grad_value, b * b_gval), d_gval, b_gval, cudaMemcpyDeviceToHost,
-                              ws->s_out));
+                              s_out));
+    }
   }
-  MSDA_CU(cudaStreamSynchronize(ws->s_out));
+  for (int i = 0; i < ws->n_copy; ++i) MSDA_CU(cudaStreamSynchronize(ws->s_out[i]));
   MSDA_CU(cudaStreamSynchronize(ws->s_cmp));
-  MSDA_CU(cudaStreamSynchronize(ws->s_in));
+  for (int i = 0; i < ws->n_copy; ++i) MSDA_CU(cudaStreamSynchronize(ws->s_in[i]));
   return MSDA_OK;
 }
 

@@ -17,6 +17,7 @@ struct Tuning {
   int bwd_split = 0;  // 0 = heuristic
   int linear_bk = 16; // linear256 K-chunk: 16 (two CTAs per SM) or 32 (one)
   int linear_bm = 0;  // rows per CTA: 128 (default, also 0) or 256
+  int copy_streams = 1;  // host-buffer entry points: upload / download streams per direction (1..4)
 };
 const Tuning& tuning();
 
