@@ -444,6 +444,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--sets', type=int, default=4, help='distinct input sets rotated per step')
+    ap.add_argument('--frames', type=int, default=0, help='override the batch entries (frames) per step of an op workload: the batch sweep of BASELINE config 5')
     ap.add_argument('--fused', action='store_true', help='time the fused-prologue kernels (offsets/logits in, softmax + location transform in-kernel) on the same problem')
     ap.add_argument('--piece-mb', type=float, default=0, help='e2e: upload MiB per pipeline piece (0 = library default)')
     args = ap.parse_args()
@@ -482,7 +483,8 @@ def main():
     cfg = WORKLOADS[wl]
     vdt = torch.float32 if args.value_dtype == 'f32' else torch.bfloat16
     # every rank owns its own clips: weak scaling, `sets` distinct clips per rank
-    probs = [make_problem(wl, seed=1000 * rank + i, device=device, value_dtype=vdt)
+    probs = [make_problem(wl, seed=1000 * rank + i, device=device, value_dtype=vdt,
+                          frames=args.frames or None)
              for i in range(args.sets)]
     dims = probs[0]['dims']
     q_per_step = dims['B'] * dims['Q']

@@ -32,9 +32,9 @@ __device__ __forceinline__ void red_add_row(float* p, const float (&v)[4]) {
 // How the lanes of a group cover a row in the backward: the width of the GRADIENT element
 // decides.  Under bf16 value storage with fp32 gradients a lane takes 4 channels - an 8-byte
 // value load and ONE 16-byte reduction - so a row leaves the SM as one 128-byte request, like
-// the fp32 kernel.  (Measured on B200: reductions cost ~3.9 ps per request + 0.114 ps per byte;
-// covering the row with 4 lanes x two 64-byte halves ran config 2 in 0.786 ms against 0.642 ms
-// for fp32 values.)
+// the fp32 kernel.  (Measured on B200: 64-byte reduction requests reach only ~80 % of the byte
+// rate of 128-byte ones; covering the row with 4 lanes x two 64-byte halves ran config 2 in
+// 0.786 ms against 0.642 ms for fp32 values.)
 template <typename VT, typename GT>
 struct BwdVec : Vec16<VT> {};
 template <>

@@ -13,12 +13,12 @@ __device__ __forceinline__ uint32_t mix(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x;
 }
 
-enum Mode { LD4 = 0, ST4, RED1, RED2, RED4, REDBF };
+enum Mode { LD4 = 0, ST4, RED1, RED2, RED4, REDBF, RED4W };  // RED4W: 256-byte rows (two adjacent fp32 rows), 16 lanes
 
 template <int MODE>
 __global__ void k(float* buf, uint32_t n_rows, uint32_t hot_rows, int iters, float* sink) {
   // lanes per 128-byte fp32 row: 32 (scalar), 16 (v2), 8 (v4); bf16 row is 64 bytes: 4 lanes
-  constexpr int G = MODE == RED1 ? 32 : MODE == RED2 ? 16 : MODE == REDBF ? 4 : 8;
+  constexpr int G = MODE == RED1 ? 32 : (MODE == RED2 || MODE == RED4W) ? 16 : MODE == REDBF ? 4 : 8;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t grp = tid / G, gl = tid % G;
   float acc = 0.f;
@@ -35,6 +35,9 @@ __global__ void k(float* buf, uint32_t n_rows, uint32_t hot_rows, int iters, flo
       asm volatile("red.global.add.f32 [%0], %1;" ::"l"(row + gl), "f"(1.0f) : "memory");
     } else if (MODE == RED2) {
       asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(row + gl * 2), "f"(1.0f), "f"(2.0f) : "memory");
+    } else if (MODE == RED4W) {
+      float* row2 = buf + (size_t)(r & ~1u) * 32;   // an aligned pair of rows = 256 contiguous bytes
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row2 + gl * 4), "f"(1.0f), "f"(2.0f), "f"(3.0f), "f"(4.0f) : "memory");
     } else if (MODE == RED4) {
       asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + gl * 4), "f"(1.0f), "f"(2.0f), "f"(3.0f), "f"(4.0f) : "memory");
     } else {
@@ -48,7 +51,7 @@ __global__ void k(float* buf, uint32_t n_rows, uint32_t hot_rows, int iters, flo
 
 template <int MODE>
 void run(const char* name, float* buf, uint32_t n_rows, uint32_t hot, float* sink) {
-  constexpr int G = MODE == RED1 ? 32 : MODE == RED2 ? 16 : MODE == REDBF ? 4 : 8;
+  constexpr int G = MODE == RED1 ? 32 : (MODE == RED2 || MODE == RED4W) ? 16 : MODE == REDBF ? 4 : 8;
   const int iters = 64;
   const long rows_total = 1L << 25;                 // 32 Mi rows per launch
   const long groups = rows_total / iters;
@@ -65,7 +68,7 @@ void run(const char* name, float* buf, uint32_t n_rows, uint32_t hot, float* sin
     cudaEventRecord(b); cudaEventSynchronize(b);
     float ms; cudaEventElapsedTime(&ms, a, b); if (ms < best) best = ms;
   }
-  const double row_bytes = MODE == REDBF ? 64.0 : 128.0;
+  const double row_bytes = MODE == REDBF ? 64.0 : MODE == RED4W ? 256.0 : 128.0;
   printf("%-22s hot=%-6u  %8.3f ms  %7.2f Grows/s  %8.1f GB/s payload\n", name, hot, best,
          rows_total / best * 1e-6, rows_total * row_bytes / best * 1e-6);
   cudaError_t e = cudaGetLastError();
@@ -84,6 +87,7 @@ int main() {
     run<RED2>("red.add.v2.f32 (x16)", buf, n_rows, hot, sink);
     run<RED4>("red.add.v4.f32 (x8)", buf, n_rows, hot, sink);
     run<REDBF>("red.add.v4.bf16x2 (x4)", buf, n_rows, hot, sink);
+    run<RED4W>("red.add.v4.f32 (x16, 256 B)", buf, n_rows, hot, sink);
   }
   return 0;
 }
