@@ -121,6 +121,12 @@ static int check_dtypes(int dtype, int value_dtype, int grad_value_dtype) {
 
 static bool misaligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
 
+// the forward rows kernels address a batch entry with 31-bit BYTE offsets
+static bool entry_bytes_overflow(const Dims& d, int value_dtype) {
+  return static_cast<int64_t>(d.S) * d.M * d.D * static_cast<int64_t>(dtype_size(value_dtype)) >=
+         (int64_t(1) << 31);
+}
+
 }  // namespace msda
 
 using namespace msda;
@@ -159,8 +165,9 @@ int msda_forward(const void* d_value, const int64_t* d_spatial_shapes,
   rc = current_sm_count(&sms);
   if (rc) return rc;
   // the vector kernels need 16-byte aligned rows; fall back to scalar access otherwise
+  // ... and keep byte offsets inside a batch entry in 31 bits (the generic kernel indexes in int64)
   const int generic = tuning().force_generic || misaligned16(d_value) || misaligned16(d_output) ||
-                      misaligned16(d_sampling_loc);
+                      misaligned16(d_sampling_loc) || entry_bytes_overflow(d, value_dtype);
   const cudaError_t e =
       launch_forward(d_value, d_spatial_shapes, d_level_start_index, d_sampling_loc, d_attn_weight,
                      d_output, d, dtype, value_dtype, sms, generic, static_cast<cudaStream_t>(stream));
@@ -227,6 +234,8 @@ int msda_fused_forward(const void* d_value, const int64_t* d_spatial_shapes,
   if (rc) return rc;
   if (misaligned16(d_value) || misaligned16(d_output) || misaligned16(d_offsets))
     return fail(MSDA_ERR_UNSUPPORTED, "msda_fused_forward needs 16-byte aligned buffers");
+  if (entry_bytes_overflow(d, value_dtype))
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_fused_forward: one batch entry of value must be < 2 GiB");
   FusedSource src;
   rc = fused_source(&src, d_offsets, d_logits, d_ref_points, d_scale, d_softmax_stats,
                     ref_points_per_level, num_point);
