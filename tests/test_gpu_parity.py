@@ -195,15 +195,18 @@ def test_rows_and_generic_kernels_agree(op_golden):
     assert pavenet_b200._capi.kernel_name(30, 0, 0) == 'generic'
 
 
-def test_bf16_value_storage(fn):
-    """bf16 value storage (new capability).  Stated bound: the only error
+@pytest.mark.parametrize('D,Q', [(32, 300), (16, 300), (64, 120), (32, 20)])
+def test_bf16_value_storage(fn, D, Q):
+    """bf16 value storage (new capability), every head size of the rows kernels and a
+    small-Q (split) shape: the backward covers a row with D/4 lanes (fp32 gradient
+    accumulation), the forward with D/8.  Stated bound: the only error
     source in the forward is the 8-bit mantissa of the stored value
     (rel. 2^-9 per element, averaged down by the weighted sum): outputs within
     4e-3 of the fp32-value result, and within 2e-5 of the oracle run on the
     SAME bf16-rounded value.  Gradients: grad_loc / grad_attn_weight within
     1e-3 of the oracle on the rounded value; grad_value (fp32 accumulation,
     rounded once to bf16) within 4e-3."""
-    value, shapes_t, loc, aw, go = _random_problem(9, 2, 300, 8, 32, 15, MID_LEVELS)
+    value, shapes_t, loc, aw, go = _random_problem(9, 2, Q, 8, D, 15, MID_LEVELS)
     lsi = O.level_start_index(shapes_t)
     v16 = value.to(torch.bfloat16)
     out, gv, gl, ga = _fwd_bwd(fn, v16.cuda(), shapes_t.cuda(), lsi.cuda(), loc.cuda(), aw.cuda(), go)
