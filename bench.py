@@ -356,6 +356,7 @@ def run_model_step(args, world, rank, local):
     torch.manual_seed(0)
     vdt = None if args.value_dtype == 'f32' else torch.bfloat16
     model = clip_model.PaveNetR50(value_dtype=vdt).to(device).train()
+    model.fold_frozen_bn = os.environ.get('PAVENET_FOLD_BN', '1') != '0'   # A/B switch, default on
     if args.graphs:
         model.enable_graphs()
     ddp = flat = None

@@ -196,7 +196,7 @@ class PaveNetR50(nn.Module):
         self.refine_sigma = nn.ModuleList(mlp(256, 256, 2, n_hidden=1) for _ in range(2))
         self.flow = RealNVP()
         nn.init.constant_(self.cls_branches[0].bias, -4.6)
-        self._geo_cache, self._graphed = {}, None
+        self._geo_cache, self._graphed, self._fold_cache = {}, None, {}
 
     def train(self, mode=True):
         super().train(mode)
@@ -205,7 +205,62 @@ class PaveNetR50(nn.Module):
                 m.eval()
         self.stem.eval()
         self.layer1.eval()
+        self._fold_cache = {}
         return self
+
+    def load_state_dict(self, *args, **kwargs):
+        self._fold_cache = {}
+        return super().load_state_dict(*args, **kwargs)
+
+    # ---- frozen BatchNorm folded into the convolution in front of it -------------------------
+    #: Every BatchNorm of the backbone is frozen (norm_eval=True, requires_grad=False:
+    #: mmdet/models/backbones/resnet.py:632-653), i.e. a per-channel affine y = s * conv(x) + t with
+    #: constant s, t.  Folding it into the convolution (w' = s * w, bias t) is the same function and
+    #: removes one read + write of every backbone activation in the forward and one in the backward
+    #: (53 `bn_fw_inf` launches, 5.5 ms of a 60 ms step on B200).  False: torchvision's module-by-module path.
+    fold_frozen_bn = True
+
+    def _bn_affine(self, bn):
+        hit = self._fold_cache.get(id(bn))
+        if hit is None:
+            with torch.no_grad():
+                s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+                hit = (s.view(-1, 1, 1, 1).contiguous(), (bn.bias - bn.running_mean * s).contiguous())
+            self._fold_cache[id(bn)] = hit
+        return hit
+
+    def _conv_bn(self, conv, bn, x):
+        s, t = self._bn_affine(bn)
+        if conv.weight.requires_grad:
+            w = conv.weight * s
+        else:                                     # frozen stage: fold once
+            w = self._fold_cache.get(id(conv))
+            if w is None:
+                with torch.no_grad():
+                    w = (conv.weight * s).contiguous(memory_format=torch.channels_last)
+                self._fold_cache[id(conv)] = w
+        return F.conv2d(x, w, t, conv.stride, conv.padding, conv.dilation, conv.groups)
+
+    def _bottleneck(self, blk, x):
+        """torchvision Bottleneck.forward with the BatchNorms folded."""
+        out = F.relu_(self._conv_bn(blk.conv1, blk.bn1, x))
+        out = F.relu_(self._conv_bn(blk.conv2, blk.bn2, out))
+        out = self._conv_bn(blk.conv3, blk.bn3, out)
+        idt = x if blk.downsample is None else self._conv_bn(blk.downsample[0], blk.downsample[1], x)
+        return F.relu_(out.add_(idt))
+
+    def _res_layer(self, layer, x):
+        if not self.fold_frozen_bn:
+            return layer(x)
+        for blk in layer:
+            x = self._bottleneck(blk, x)
+        return x
+
+    def _stem(self, x):
+        if not self.fold_frozen_bn:
+            return self.stem(x)
+        conv, bn, _, pool = self.stem
+        return pool(F.relu_(self._conv_bn(conv, bn, x)))
 
     #: diagnostic hook: set to a callable(name) to get a call at each phase boundary of
     #: forward_train (tools/phase_step.py synchronises and timestamps there)
@@ -219,10 +274,10 @@ class PaveNetR50(nn.Module):
     def extract_feat(self, images):                   # (Bc, T, 3, H, W) -> 4 levels of (Bc*T, 256, h, w)
         x = images.flatten(0, 1).contiguous(memory_format=torch.channels_last)
         with torch.no_grad():
-            x = self.layer1(self.stem(x))
-        c3 = self.layer2(x)
-        c4 = self.layer3(c3)
-        c5 = self.layer4(c4)
+            x = self._res_layer(self.layer1, self._stem(x))
+        c3 = self._res_layer(self.layer2, x)
+        c4 = self._res_layer(self.layer3, c3)
+        c5 = self._res_layer(self.layer4, c4)
         return [l(c) for l, c in zip(self.lateral, (c3, c4, c5))] + [self.extra(c5)]
 
     @staticmethod

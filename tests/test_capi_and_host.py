@@ -251,3 +251,32 @@ def test_value_error_on_bad_reference_points(monkeypatch):
     with pytest.raises(ValueError, match='2K'):
         p(torch.randn(3, 1, 32), None, torch.randn(4, 1, 32),
           reference_points=torch.rand(1, 3, 1, 8), spatial_shapes=shapes, level_start_index=lsi)
+
+
+def test_clip_model_frozen_bn_fold_is_the_same_function():
+    """The PAVE-Net step folds the backbone's frozen BatchNorms into the convolutions in front of
+    them (clip_model.PaveNetR50.fold_frozen_bn); same features and same weight gradients as
+    torchvision's conv -> bn -> relu path, checked in float64 on the CPU (pure PyTorch code)."""
+    from pavenet_b200 import clip_model
+    torch.manual_seed(0)
+    m = clip_model.PaveNetR50(num_query=20).double().train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.5)
+            mod.running_var.uniform_(0.5, 2.0)
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.3)
+    m.train()                                   # clears the fold cache
+    x = torch.randn(1, 3, 3, 64, 96, dtype=torch.float64)
+    names = ['layer4.2.conv3.weight', 'layer3.0.conv2.weight', 'layer2.0.downsample.0.weight']
+    params = dict(m.named_parameters())
+    res = {}
+    for fold in (True, False):
+        m.fold_frozen_bn = fold
+        feats = m.extract_feat(x)
+        loss = sum(t.square().sum() for t in feats)
+        res[fold] = (feats, torch.autograd.grad(loss, [params[n] for n in names]))
+    for a, b in zip(res[True][0], res[False][0]):
+        assert float((a - b).abs().max() / b.abs().max()) < 1e-10
+    for a, b in zip(res[True][1], res[False][1]):
+        assert float((a - b).abs().max() / b.abs().max()) < 1e-6
