@@ -7,8 +7,11 @@ SEL='linear256_matches_fp64 or linear256_masks or bf16_value_storage or layer_no
 run() {  # name tool [env...]
   name=$1; tool=$2; shift 2
   echo "== $name ($tool)"
-  env "$@" timeout 900 compute-sanitizer --tool $tool --error-exitcode 99 --target-processes all \
-    python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$SEL" > $OUT/$name.log 2>&1
+  sel="$SEL"
+  # racecheck slows kernels down by orders of magnitude: leave the 66 669-row cases to memcheck
+  [ $tool = racecheck ] && sel="($SEL) and not 66669"
+  env "$@" timeout 300 compute-sanitizer --tool $tool --error-exitcode 99 --target-processes all \
+    python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$sel" > $OUT/$name.log 2>&1
   echo "exit $?" | tee -a $OUT/$name.log
   grep -E "ERROR SUMMARY|passed|failed|RACECHECK SUMMARY" $OUT/$name.log | tail -3
 }
