@@ -332,7 +332,11 @@ def run_reference_arm(args, world, rank):
         'unit': 'queries/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': wl, 'description': cfg['desc'], 'sample': sample},
+        'config': {'workload': wl, 'description': cfg['desc'],
+                   'dims': dict(prob['dims'], B=cfg['B'], Q=full_q),      # the full workload ...
+                   'queries_per_step': cfg['B'] * full_q,
+                   'sample': sample,                                       # ... and what one CPU step covers
+                   'parallelism': 'host threads of rank 0 only'},
         'cpu_baseline': {'value': qps, 'unit': 'queries/s', 'cores': torch.get_num_threads(),
                          'kind': 'port', 'sample': sample},
         'e2e': {'value': qps, 'unit': 'queries/s', 'h2d_bytes_per_step': 0,

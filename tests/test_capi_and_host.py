@@ -280,3 +280,41 @@ def test_clip_model_frozen_bn_fold_is_the_same_function():
         assert float((a - b).abs().max() / b.abs().max()) < 1e-10
     for a, b in zip(res[True][1], res[False][1]):
         assert float((a - b).abs().max() / b.abs().max()) < 1e-6
+
+
+def test_bench_algorithmic_bytes_match_the_survey_figures():
+    """bench.py's roofline numerator: config 2 forward 238.9 MB, backward
+    409.6 MB, 9.73 KB per query; config 3 (T=5, P=17) 371.3 MB fp32 / 200.7 MB... per fwd+bwd."""
+    import bench
+    S = sum(h * w for h, w in bench.R50_LEVELS)
+    assert S == 22223
+    cfg2 = bench.algorithmic_bytes(dict(B=3, S=S, M=8, D=32, L=4, Q=S, P=4))
+    assert round(cfg2['fwd'] / 1e6, 1) == 238.9 and round(cfg2['bwd'] / 1e6, 1) == 409.6
+    assert round((cfg2['fwd'] + cfg2['bwd']) / (3 * S) / 1e3, 2) == 9.73
+    cfg3 = bench.algorithmic_bytes(dict(B=1, S=5 * S, M=8, D=32, L=20, Q=300, P=17))
+    assert round((cfg3['fwd'] + cfg3['bwd']) / 1e6, 1) == 371.3
+    cfg1 = bench.algorithmic_bytes(dict(B=1, S=S, M=8, D=32, L=4, Q=300, P=17))
+    assert round(cfg1['fwd'] / 1e6, 1) == 25.0 and round(cfg1['bwd'] / 1e6, 1) == 49.7
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours) runs without a GPU
+    and prints ONE JSON line with the keys of the contract."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference',
+                           '--steps', '1', '--warmup', '3', '--workload', 'petr_cfg1'],
+                          capture_output=True, text=True, timeout=600, cwd=root)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, proc.stdout
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'queries/s' and d['higher_is_better'] is True
+    assert d['metric'] == 'deform-attn fwd+bwd queries/s' and d['value'] > 0
+    assert d['config']['workload'] == 'petr_cfg1' and d['config']['dims']['Q'] == 300
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e'] == {'value': d['value'], 'unit': 'queries/s', 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': 0}
+    assert d['gpu_launches'] == 0
