@@ -152,3 +152,31 @@ def test_c_oracle_agrees_with_port_on_random_shapes():
         assert rel_err(gv, vv.grad) < 1e-13
         assert rel_err(gl, ll.grad) < 1e-12
         assert rel_err(ga, aa.grad) < 1e-13
+
+
+def test_c_oracle_structural_properties():
+    """Properties the full-size GPU tests lean on, held by the oracle itself: the op is linear in
+    `value` and in the attention weights, blind to the order of the points inside a level, and a
+    sample whose weight is zero contributes nothing to the output or to grad_value."""
+    g = torch.Generator().manual_seed(5)
+    shapes = torch.tensor([(9, 7), (4, 5), (2, 3)])
+    S, L, M, D, Q, P = int(shapes.prod(1).sum()), 3, 2, 6, 11, 4
+    dt = torch.float64
+    v1 = torch.randn(1, S, M, D, generator=g, dtype=dt)
+    v2 = torch.randn(1, S, M, D, generator=g, dtype=dt)
+    loc = torch.rand(1, Q, M, L, P, 2, generator=g, dtype=dt) * 1.3 - 0.15
+    aw = torch.rand(1, Q, M, L, P, generator=g, dtype=dt)
+    go = torch.randn(1, Q, M * D, generator=g, dtype=dt)
+    f = lambda v, a=aw, l=loc: O.c_forward(v, shapes, None, l, a)   # noqa: E731
+    assert rel_err(f(2.5 * v1 - v2), 2.5 * f(v1) - f(v2)) < 1e-13
+    assert rel_err(f(v1, 3.0 * aw), 3.0 * f(v1)) < 1e-13
+    perm = torch.tensor([2, 0, 3, 1])
+    assert rel_err(f(v1, aw[..., perm], loc[..., perm, :]), f(v1)) < 1e-13
+    aw0 = aw.clone()
+    aw0[..., 1, :] = 0                                  # silence level 1
+    v_mod = v1.clone()
+    start1 = int(shapes[0].prod())
+    v_mod[:, start1:start1 + int(shapes[1].prod())] = 123.0     # ... then its values cannot matter
+    assert rel_err(f(v_mod, aw0), f(v1, aw0)) < 1e-13
+    gv, _, _ = O.c_backward(v1, shapes, None, loc, aw0, go)
+    assert float(gv[:, start1:start1 + int(shapes[1].prod())].abs().max()) == 0.0
