@@ -23,6 +23,8 @@
 //   gate (the backward of ReLU + dropout), dropout, the padding mask and a residual,
 //   then stores fp32 or bf16 rows — for value_proj the (B, S, M, D) layout the
 //   sampling kernels read, so no further pass touches the projected value.
+#include <atomic>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -731,15 +733,15 @@ EncodeTiledFn encode_fn() {
 // cudaFuncSetAttribute once per kernel and device (later launches may be inside a stream capture,
 // where the fewer host-side driver calls the better)
 struct SmemOptIn {
-  unsigned long long done = 0;   // bit d: set on device d
+  std::atomic<unsigned long long> done{0};   // bit d: set on device d (forward and autograd threads both launch)
   template <typename K>
   cudaError_t ensure(K kernel, uint32_t smem) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev < 64 && ((done >> dev) & 1ull)) return cudaSuccess;
+    if (dev < 64 && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return cudaSuccess;
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess && dev < 64) done |= 1ull << dev;
+    if (e == cudaSuccess && dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
     return e;
   }
 };
