@@ -318,3 +318,29 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d['e2e'] == {'value': d['value'], 'unit': 'queries/s', 'h2d_bytes_per_step': 0,
                         'd2h_bytes_per_step': 0}
     assert d['gpu_launches'] == 0
+
+
+def test_integration_md_ctypes_stub_matches_the_abi():
+    """INTEGRATION.md section 2b shows the binding a maintainer would paste into mmcv.  Execute that
+    very text against the built library (no kernel is launched) and check that it declares the two
+    entry points exactly as pavenet_b200._capi does."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, 'INTEGRATION.md')).read()
+    sec = text[text.index('### 2b.'):text.index('### 2c.')]
+    blocks = re.findall(r'```python\n(.*?)```', sec, flags=re.S)
+    stub = [b for b in blocks if 'ctypes.CDLL' in b]
+    assert len(stub) == 1
+    code = stub[0].replace("ctypes.CDLL('libpavenet_msda.so')",
+                           'ctypes.CDLL(%r)' % pavenet_b200._build.LIB_PATH)
+    ns = {}
+    exec(compile(code, 'INTEGRATION.md:2b', 'exec'), ns)
+    lib = pavenet_b200._capi.load()
+    assert len(ns['_lib'].msda_forward.argtypes) == len(lib.msda_forward.argtypes) == 16
+    assert len(ns['_lib'].msda_backward.argtypes) == len(lib.msda_backward.argtypes) == 20
+    for mine, theirs in ((ns['_lib'].msda_forward.argtypes, lib.msda_forward.argtypes),
+                         (ns['_lib'].msda_backward.argtypes, lib.msda_backward.argtypes)):
+        assert [ctypes.sizeof(a) for a in mine] == [ctypes.sizeof(a) for a in theirs]
+    assert callable(ns['ext_module'].ms_deform_attn_forward)
+    assert callable(ns['ext_module'].ms_deform_attn_backward)
+    assert ns['_DT'] == {torch.float32: pavenet_b200._capi.MSDA_F32, torch.float64: pavenet_b200._capi.MSDA_F64,
+                         torch.bfloat16: pavenet_b200._capi.MSDA_BF16}
