@@ -452,6 +452,12 @@ def main():
     ap.add_argument('--frames', type=int, default=0, help='override the batch entries (frames) per step of an op workload: the batch sweep of BASELINE config 5')
     ap.add_argument('--fused', action='store_true', help='time the fused-prologue kernels (offsets/logits in, softmax + location transform in-kernel) on the same problem')
     ap.add_argument('--piece-mb', type=float, default=0, help='e2e: upload MiB per pipeline piece (0 = library default)')
+    ap.add_argument('--fold-clear', default='auto', choices=['auto', '0', '1'],
+                    help='zero-fill grad_value inside the forward call (msda_forward_clear) instead of a '
+                         'separate memset between forward and backward; auto = for the small-Q (pose) workloads, '
+                         'whose persistent forward kernel folds the fill in')
+    ap.add_argument('--option', action='append', default=[], metavar='NAME=INT',
+                    help='library kernel-selection knob (msda_set_option), e.g. flat=0, bwd_variant=2')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -483,9 +489,13 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=device)
     _capi.load()
+    for opt in args.option:
+        name, val = opt.split('=')
+        _capi.set_option(name, int(val))
 
     wl = args.workload
     cfg = WORKLOADS[wl]
+    fold_clear = (cfg['kind'] == 'pose') if args.fold_clear == 'auto' else args.fold_clear == '1'
     vdt = torch.float32 if args.value_dtype == 'f32' else torch.bfloat16
     # every rank owns its own clips: weak scaling, `sets` distinct clips per rank
     probs = [make_problem(wl, seed=1000 * rank + i, device=device, value_dtype=vdt,
@@ -525,20 +535,26 @@ def main():
                 p['value'].data_ptr(), p['shapes'].data_ptr(), p['lsi'].data_ptr(),
                 p['off'].data_ptr(), p['logit'].data_ptr(), p['ref'].data_ptr(), None,
                 p['out'].data_ptr(), p['stats'].data_ptr(), dims['B'], dims['S'], dims['M'],
-                dims['D'], dims['L'], dims['Q'], dims['P'], 1, vcode, stream), 'msda_fused_forward')
+                dims['D'], dims['L'], dims['Q'], dims['P'], 1, vcode,
+                b['grad_value'].data_ptr() if fold_clear else None,
+                b['grad_value'].numel() * b['grad_value'].element_size() if fold_clear else 0,
+                stream), 'msda_fused_forward')
             out = p['out']
         else:
-            out = ms_deform_attn_forward(p['value'], p['shapes'], p['lsi'], p['loc'], p['aw'], 64)
+            out = ms_deform_attn_forward(p['value'], p['shapes'], p['lsi'], p['loc'], p['aw'], 64,
+                                         clear=b['grad_value'] if fold_clear else None)
         if ev:
             ev[1].record()
-        b['grad_value'].zero_()
+        if not fold_clear:
+            b['grad_value'].zero_()
         if ev:
             ev[2].record()
         if args.fused:
             _capi.check(lib.msda_fused_backward(
                 p['value'].data_ptr(), p['shapes'].data_ptr(), p['lsi'].data_ptr(),
                 p['off'].data_ptr(), p['logit'].data_ptr(), p['ref'].data_ptr(), None,
-                p['stats'].data_ptr(), p['grad_out'].data_ptr(), b['grad_value'].data_ptr(),
+                p['stats'].data_ptr(), p['out'].data_ptr(), p['grad_out'].data_ptr(),
+                b['grad_value'].data_ptr(),
                 b['grad_loc'].data_ptr(), b['grad_aw'].data_ptr(), None, dims['B'], dims['S'],
                 dims['M'], dims['D'], dims['L'], dims['Q'], dims['P'], 1, vcode, stream),
                 'msda_fused_backward')
@@ -707,7 +723,10 @@ def main():
                 'bwd': onchip(bwd_ms, 53.97, 'sm_to_l2_reduction', 'profiles/r01_microbench_scatter_rows.txt'),
                 'fwd': onchip(fwd_ms, 157.63, 'l1_gather', 'profiles/r01_microbench_gather_rows.txt',
                               peak_if_l1_resident=259.55)},
-            'kernel_ms': {'fwd': fwd_ms, 'grad_value_zero_fill': zero_ms, 'bwd': bwd_ms},
+            'kernel_ms': {'fwd': fwd_ms, 'grad_value_zero_fill': zero_ms, 'bwd': bwd_ms,
+                          'grad_value_zero_fill_folded_into_fwd': bool(fold_clear)},
+            'kernel_families': {k: v for k, v in _capi.family_counts().items() if v},
+            'options': args.option,
             'clocks': clock_info, 'gpu_launches': int(launches), 'e2e': e2e,
             'e2e_autograd': e2e_autograd,
         }

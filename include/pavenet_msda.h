@@ -60,7 +60,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 1
+#define MSDA_ABI_VERSION 2
 
 enum msda_dtype { MSDA_F32 = 0, MSDA_F64 = 1, MSDA_BF16 = 2 };
 
@@ -81,6 +81,22 @@ const char *msda_last_error(void);
 /* Number of CUDA kernels this library has launched since load (all threads). */
 uint64_t msda_launch_count(void);
 
+/* Kernel-selection knobs for tests and benchmarks (not thread safe; set between calls).
+ * Also read once from the environment at load: PAVENET_MSDA_<NAME IN CAPITALS>.
+ *   "force_generic" 0/1      any-D scalar kernels instead of the vector ones
+ *   "fwd_split", "bwd_split" lane groups per row of the rows kernels (0 = heuristic)
+ *   "flat"                   small-Q flat kernels: 0 never, 1 heuristic (default), 2 always
+ *   "fwd_variant", "bwd_variant"  large-Q kernel variants (0 = default)
+ * Returns MSDA_ERR_INVALID_ARGUMENT for an unknown name. */
+int msda_set_option(const char *name, int value);
+
+/* Launches of ONE kernel family since load, so a test can assert that the kernel it means
+ * to check is the one that ran.  Families: 0 generic forward, 1 generic backward, 2 rows
+ * forward, 3 rows backward, 4 / 5 the same with the fused prologue, 6 flat (small-Q)
+ * forward, 7 flat backward, 8 / 9 the same fused, 10 tcgen05 linear, 11 its weight
+ * gradient, 12 column sums, 13 LayerNorm, 14 tile-aggregating backward.  Unknown codes: 0. */
+uint64_t msda_launch_count_family(int family);
+
 /* Name of the kernel family the dispatcher would use for this problem
  * ("rows<D=32,f32>", "generic", ...).  Static storage; never NULL. */
 const char *msda_kernel_name(int channels, int dtype, int value_dtype);
@@ -98,6 +114,22 @@ int msda_forward(const void *d_value, const int64_t *d_spatial_shapes,
                  void *d_output, int batch, int spatial_size, int num_heads,
                  int channels, int num_levels, int num_query, int num_point,
                  int dtype, int value_dtype, void *stream);
+
+/*
+ * msda_forward that also zero-fills `d_clear` (clear_bytes bytes; both zero = plain
+ * msda_forward) on the same stream: the grad_value buffer the coming msda_backward will
+ * accumulate into (the reference zero-fills it in its autograd wrapper,
+ * multi_scale_deform_attn.py:72).  For the small-Q shapes (pose decoder) the fill is folded
+ * into the persistent forward kernel, whose warps leave most of the DRAM write bandwidth
+ * idle; otherwise it is a memset ahead of the kernel.  `d_clear` must not alias an input.
+ */
+int msda_forward_clear(const void *d_value, const int64_t *d_spatial_shapes,
+                       const int64_t *d_level_start_index,
+                       const void *d_sampling_loc, const void *d_attn_weight,
+                       void *d_output, int batch, int spatial_size, int num_heads,
+                       int channels, int num_levels, int num_query, int num_point,
+                       int dtype, int value_dtype, void *d_clear,
+                       size_t clear_bytes, void *stream);
 
 /*
  * Backward.  Replaces ms_deform_attn_backward (ms_deform_attn.cpp:48-60).
@@ -127,10 +159,13 @@ int msda_backward(const void *d_value, const int64_t *d_spatial_shapes,
  * over L*P themselves.  fp32 only; channels must be 32 (MSDA_ERR_UNSUPPORTED
  * otherwise — callers then fall back to msda_forward / msda_backward).
  * d_softmax_stats (B,Q,M,2) is written by the forward (row max, 1/sum) and
- * read by the backward.  The backward accumulates into the zero-initialised
- * d_grad_value and overwrites d_grad_offsets / d_grad_logits (softmax and
- * scale already differentiated through); d_grad_loc, if not NULL, receives
- * d/d(loc) for callers that need reference-point gradients.
+ * read by the backward, which also takes the forward's d_output: the softmax
+ * backward's row term sum_t w_t dL/dw_t equals <grad_output[row], output[row]>,
+ * so no reduction over the samples is needed.  The backward accumulates into the
+ * zero-initialised d_grad_value and overwrites d_grad_offsets / d_grad_logits
+ * (softmax and scale already differentiated through); d_grad_loc, if not NULL,
+ * receives d/d(loc) for callers that need reference-point gradients.
+ * d_clear / clear_bytes of the forward: as in msda_forward_clear (NULL, 0 = none).
  */
 int msda_fused_forward(const void *d_value, const int64_t *d_spatial_shapes,
                        const int64_t *d_level_start_index, const float *d_offsets,
@@ -139,13 +174,15 @@ int msda_fused_forward(const void *d_value, const int64_t *d_spatial_shapes,
                        float *d_softmax_stats, int batch, int spatial_size,
                        int num_heads, int channels, int num_levels,
                        int num_query, int num_point, int ref_points_per_level,
-                       int value_dtype, void *stream);
+                       int value_dtype, void *d_clear, size_t clear_bytes,
+                       void *stream);
 
 int msda_fused_backward(const void *d_value, const int64_t *d_spatial_shapes,
                         const int64_t *d_level_start_index,
                         const float *d_offsets, const float *d_logits,
                         const float *d_ref_points, const float *d_scale,
-                        const float *d_softmax_stats, const float *d_grad_output,
+                        const float *d_softmax_stats, const float *d_output,
+                        const float *d_grad_output,
                         float *d_grad_value, float *d_grad_offsets,
                         float *d_grad_logits, float *d_grad_loc, int batch,
                         int spatial_size, int num_heads, int channels,

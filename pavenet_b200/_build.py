@@ -19,13 +19,13 @@ LIB_DIR = os.path.join(_HERE, 'lib')
 LIB_PATH = os.environ.get('PAVENET_MSDA_LIB') or os.path.join(LIB_DIR, 'libpavenet_msda.so')
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), 'include')
 
-SOURCES = ['msda_fwd.cu', 'msda_bwd.cu', 'linear256_tc.cu', 'layernorm.cu', 'msda_capi.cu']
-HEADERS = ['msda_common.cuh', 'msda_kernels.h']
+SOURCES = ['msda_fwd.cu', 'msda_bwd.cu', 'msda_flat.cu', 'linear256_tc.cu', 'layernorm.cu', 'msda_capi.cu']
+HEADERS = ['msda_common.cuh', 'msda_bwd_io.cuh', 'msda_kernels.h']
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
     '-O3', '-std=c++17', '-lineinfo',
-    '-Xcompiler', '-fPIC', '-shared',
+    '-Xcompiler', '-fPIC',
 ]
 
 
@@ -53,21 +53,40 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get('PAVENET_MSDA_NVCC_EXTRA', '').split()
+    base = [_nvcc()] + NVCC_FLAGS + os.environ.get('PAVENET_MSDA_NVCC_EXTRA', '').split()
     if verbose:
-        cmd += ['-Xptxas', '-v']
+        base += ['-Xptxas', '-v']
+    objdir = os.path.join(LIB_DIR, 'obj%d' % os.getpid())
+    os.makedirs(objdir, exist_ok=True)
     tmp = LIB_PATH + '.tmp%d' % os.getpid()
-    cmd += ['-o', tmp] + [os.path.join(CSRC, s) for s in SOURCES]
-    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                          text=True)
-    if verbose or proc.returncode != 0:
-        sys.stderr.write(proc.stdout)
-    if proc.returncode != 0:
+    try:
+        # one nvcc per translation unit, side by side; then one link
+        procs = []
+        for src in SOURCES:
+            obj = os.path.join(objdir, src[:-3] + '.o')
+            cmd = base + ['-c', '-o', obj, os.path.join(CSRC, src)]
+            procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE,
+                                                     stderr=subprocess.STDOUT, text=True)))
+        log, failed = [], []
+        for src, obj, proc in procs:
+            out, _ = proc.communicate()
+            log.append(out)
+            if proc.returncode != 0:
+                failed.append(src)
+        if verbose or failed:
+            sys.stderr.write(''.join(log))
+        if failed:
+            raise RuntimeError('nvcc failed on %s:\n%s' % (failed, ''.join(log)[-4000:]))
+        link = [_nvcc(), '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', tmp]
+        link += [obj for _, obj, _ in procs]
+        proc = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError('link failed (exit %d):\n%s' % (proc.returncode, proc.stdout[-4000:]))
+        os.replace(tmp, LIB_PATH)
+    finally:
+        shutil.rmtree(objdir, ignore_errors=True)
         if os.path.exists(tmp):
             os.remove(tmp)
-        raise RuntimeError('nvcc failed (exit %d):\n%s' %
-                           (proc.returncode, proc.stdout[-4000:]))
-    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 

@@ -14,8 +14,9 @@ MSDA_OK = 0
 
 #: every symbol include/pavenet_msda.h declares (tests check the export list)
 EXPORTED_SYMBOLS = (
-    'msda_abi_version', 'msda_last_error', 'msda_launch_count',
-    'msda_kernel_name', 'msda_forward', 'msda_backward', 'msda_fused_forward',
+    'msda_abi_version', 'msda_last_error', 'msda_launch_count', 'msda_launch_count_family',
+    'msda_set_option',
+    'msda_kernel_name', 'msda_forward', 'msda_forward_clear', 'msda_backward', 'msda_fused_forward',
     'msda_fused_backward', 'msda_linear256', 'msda_linear256_wgrad',
     'msda_colsum256', 'msda_linear_fused', 'msda_dropout_backward',
     'msda_layernorm_forward', 'msda_layernorm_backward',
@@ -46,14 +47,23 @@ def _declare(lib):
     lib.msda_forward.argtypes = (
         [c_void_p, c_i64p, c_i64p, c_void_p, c_void_p, c_void_p] +
         [c_int] * 7 + [c_int, c_int, c_void_p])
+    lib.msda_set_option.restype = c_int
+    lib.msda_set_option.argtypes = [ctypes.c_char_p, c_int]
+    lib.msda_launch_count_family.restype = ctypes.c_uint64
+    lib.msda_launch_count_family.argtypes = [c_int]
+    lib.msda_forward_clear.restype = c_int
+    lib.msda_forward_clear.argtypes = (
+        [c_void_p, c_i64p, c_i64p, c_void_p, c_void_p, c_void_p] +
+        [c_int] * 7 + [c_int, c_int, c_void_p, ctypes.c_size_t, c_void_p])
     lib.msda_backward.restype = c_int
     lib.msda_backward.argtypes = (
         [c_void_p, c_i64p, c_i64p, c_void_p, c_void_p, c_void_p, c_void_p,
          c_void_p, c_void_p] + [c_int] * 7 + [c_int, c_int, c_int, c_void_p])
     lib.msda_fused_forward.restype = c_int
-    lib.msda_fused_forward.argtypes = [c_void_p] * 9 + [c_int] * 9 + [c_void_p]
+    lib.msda_fused_forward.argtypes = ([c_void_p] * 9 + [c_int] * 9 +
+                                       [c_void_p, ctypes.c_size_t, c_void_p])
     lib.msda_fused_backward.restype = c_int
-    lib.msda_fused_backward.argtypes = [c_void_p] * 13 + [c_int] * 9 + [c_void_p]
+    lib.msda_fused_backward.argtypes = [c_void_p] * 14 + [c_int] * 9 + [c_void_p]
     lib.msda_linear256.restype = c_int
     lib.msda_linear256.argtypes = [c_void_p] * 4 + [c_int, c_void_p] + [c_int] * 4 + [c_void_p, c_void_p]
     lib.msda_linear256_wgrad.restype = c_int
@@ -122,6 +132,23 @@ def check(status, what):
 
 def launch_count():
     return int(load().msda_launch_count())
+
+
+#: kernel families of msda_launch_count_family (include/pavenet_msda.h)
+KERNEL_FAMILIES = ('fwd_generic', 'bwd_generic', 'fwd_rows', 'bwd_rows', 'fwd_rows_fused',
+                   'bwd_rows_fused', 'fwd_flat', 'bwd_flat', 'fwd_flat_fused', 'bwd_flat_fused',
+                   'linear', 'linear_wgrad', 'colsum', 'layernorm', 'bwd_tile')
+
+
+def family_counts():
+    """{family name: launches since load} -- lets a test assert which kernel ran."""
+    lib = load()
+    return {name: int(lib.msda_launch_count_family(i)) for i, name in enumerate(KERNEL_FAMILIES)}
+
+
+def set_option(name, value):
+    """Kernel-selection knob (include/pavenet_msda.h, msda_set_option)."""
+    check(load().msda_set_option(name.encode(), int(value)), 'msda_set_option')
 
 
 def kernel_name(channels, dtype, value_dtype):

@@ -142,6 +142,7 @@ cudaError_t launch_layernorm_forward(const float* x, const float* gamma, const f
   layernorm256_fwd_kernel<<<ln_grid(rows, sm_count), kLnWarps * 32, 0, st>>>(x, gamma, beta, y, mean, rstd,
                                                                              rows, eps);
   note_launches(1);
+  note_kernel(KF_LAYERNORM);
   return cudaGetLastError();
 }
 
@@ -155,6 +156,7 @@ cudaError_t launch_layernorm_backward(const float* x, const float* dy, const flo
   layernorm256_bwd_kernel<<<ln_grid(rows, sm_count), kLnWarps * 32, 0, st>>>(x, dy, gamma, mean, rstd, dx,
                                                                              dgamma, dbeta, rows);
   note_launches(1);
+  note_kernel(KF_LAYERNORM);
   return cudaGetLastError();
 }
 

@@ -867,6 +867,7 @@ cudaError_t launch_wgrad_shape(const float* dy, const float* x, const uint8_t* r
   linear256_wgrad_kernel<MT, NT><<<grid, kThreads, smem, st>>>(
       mdy, mx, row_mask, mask_mode == 1, mask_mode == 2, dw, rows, rows_per_cta, n_tiles, in_total);
   note_launches(1);
+  note_kernel(KF_LINEAR_WGRAD);
   return cudaGetLastError();
 }
 
@@ -943,6 +944,7 @@ cudaError_t launch_linear256(const float* x, const float* w, const LinearEpilogu
   float* w_lo = scratch + n;
   split_weight_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, w_hi, w_lo, n);
   note_launches(2);
+  note_kernel(KF_LINEAR);
   const bool wide = out_features != 128;      // column tiles of 256, or one of 128
   switch (in_features) {
     case 128:
@@ -994,6 +996,7 @@ cudaError_t launch_colsum256(const float* dy, const uint8_t* row_mask, float* ou
   else MSDA_COLSUM(1024);
 #undef MSDA_COLSUM
   note_launches(1);
+  note_kernel(KF_COLSUM);
   return cudaGetLastError();
 }
 

@@ -20,164 +20,12 @@
 #include <type_traits>
 
 #include "msda_kernels.h"
+#include "msda_bwd_io.cuh"
 
 namespace msda {
 
-// ---- vector reductions into global memory --------------------------------
-__device__ __forceinline__ void red_add_row(float* p, const float (&v)[4]) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]),
-               "f"(v[2]), "f"(v[3])
-               : "memory");
-}
-// How the lanes of a group cover a row in the backward: the width of the GRADIENT element
-// decides.  Under bf16 value storage with fp32 gradients a lane takes 4 channels - an 8-byte
-// value load and ONE 16-byte reduction - so a row leaves the SM as one 128-byte request, like
-// the fp32 kernel.  (Measured on B200: 64-byte reduction requests reach only ~80 % of the byte
-// rate of 128-byte ones; covering the row with 4 lanes x two 64-byte halves ran config 2 in
-// 0.786 ms against 0.642 ms for fp32 values.)
-template <typename VT, typename GT>
-struct BwdVec : Vec16<VT> {};
-template <>
-struct BwdVec<__nv_bfloat16, float> {
-  static constexpr int VEC = 4;
-  __device__ __forceinline__ static void load(const __nv_bfloat16* p, float (&v)[4]) {
-    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
-    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
-    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
-  }
-};
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&t);
-}
-__device__ __forceinline__ void red_add_row(__nv_bfloat16* p, const float (&v)[8]) {
-  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(p),
-               "r"(pack_bf16x2(v[0], v[1])), "r"(pack_bf16x2(v[2], v[3])),
-               "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7]))
-               : "memory");
-}
-__device__ __forceinline__ void red_add_row(__nv_bfloat16* p, const float (&v)[4]) {
-  asm volatile("red.global.add.noftz.v2.bf16x2 [%0], {%1, %2};" ::"l"(p),
-               "r"(pack_bf16x2(v[0], v[1])), "r"(pack_bf16x2(v[2], v[3]))
-               : "memory");
-}
-
-// Sum p[j] over the G lanes of a group; lane gl ends up with the total of
-// sample j == gl.  log2(G) rounds, G-1 shuffles in all.
-template <int G>
-__device__ __forceinline__ float group_transpose_reduce(float (&p)[G], int gl) {
-#pragma unroll
-  for (int half = G / 2; half >= 1; half >>= 1) {
-    const bool upper = (gl & half) != 0;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const float send = upper ? p[i] : p[i + half];
-      const float keep = upper ? p[i + half] : p[i];
-      p[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-    }
-  }
-  return p[0];
-}
-
 constexpr int kRowsThreads = 256;
 constexpr int kRowsWarps = kRowsThreads / 32;
-
-// ---- where the per-sample gradients go -------------------------------------
-// PlainIO: the reference op's outputs, grad_sampling_loc and grad_attn_weight.
-// FusedIO: gradients of the raw projections — grad_offsets = grad_loc * scale
-// and, after a row-wide reduction, the softmax backward
-//   grad_logit_s = w_s * (gw_s - sum_t w_t gw_t)
-// (what autograd would compute through softmax and the location transform,
-// multi_scale_deform_attn.py:375-393), optionally grad_loc for callers that
-// need reference-point gradients.
-struct PlainIO {
-  PlainSource src;
-  float* grad_loc;
-  float* grad_aw;
-  static constexpr bool kFused = false;
-  __device__ __forceinline__ void bind(int64_t unit, int LP, int M, int64_t bq) {
-    src.bind(unit, LP, M, bq);
-    grad_loc += unit * LP * 2;
-    grad_aw += unit * LP;
-  }
-  // gw: d/d(attention weight); (tx, ty): d/d(pixel coordinate), so d/d(location) = (W tx, H ty)
-  __device__ __forceinline__ void store(int s, int, int, float gw, float tx, float ty, float,
-                                        float Wf, float Hf) {
-    __stcs(grad_aw + s, gw);
-    __stcs(reinterpret_cast<float2*>(grad_loc + 2 * s), make_float2(Wf * tx, Hf * ty));
-  }
-};
-
-struct FusedIO {
-  FusedSource src;
-  float* grad_off;    // (B,Q,M,L,P,2)
-  float* grad_logit;  // (B,Q,M,L*P)
-  float* grad_loc;    // optional (B,Q,M,L,P,2), NULL if reference points need no gradient
-  float dot;          // this lane's share of sum_t w_t gw_t
-  // (w_s, gw_s) of the first kCache samples this lane owns stay in registers until the
-  // row's dot product is known; later ones are parked in grad_logit and re-read
-  static constexpr int kCache = 2;
-  float wc[kCache], gc[kCache];
-  static constexpr bool kFused = true;
-  __device__ __forceinline__ void bind(int64_t unit, int LP, int M, int64_t bq) {
-    src.bind(unit, LP, M, bq);
-    grad_off += unit * LP * 2;
-    grad_logit += unit * LP;
-    if (grad_loc) grad_loc += unit * LP * 2;
-    dot = 0.f;
-#pragma unroll
-    for (int k = 0; k < kCache; ++k) wc[k] = gc[k] = 0.f;
-  }
-  // ci: index of the chunk within this group's sample range
-  __device__ __forceinline__ void store(int s, int l, int ci, float gw, float tx, float ty, float w,
-                                        float Wf, float Hf) {
-    float2 go;
-    if (src.scale) {
-      const float2 sc = __ldg(reinterpret_cast<const float2*>(src.scale) + l);
-      go = make_float2(Wf * tx * sc.x, Hf * ty * sc.y);
-    } else {
-      go = make_float2(tx, ty);   // d loc / d off = 1 / (W, H) cancels the pixel scale
-    }
-    __stcs(reinterpret_cast<float2*>(grad_off + 2 * s), go);
-    if (grad_loc) __stcs(reinterpret_cast<float2*>(grad_loc + 2 * s), make_float2(Wf * tx, Hf * ty));
-#pragma unroll
-    for (int k = 0; k < kCache; ++k) {
-      wc[k] = (ci == k) ? w : wc[k];
-      gc[k] = (ci == k) ? gw : gc[k];
-    }
-    if (ci >= kCache) grad_logit[s] = gw;  // parked until the row's dot product is known
-    dot += w * gw;
-  }
-};
-
-template <int G>
-__device__ __forceinline__ void finish_softmax_backward(PlainIO&, float*, int, int, int, int, int) {}
-
-// grad_logit_s = w_s (gw_s - dot), dot = sum_t w_t gw_t over the row.  A row
-// split over several groups of the block (nsplit > 1) adds its partial dots in
-// shared memory; every thread of the block must then reach the barrier.
-template <int G>
-__device__ __forceinline__ void finish_softmax_backward(FusedIO& io, float* s_dot, int row_in_block,
-                                                        int s_begin, int s_end, int gl, int nsplit) {
-  float dot = io.dot;
-#pragma unroll
-  for (int o = G / 2; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-  if (nsplit > 1) {
-    if (gl == 0 && s_end > s_begin) atomicAdd(&s_dot[row_in_block], dot);
-    __syncthreads();
-    dot = s_dot[row_in_block];
-  }
-#pragma unroll
-  for (int k = 0; k < FusedIO::kCache; ++k) {
-    const int s = s_begin + gl + k * G;
-    if (s < s_end) io.grad_logit[s] = io.wc[k] * (io.gc[k] - dot);
-  }
-  for (int s = s_begin + gl + FusedIO::kCache * G; s < s_end; s += G) {
-    const float w = __expf(__ldg(io.src.logit + s) - io.src.mx) * io.src.inv;
-    io.grad_logit[s] = w * (io.grad_logit[s] - dot);   // own earlier write: same thread
-  }
-}
 
 template <int D, typename VT, typename GT, class IO>
 __global__ void __launch_bounds__(kRowsThreads, IO::kFused ? 2 : 0)
@@ -191,11 +39,9 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
 
   __shared__ LevelInfo s_lvl[kMaxSmemLevels];
   __shared__ int4 s_board[kRowsWarps][G * (2 * (32 / G) + 1)];
-  __shared__ float s_dot[IO::kFused ? kRowsThreads / G : 1];  // fused: per-row sum_t w_t gw_t
 
   const int MD = d.M * D;
   for (int l = threadIdx.x; l < d.L; l += blockDim.x) s_lvl[l] = load_level(shapes, lsi, l, MD);
-  if (IO::kFused && threadIdx.x < kRowsThreads / G) s_dot[threadIdx.x] = 0.f;
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -235,6 +81,7 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
       g[c] = t.x; g[c + 1] = t.y; g[c + 2] = t.z; g[c + 3] = t.w;
     }
   }
+  io.template row_dot<G, VEC>(g, unit, D, gl);   // fused: <grad_out[row], out[row]>
 
   const int per = ((LP + nsplit - 1) / nsplit + G - 1) / G * G;
   const int s_begin = split * per;
@@ -330,10 +177,9 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     const float tw = group_transpose_reduce<G>(pw, gl);
     const float tx = group_transpose_reduce<G>(px, gl);
     const float ty = group_transpose_reduce<G>(py, gl);
-    if (s < s_end) io.store(s, lvl, (s0 - s_begin) / G, tw, tx, ty, w_true, Wf, Hf);
+    if (s < s_end) io.store(s, lvl, tw, tx, ty, w_true, Wf, Hf);
     __syncwarp();
   }
-  finish_softmax_backward<G>(io, s_dot, gib / nsplit, s_begin, s_end, gl, nsplit);
 }
 
 // --------------------------------------------------------------------------
@@ -448,6 +294,7 @@ static cudaError_t launch_bwd_rows(const void* value, const int64_t* shapes, con
   msda_bwd_rows_kernel<D, VT, GT, IO><<<static_cast<unsigned>(blocks), kRowsThreads, 0, st>>>(
       static_cast<const VT*>(value), shapes, lsi, io, go, static_cast<GT*>(gv), d, nsplit);
   note_launches(1);
+  note_kernel(IO::kFused ? KF_BWD_ROWS_FUSED : KF_BWD_ROWS);
   return cudaGetLastError();
 }
 
@@ -479,6 +326,12 @@ cudaError_t launch_backward(const void* value, const int64_t* shapes, const int6
     io.grad_loc = static_cast<float*>(grad_loc);
     io.grad_aw = static_cast<float*>(grad_aw);
     const float* gof = static_cast<const float*>(grad_out);
+    {
+      const int vec = (value_dtype == MSDA_BF16 && grad_value_dtype == MSDA_BF16) ? 8 : 4;
+      if (flat_preferred(d, d.D / vec, sm_count))
+        return launch_backward_flat(value, shapes, lsi, io, gof, grad_value, d, value_dtype,
+                                    grad_value_dtype, sm_count, st);
+    }
 #define MSDA_BWD_CASE(DD)                                                                         \
   case DD:                                                                                        \
     if (value_dtype == MSDA_F32) {                                                                \
@@ -519,22 +372,29 @@ cudaError_t launch_backward(const void* value, const int64_t* shapes, const int6
   }
 #undef MSDA_GEN
   note_launches(1);
+  note_kernel(KF_BWD_GENERIC);
   return cudaGetLastError();
 }
 
 // fused epilogue: D = 32, fp32 gradients, fp32 or bf16 value
 cudaError_t launch_backward_fused(const void* value, const int64_t* shapes, const int64_t* lsi,
-                                  const FusedSource& src, const float* grad_out, float* grad_value,
-                                  float* grad_off, float* grad_logit, float* grad_loc,
-                                  const Dims& d, int value_dtype, int sm_count, cudaStream_t st) {
-  if (d.D != 32 || d.L > kMaxSmemLevels) return cudaErrorNotSupported;
+                                  const FusedSource& src, const float* out, const float* grad_out,
+                                  float* grad_value, float* grad_off, float* grad_logit,
+                                  float* grad_loc, const Dims& d, int value_dtype, int sm_count,
+                                  cudaStream_t st) {
+  if (d.D != 32 || d.L > kMaxSmemLevels || !out) return cudaErrorNotSupported;
+  if (value_dtype != MSDA_F32 && value_dtype != MSDA_BF16) return cudaErrorNotSupported;
   FusedIO io;
+  io.out = out;
   io.src = src;
   io.src.stats_ready = 1;
   io.grad_off = grad_off;
   io.grad_logit = grad_logit;
   io.grad_loc = grad_loc;
   io.dot = 0.f;
+  if (flat_preferred(d, 8, sm_count))
+    return launch_backward_flat_fused(value, shapes, lsi, io, grad_out, grad_value, d, value_dtype,
+                                      sm_count, st);
   if (value_dtype == MSDA_F32)
     return launch_bwd_rows<32, float, float, FusedIO>(value, shapes, lsi, io, grad_out, grad_value,
                                                       d, choose_bwd_split(d, 8, sm_count), st);

@@ -15,6 +15,10 @@ namespace msda {
 
 static std::atomic<uint64_t> g_launches{0};
 void note_launches(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+static std::atomic<uint64_t> g_family[KF_COUNT];
+void note_kernel(int family) {
+  if (family >= 0 && family < KF_COUNT) g_family[family].fetch_add(1, std::memory_order_relaxed);
+}
 
 static thread_local char t_err[512] = "";
 
@@ -31,7 +35,7 @@ static int env_int(const char* name, int dflt) {
   return (v && *v) ? std::atoi(v) : dflt;
 }
 
-const Tuning& tuning() {
+static Tuning& tuning_mut() {
   static Tuning t = [] {
     Tuning x;
     x.force_generic = env_int("PAVENET_MSDA_FORCE_GENERIC", 0);
@@ -43,10 +47,16 @@ const Tuning& tuning() {
     x.copy_streams = env_int("PAVENET_MSDA_COPY_STREAMS", 1);
     if (x.copy_streams < 1) x.copy_streams = 1;
     if (x.copy_streams > 4) x.copy_streams = 4;
+    x.flat = env_int("PAVENET_MSDA_FLAT", 1);
+    x.l2_prefetch = env_int("PAVENET_MSDA_L2_PREFETCH", x.l2_prefetch);
+    x.l2_prefetch_mb = env_int("PAVENET_MSDA_L2_PREFETCH_MB", x.l2_prefetch_mb);
+    x.bwd_variant = env_int("PAVENET_MSDA_BWD_VARIANT", 0);
+    x.fwd_variant = env_int("PAVENET_MSDA_FWD_VARIANT", 0);
     return x;
   }();
   return t;
 }
+const Tuning& tuning() { return tuning_mut(); }
 
 // SM count of the current device, cached per device ordinal.
 static int current_sm_count(int* out) {
@@ -139,6 +149,27 @@ const char* msda_last_error(void) { return t_err; }
 
 uint64_t msda_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int msda_set_option(const char* name, int value) {
+  if (!name) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_set_option: NULL name");
+  Tuning& t = tuning_mut();
+  int* slot = nullptr;
+  if (!std::strcmp(name, "force_generic")) slot = &t.force_generic;
+  else if (!std::strcmp(name, "fwd_split")) slot = &t.fwd_split;
+  else if (!std::strcmp(name, "bwd_split")) slot = &t.bwd_split;
+  else if (!std::strcmp(name, "flat")) slot = &t.flat;
+  else if (!std::strcmp(name, "l2_prefetch")) slot = &t.l2_prefetch;
+  else if (!std::strcmp(name, "l2_prefetch_mb")) slot = &t.l2_prefetch_mb;
+  else if (!std::strcmp(name, "bwd_variant")) slot = &t.bwd_variant;
+  else if (!std::strcmp(name, "fwd_variant")) slot = &t.fwd_variant;
+  if (!slot) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_set_option: unknown option '%s'", name);
+  *slot = value;
+  return MSDA_OK;
+}
+
+uint64_t msda_launch_count_family(int family) {
+  return (family >= 0 && family < KF_COUNT) ? g_family[family].load(std::memory_order_relaxed) : 0;
+}
+
 const char* msda_kernel_name(int channels, int dtype, int value_dtype) {
   if (dtype == MSDA_F32 && !tuning().force_generic && rows_supported(channels, value_dtype)) {
     if (value_dtype == MSDA_BF16)
@@ -153,6 +184,19 @@ int msda_forward(const void* d_value, const int64_t* d_spatial_shapes,
                  const void* d_attn_weight, void* d_output, int batch, int spatial_size,
                  int num_heads, int channels, int num_levels, int num_query, int num_point,
                  int dtype, int value_dtype, void* stream) {
+  return msda_forward_clear(d_value, d_spatial_shapes, d_level_start_index, d_sampling_loc,
+                            d_attn_weight, d_output, batch, spatial_size, num_heads, channels,
+                            num_levels, num_query, num_point, dtype, value_dtype, nullptr, 0, stream);
+}
+
+int msda_forward_clear(const void* d_value, const int64_t* d_spatial_shapes,
+                       const int64_t* d_level_start_index, const void* d_sampling_loc,
+                       const void* d_attn_weight, void* d_output, int batch, int spatial_size,
+                       int num_heads, int channels, int num_levels, int num_query, int num_point,
+                       int dtype, int value_dtype, void* d_clear, size_t clear_bytes,
+                       void* stream) {
+  if ((d_clear == nullptr) != (clear_bytes == 0))
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_forward_clear: d_clear and clear_bytes must both be set or both be zero");
   if (!d_value || !d_spatial_shapes || !d_level_start_index || !d_sampling_loc || !d_attn_weight ||
       !d_output)
     return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_forward: NULL pointer argument");
@@ -170,7 +214,8 @@ int msda_forward(const void* d_value, const int64_t* d_spatial_shapes,
                       misaligned16(d_sampling_loc) || entry_bytes_overflow(d, value_dtype);
   const cudaError_t e =
       launch_forward(d_value, d_spatial_shapes, d_level_start_index, d_sampling_loc, d_attn_weight,
-                     d_output, d, dtype, value_dtype, sms, generic, static_cast<cudaStream_t>(stream));
+                     d_output, d, dtype, value_dtype, sms, generic, d_clear, clear_bytes,
+                     static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess)
     return fail(MSDA_ERR_CUDA, "msda_forward launch failed: %s", cudaGetErrorString(e));
   return MSDA_OK;
@@ -223,10 +268,13 @@ int msda_fused_forward(const void* d_value, const int64_t* d_spatial_shapes,
                        const float* d_logits, const float* d_ref_points, const float* d_scale,
                        float* d_output, float* d_softmax_stats, int batch, int spatial_size,
                        int num_heads, int channels, int num_levels, int num_query, int num_point,
-                       int ref_points_per_level, int value_dtype, void* stream) {
+                       int ref_points_per_level, int value_dtype, void* d_clear, size_t clear_bytes,
+                       void* stream) {
   if (!d_value || !d_spatial_shapes || !d_level_start_index || !d_offsets || !d_logits ||
       !d_ref_points || !d_output || !d_softmax_stats)
     return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_fused_forward: NULL pointer argument");
+  if ((d_clear == nullptr) != (clear_bytes == 0))
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_fused_forward: d_clear and clear_bytes must both be set or both be zero");
   Dims d;
   int rc = check_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, &d);
   if (rc) return rc;
@@ -244,7 +292,7 @@ int msda_fused_forward(const void* d_value, const int64_t* d_spatial_shapes,
   rc = current_sm_count(&sms);
   if (rc) return rc;
   const cudaError_t e = launch_forward_fused(d_value, d_spatial_shapes, d_level_start_index, src,
-                                             d_output, d, value_dtype, sms,
+                                             d_output, d, value_dtype, sms, d_clear, clear_bytes,
                                              static_cast<cudaStream_t>(stream));
   if (e == cudaErrorNotSupported)
     return fail(MSDA_ERR_UNSUPPORTED, "msda_fused_forward: only channels == 32 and <= %d levels",
@@ -257,14 +305,15 @@ int msda_fused_forward(const void* d_value, const int64_t* d_spatial_shapes,
 int msda_fused_backward(const void* d_value, const int64_t* d_spatial_shapes,
                         const int64_t* d_level_start_index, const float* d_offsets,
                         const float* d_logits, const float* d_ref_points, const float* d_scale,
-                        const float* d_softmax_stats, const float* d_grad_output,
+                        const float* d_softmax_stats, const float* d_output,
+                        const float* d_grad_output,
                         float* d_grad_value, float* d_grad_offsets, float* d_grad_logits,
                         float* d_grad_loc, int batch, int spatial_size, int num_heads,
                         int channels, int num_levels, int num_query, int num_point,
                         int ref_points_per_level, int value_dtype, void* stream) {
   if (!d_value || !d_spatial_shapes || !d_level_start_index || !d_offsets || !d_logits ||
-      !d_ref_points || !d_softmax_stats || !d_grad_output || !d_grad_value || !d_grad_offsets ||
-      !d_grad_logits)
+      !d_ref_points || !d_softmax_stats || !d_output || !d_grad_output || !d_grad_value ||
+      !d_grad_offsets || !d_grad_logits)
     return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_fused_backward: NULL pointer argument");
   Dims d;
   int rc = check_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, &d);
@@ -272,7 +321,7 @@ int msda_fused_backward(const void* d_value, const int64_t* d_spatial_shapes,
   rc = check_dtypes(MSDA_F32, value_dtype, MSDA_F32);
   if (rc) return rc;
   if (misaligned16(d_value) || misaligned16(d_grad_output) || misaligned16(d_grad_value) ||
-      misaligned16(d_offsets) || misaligned16(d_grad_offsets))
+      misaligned16(d_offsets) || misaligned16(d_grad_offsets) || misaligned16(d_output))
     return fail(MSDA_ERR_UNSUPPORTED, "msda_fused_backward needs 16-byte aligned buffers");
   FusedSource src;
   rc = fused_source(&src, d_offsets, d_logits, d_ref_points, d_scale,
@@ -282,7 +331,7 @@ int msda_fused_backward(const void* d_value, const int64_t* d_spatial_shapes,
   rc = current_sm_count(&sms);
   if (rc) return rc;
   const cudaError_t e = launch_backward_fused(
-      d_value, d_spatial_shapes, d_level_start_index, src, d_grad_output, d_grad_value,
+      d_value, d_spatial_shapes, d_level_start_index, src, d_output, d_grad_output, d_grad_value,
       d_grad_offsets, d_grad_logits, d_grad_loc, d, value_dtype, sms,
       static_cast<cudaStream_t>(stream));
   if (e == cudaErrorNotSupported)

@@ -17,6 +17,8 @@
 //    end) so small-Q pose-decoder shapes still fill the machine.
 //  * generic<T,VT>: any D, fp32/fp64 — the parity path for the shapes the
 //    reference's tests use (D = 2, 4, 30, 71, 1025, double precision).
+#include <type_traits>
+
 #include "msda_kernels.h"
 
 namespace msda {
@@ -258,6 +260,7 @@ static cudaError_t launch_rows_split(const void* value, const int64_t* shapes, c
   msda_fwd_rows_kernel<D, VT, SPLIT, SRC><<<static_cast<unsigned>(blocks), kRowsThreads, 0, st>>>(
       static_cast<const VT*>(value), shapes, lsi, src, out, d);
   note_launches(1);
+  note_kernel(std::is_same<SRC, FusedSource>::value ? KF_FWD_ROWS_FUSED : KF_FWD_ROWS);
   return cudaGetLastError();
 }
 
@@ -297,15 +300,27 @@ bool rows_supported(int D, int value_dtype) {
   return D == 16 || D == 32 || D == 64;
 }
 
+// zero-fill of the optional `clear` buffer for the kernel families that do not fold it in
+static cudaError_t clear_by_memset(void* clear, size_t clear_bytes, cudaStream_t st) {
+  if (!clear || !clear_bytes) return cudaSuccess;
+  return cudaMemsetAsync(clear, 0, clear_bytes, st);
+}
+
 cudaError_t launch_forward(const void* value, const int64_t* shapes, const int64_t* lsi,
                            const void* loc, const void* aw, void* out, const Dims& d, int dtype,
-                           int value_dtype, int sm_count, int force_generic, cudaStream_t st) {
+                           int value_dtype, int sm_count, int force_generic, void* clear,
+                           size_t clear_bytes, cudaStream_t st) {
   if (dtype == MSDA_F32 && !force_generic && d.L <= kMaxSmemLevels &&
       rows_supported(d.D, value_dtype)) {
     PlainSource src;
     src.loc = static_cast<const float*>(loc);
     src.aw = static_cast<const float*>(aw);
     float* outf = static_cast<float*>(out);
+    if (flat_preferred(d, d.D / (value_dtype == MSDA_F32 ? 4 : 8), sm_count))
+      return launch_forward_flat(value, shapes, lsi, src, outf, d, value_dtype, sm_count,
+                                 (clear_bytes % 16 == 0) ? clear : nullptr, clear_bytes, st) ;
+    const cudaError_t ce = clear_by_memset(clear, clear_bytes, st);
+    if (ce != cudaSuccess) return ce;
 #define MSDA_ROWS_CASE(DD)                                                                   \
   case DD:                                                                                   \
     if (value_dtype == MSDA_F32) {                                                           \
@@ -324,6 +339,10 @@ cudaError_t launch_forward(const void* value, const int64_t* shapes, const int64
 #undef MSDA_ROWS_CASE
   }
   // generic path
+  {
+    const cudaError_t ce = clear_by_memset(clear, clear_bytes, st);
+    if (ce != cudaSuccess) return ce;
+  }
   const int64_t total = static_cast<int64_t>(d.B) * d.Q * d.M * d.D;
   const int64_t want = (total + 255) / 256;
   const unsigned blocks = static_cast<unsigned>(want < (1 << 20) ? want : (1 << 20));
@@ -343,14 +362,21 @@ cudaError_t launch_forward(const void* value, const int64_t* shapes, const int64
     return cudaErrorInvalidValue;
   }
   note_launches(1);
+  note_kernel(KF_FWD_GENERIC);
   return cudaGetLastError();
 }
 
 // fused prologue: D = 32 only (PAVE-Net's head size), fp32 or bf16 value
 cudaError_t launch_forward_fused(const void* value, const int64_t* shapes, const int64_t* lsi,
                                  const FusedSource& src, float* out, const Dims& d, int value_dtype,
-                                 int sm_count, cudaStream_t st) {
+                                 int sm_count, void* clear, size_t clear_bytes, cudaStream_t st) {
   if (d.D != 32 || d.L > kMaxSmemLevels) return cudaErrorNotSupported;
+  if (value_dtype != MSDA_F32 && value_dtype != MSDA_BF16) return cudaErrorNotSupported;
+  if (flat_preferred(d, value_dtype == MSDA_F32 ? 8 : 4, sm_count))
+    return launch_forward_flat_fused(value, shapes, lsi, src, out, d, value_dtype, sm_count,
+                                     (clear_bytes % 16 == 0) ? clear : nullptr, clear_bytes, st);
+  const cudaError_t ce = clear_by_memset(clear, clear_bytes, st);
+  if (ce != cudaSuccess) return ce;
   if (value_dtype == MSDA_F32)
     return launch_rows<32, float, FusedSource>(value, shapes, lsi, src, out, d,
                                                choose_split(d, 8, sm_count), st);

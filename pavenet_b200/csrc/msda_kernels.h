@@ -5,6 +5,7 @@
 
 #include "../../include/pavenet_msda.h"
 #include "msda_common.cuh"
+#include "msda_bwd_io.cuh"
 
 namespace msda {
 
@@ -18,15 +19,50 @@ struct Tuning {
   int linear_bk = 16; // linear256 K-chunk: 16 (two CTAs per SM) or 32 (one)
   int linear_bm = 0;  // rows per CTA: 128 (default, also 0) or 256
   int copy_streams = 1;  // host-buffer entry points: upload / download streams per direction (1..4)
+  int flat = 1;          // flat small-Q kernels (msda_flat.cu): 0 never, 1 heuristic, 2 whenever legal
+  int l2_prefetch = 0;     // flat kernels stream value into L2 first: bit 0 forward, bit 1 backward
+  int l2_prefetch_mb = 120;  // ... when value is at most this many MiB
+  int bwd_variant = 0;   // large-Q backward: 0 default, 1 plain rows, 2 warp-aggregated, 3 tile
+  int fwd_variant = 0;   // large-Q forward: 0 default, 1 plain rows, 2 ...
 };
 const Tuning& tuning();
 
 bool rows_supported(int D, int value_dtype);
 int choose_split(const Dims& d, int G, int sm_count);
 
+// Kernel families, for msda_launch_count_family(): tests assert that the kernel they
+// mean to check is the one that ran.
+enum KernelFamily {
+  KF_FWD_GENERIC = 0, KF_BWD_GENERIC, KF_FWD_ROWS, KF_BWD_ROWS, KF_FWD_ROWS_FUSED,
+  KF_BWD_ROWS_FUSED, KF_FWD_FLAT, KF_BWD_FLAT, KF_FWD_FLAT_FUSED, KF_BWD_FLAT_FUSED,
+  KF_LINEAR, KF_LINEAR_WGRAD, KF_COLSUM, KF_LAYERNORM, KF_BWD_TILE, KF_COUNT
+};
+void note_kernel(int family);
+
+// `clear` / `clear_bytes`: optional buffer (the coming backward's grad_value) the forward
+// zero-fills on the same stream — inside the kernel for the flat family, as a memset otherwise.
 cudaError_t launch_forward(const void* value, const int64_t* shapes, const int64_t* lsi,
                            const void* loc, const void* aw, void* out, const Dims& d, int dtype,
-                           int value_dtype, int sm_count, int force_generic, cudaStream_t st);
+                           int value_dtype, int sm_count, int force_generic, void* clear,
+                           size_t clear_bytes, cudaStream_t st);
+
+// flat small-Q family (msda_flat.cu)
+bool flat_preferred(const Dims& d, int G, int sm_count);
+cudaError_t launch_forward_flat(const void* value, const int64_t* shapes, const int64_t* lsi,
+                                const PlainSource& src, float* out, const Dims& d, int value_dtype,
+                                int sm_count, void* clear, size_t clear_bytes, cudaStream_t st);
+cudaError_t launch_forward_flat_fused(const void* value, const int64_t* shapes, const int64_t* lsi,
+                                      const FusedSource& src, float* out, const Dims& d,
+                                      int value_dtype, int sm_count, void* clear,
+                                      size_t clear_bytes, cudaStream_t st);
+cudaError_t launch_backward_flat(const void* value, const int64_t* shapes, const int64_t* lsi,
+                                 const PlainIO& io, const float* grad_out, void* grad_value,
+                                 const Dims& d, int value_dtype, int grad_value_dtype, int sm_count,
+                                 cudaStream_t st);
+cudaError_t launch_backward_flat_fused(const void* value, const int64_t* shapes,
+                                       const int64_t* lsi, const FusedIO& io,
+                                       const float* grad_out, float* grad_value, const Dims& d,
+                                       int value_dtype, int sm_count, cudaStream_t st);
 
 cudaError_t launch_backward(const void* value, const int64_t* shapes, const int64_t* lsi,
                             const void* loc, const void* aw, const void* grad_out,
@@ -36,12 +72,13 @@ cudaError_t launch_backward(const void* value, const int64_t* shapes, const int6
 
 cudaError_t launch_forward_fused(const void* value, const int64_t* shapes, const int64_t* lsi,
                                  const FusedSource& src, float* out, const Dims& d, int value_dtype,
-                                 int sm_count, cudaStream_t st);
+                                 int sm_count, void* clear, size_t clear_bytes, cudaStream_t st);
 
 cudaError_t launch_backward_fused(const void* value, const int64_t* shapes, const int64_t* lsi,
-                                  const FusedSource& src, const float* grad_out, float* grad_value,
-                                  float* grad_off, float* grad_logit, float* grad_loc,
-                                  const Dims& d, int value_dtype, int sm_count, cudaStream_t st);
+                                  const FusedSource& src, const float* out, const float* grad_out,
+                                  float* grad_value, float* grad_off, float* grad_logit,
+                                  float* grad_loc, const Dims& d, int value_dtype, int sm_count,
+                                  cudaStream_t st);
 
 // Y = epilogue(X W^T), dW = dY^T X and the bias gradient for the Linear layers of the
 // attention modules and transformer layers on tcgen05 (3xTF32), linear256_tc.cu.

@@ -18,6 +18,7 @@ from . import _capi
 __all__ = [
     'MultiScaleDeformableAttnFunction', 'ext_module', 'ms_deform_attn_forward',
     'ms_deform_attn_backward', 'fuse_frames_as_levels', 'BF16_GRAD_VALUE_ATOMICS',
+    'EARLY_GRAD_VALUE_CLEAR',
     'HostWorkspace', 'FusedMultiScaleDeformableAttnFunction', 'fused_supported',
     'Linear256Function', 'linear256', 'linear256_supported',
     'FusedFFNFunction', 'fused_ffn', 'ffn_supported', 'device_dropout_seed',
@@ -29,6 +30,12 @@ __all__ = [
 #: kernel reduce straight into a bf16 tensor with packed bf16x2 atomics
 #: (True: half the scatter bytes, every partial sum rounded to 8 bits).
 BF16_GRAD_VALUE_ATOMICS = False
+
+#: Zero-fill the backward's grad_value buffer during the FORWARD call (when `value`
+#: requires grad): for the small-Q shapes the fill is folded into the persistent forward
+#: kernel (msda_forward_clear), which takes the full-tensor clear off the critical path of
+#: the backward.  The buffer then lives from forward to backward.
+EARLY_GRAD_VALUE_CLEAR = True
 
 _DTYPE_CODE = {
     torch.float32: _capi.MSDA_F32,
@@ -91,27 +98,42 @@ def _check_inputs(value, spatial_shapes, level_start_index, sampling_loc,
     return B, S, M, D, L, Q, P
 
 
+def _check_clear(clear, device):
+    if clear is None:
+        return None, 0
+    if not (isinstance(clear, torch.Tensor) and clear.is_cuda and clear.device == device
+            and clear.is_contiguous()):
+        raise RuntimeError('clear must be a contiguous CUDA tensor on %s' % device)
+    nbytes = clear.numel() * clear.element_size()
+    return (clear.data_ptr(), nbytes) if nbytes else (None, 0)
+
+
 def ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index,
-                           sampling_locations, attention_weights, im2col_step=64):
+                           sampling_locations, attention_weights, im2col_step=64, clear=None):
     """Drop-in for `ext_module.ms_deform_attn_forward` (pybind.cpp:737-742).
 
     Returns a new tensor of shape (bs, num_queries, num_heads*dim_per_head)
-    in the dtype of `sampling_locations`.
+    in the dtype of `sampling_locations`.  `clear` (not in the reference): a tensor to
+    zero-fill on the same stream, normally the coming backward's grad_value
+    (`msda_forward_clear`).
     """
     B, S, M, D, L, Q, P = _check_inputs(value, value_spatial_shapes, value_level_start_index,
                                         sampling_locations, attention_weights, im2col_step)
     lib = _capi.load()
     if min(B, S, M, D, L, Q, P) == 0:
         # nothing to sample (or nothing to write): the sum over an empty set
+        if clear is not None:
+            clear.zero_()
         return torch.zeros((B, Q, M * D), dtype=sampling_locations.dtype, device=value.device)
+    clear_ptr, clear_bytes = _check_clear(clear, value.device)
     with torch.cuda.device(value.device):
         output = torch.empty((B, Q, M * D), dtype=sampling_locations.dtype, device=value.device)
         stream = torch.cuda.current_stream().cuda_stream
-        status = lib.msda_forward(
+        status = lib.msda_forward_clear(
             value.data_ptr(), value_spatial_shapes.data_ptr(), value_level_start_index.data_ptr(),
             sampling_locations.data_ptr(), attention_weights.data_ptr(), output.data_ptr(),
             B, S, M, D, L, Q, P, _DTYPE_CODE[sampling_locations.dtype], _DTYPE_CODE[value.dtype],
-            stream)
+            clear_ptr, clear_bytes, stream)
     _capi.check(status, 'msda_forward')
     return output
 
@@ -174,6 +196,12 @@ class _ExtModule(object):
 ext_module = _ExtModule()
 
 
+def _grad_value_dtype(value, sampling_locations):
+    if value.dtype == torch.bfloat16 and BF16_GRAD_VALUE_ATOMICS:
+        return torch.bfloat16
+    return sampling_locations.dtype
+
+
 class MultiScaleDeformableAttnFunction(Function):
     """Same `apply` signature and return shape as the reference
     (multi_scale_deform_attn.py:20-89)."""
@@ -196,9 +224,19 @@ class MultiScaleDeformableAttnFunction(Function):
             (bs, num_queries, embed_dims)
         """
         ctx.im2col_step = im2col_step
-        output = ext_module.ms_deform_attn_forward(
-            value, value_spatial_shapes, value_level_start_index, sampling_locations,
-            attention_weights, im2col_step=ctx.im2col_step)
+        ctx.grad_value_buf = None
+        if (EARLY_GRAD_VALUE_CLEAR and ctx.needs_input_grad[0] and value.is_cuda
+                and value.numel() > 0):
+            # the backward's accumulator, zero-filled by the forward launch
+            ctx.grad_value_buf = torch.empty(value.shape, dtype=_grad_value_dtype(
+                value, sampling_locations), device=value.device)
+            output = ms_deform_attn_forward(
+                value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                attention_weights, im2col_step=ctx.im2col_step, clear=ctx.grad_value_buf)
+        else:
+            output = ext_module.ms_deform_attn_forward(
+                value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                attention_weights, im2col_step=ctx.im2col_step)
         ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index,
                               sampling_locations, attention_weights)
         return output
@@ -208,10 +246,10 @@ class MultiScaleDeformableAttnFunction(Function):
     def backward(ctx, grad_output):
         value, value_spatial_shapes, value_level_start_index, \
             sampling_locations, attention_weights = ctx.saved_tensors
-        acc_dtype = sampling_locations.dtype
-        if value.dtype == torch.bfloat16 and BF16_GRAD_VALUE_ATOMICS:
-            acc_dtype = torch.bfloat16
-        grad_value = torch.zeros(value.shape, dtype=acc_dtype, device=value.device)
+        grad_value, ctx.grad_value_buf = ctx.grad_value_buf, None   # used once
+        if grad_value is None:
+            grad_value = torch.zeros(value.shape, dtype=_grad_value_dtype(value, sampling_locations),
+                                     device=value.device)
         # fully overwritten by the kernels: no zero-fill needed
         grad_sampling_loc = torch.empty_like(sampling_locations)
         grad_attn_weight = torch.empty_like(attention_weights)
@@ -345,6 +383,37 @@ def fused_supported(value, offsets):
             and min(value.shape) > 0 and min(offsets.shape) > 0)
 
 
+def _check_fused_tables(value, spatial_shapes, level_start_index, logits, ref_points, scale, L):
+    """The checks `_check_inputs` makes for the plain op, for the fused entry points: the
+    kernels read the level tables, logits and reference points through raw pointers, so a
+    CPU / int32 / strided / other-device tensor must be refused here
+    (ms_deform_attn_cuda.cu:218-232 AT_ASSERTM contiguous / is_cuda)."""
+    named = [('spatial_shapes', spatial_shapes), ('level_start_index', level_start_index),
+             ('logits', logits), ('ref_points', ref_points)]
+    if scale is not None:
+        named.append(('scale', scale))
+    for name, t in named:
+        if not isinstance(t, torch.Tensor):
+            raise TypeError('%s must be a torch.Tensor, got %s' % (name, type(t)))
+        if not t.is_cuda:
+            raise RuntimeError('%s must be a CUDA tensor' % name)
+        if t.device != value.device:
+            raise RuntimeError('%s is on %s but value is on %s: all tensors must be on the '
+                               'same device' % (name, t.device, value.device))
+    for name, t in named[:2]:
+        if t.dtype != torch.int64:
+            raise RuntimeError('spatial_shapes and level_start_index must be int64 tensors')
+        if not t.is_contiguous():
+            raise RuntimeError('%s tensor has to be contiguous' % name)
+    if tuple(spatial_shapes.shape) != (L, 2) or tuple(level_start_index.shape) != (L,):
+        raise RuntimeError('spatial_shapes must be (%d, 2) and level_start_index (%d,), got %s / %s'
+                           % (L, L, tuple(spatial_shapes.shape), tuple(level_start_index.shape)))
+    if logits.dtype != torch.float32:
+        raise RuntimeError('logits must be float32, got %s' % logits.dtype)
+    if not ref_points.is_floating_point() or (scale is not None and not scale.is_floating_point()):
+        raise RuntimeError('ref_points / scale must be floating-point tensors')
+
+
 class FusedMultiScaleDeformableAttnFunction(Function):
     """The op with the modules' elementwise chain folded in.
 
@@ -379,29 +448,35 @@ class FusedMultiScaleDeformableAttnFunction(Function):
             raise RuntimeError('fused deformable attention: inconsistent shapes value %s offsets %s '
                                'logits %s ref_points %s' % (tuple(value.shape), tuple(offsets.shape),
                                                             tuple(logits.shape), tuple(ref_points.shape)))
+        _check_fused_tables(value, spatial_shapes, level_start_index, logits, ref_points, scale, L)
         value, offsets, logits = value.contiguous(), offsets.contiguous(), logits.contiguous()
         ref_points = ref_points.contiguous().float()
         scale = None if scale is None else scale.contiguous().float()
         lib = _capi.load()
+        ctx.grad_value_buf = None
         with torch.cuda.device(value.device):
             out = torch.empty((B, Q, M * D), dtype=torch.float32, device=value.device)
             stats = torch.empty((B, Q, M, 2), dtype=torch.float32, device=value.device)
+            if EARLY_GRAD_VALUE_CLEAR and ctx.needs_input_grad[0]:
+                ctx.grad_value_buf = torch.empty(value.shape, dtype=torch.float32,
+                                                 device=value.device)
+            clear_ptr, clear_bytes = _check_clear(ctx.grad_value_buf, value.device)
             status = lib.msda_fused_forward(
                 value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
                 offsets.data_ptr(), logits.data_ptr(), ref_points.data_ptr(),
                 None if scale is None else scale.data_ptr(), out.data_ptr(), stats.data_ptr(),
-                B, S, M, D, L, Q, P, R, _DTYPE_CODE[value.dtype],
+                B, S, M, D, L, Q, P, R, _DTYPE_CODE[value.dtype], clear_ptr, clear_bytes,
                 torch.cuda.current_stream().cuda_stream)
         _capi.check(status, 'msda_fused_forward')
         ctx.save_for_backward(value, spatial_shapes, level_start_index, offsets, logits,
-                              ref_points, scale, stats)
+                              ref_points, scale, stats, out)
         ctx.has_scale = scale is not None
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
-        value, spatial_shapes, level_start_index, offsets, logits, ref_points, scale, stats = \
+        value, spatial_shapes, level_start_index, offsets, logits, ref_points, scale, stats, out = \
             ctx.saved_tensors
         B, S, M, D = value.shape
         _, Q, _, L, P, _ = offsets.shape
@@ -410,14 +485,16 @@ class FusedMultiScaleDeformableAttnFunction(Function):
         need_scale = ctx.has_scale and ctx.needs_input_grad[6]
         lib = _capi.load()
         with torch.cuda.device(value.device):
-            grad_value = torch.zeros(value.shape, dtype=torch.float32, device=value.device)
+            grad_value, ctx.grad_value_buf = ctx.grad_value_buf, None   # used once
+            if grad_value is None:
+                grad_value = torch.zeros(value.shape, dtype=torch.float32, device=value.device)
             grad_offsets = torch.empty_like(offsets)
             grad_logits = torch.empty_like(logits)
             grad_loc = torch.empty_like(offsets) if (need_ref or need_scale) else None
             status = lib.msda_fused_backward(
                 value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
                 offsets.data_ptr(), logits.data_ptr(), ref_points.data_ptr(),
-                None if scale is None else scale.data_ptr(), stats.data_ptr(),
+                None if scale is None else scale.data_ptr(), stats.data_ptr(), out.data_ptr(),
                 grad_output.contiguous().data_ptr(), grad_value.data_ptr(),
                 grad_offsets.data_ptr(), grad_logits.data_ptr(),
                 None if grad_loc is None else grad_loc.data_ptr(),

@@ -44,6 +44,8 @@ import torch.nn.functional as F
 
 REF = sys.argv[1] if len(sys.argv) > 1 else '/root/reference'
 OUT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, OUT)
+import recipe256  # noqa: E402  (seeded parameters / inputs of the production-geometry cases)
 MSDA_PY = os.path.join(REF, 'third_party/mmcv/mmcv/ops/multi_scale_deform_attn.py')
 OT_PY = os.path.join(REF, 'opera/models/utils/transformer.py')
 
@@ -393,7 +395,67 @@ def gen_module_golden():
     print('module_golden.npz: %d arrays' % len(store))
 
 
+def gen_module_golden_256():
+    """The six module classes at PAVE-Net's PRODUCTION geometry — embed_dims 256, 8 heads
+    (32 channels per head), 4 levels, P = 4 / 15 / 17
+    (configs/videopose/2025-2-13/2025_2_13_res50_num_frames_3_posetrack17.py:53-107) — forward
+    AND backward (torch autograd through the reference classes).  Parameters and inputs are
+    NOT stored: tests/golden/recipe256.py regenerates them from seeds (the state dicts alone
+    would be ~20 MB); what is stored is the reference's output, the gradients of the inputs,
+    the bias gradients, and two seeded random projections of every weight gradient
+    (u^T dW and dW v), plus a checksum of the regenerated tensors."""
+    store = {}
+    ns_m = module_namespace()
+    for _, src in extract(MSDA_PY, [
+            'MultiScaleDeformableAttention',
+            'MulFramesMultiScaleDeformableAttentionNumFrames3',
+            'MulFramesMultiScaleDeformableAttentionNumFrames5']).items():
+        exec(src, ns_m)
+    ns_o = module_namespace()
+    for _, src in extract(OT_PY, [
+            'MultiScaleDeformablePoseAttention',
+            'MulFramesMultiScaleDeformablePoseAttentionNumFrames3',
+            'MulFramesMultiScaleDeformablePoseAttentionNumFrames5']).items():
+        exec(src, ns_o)
+    namespaces = {'msda': ns_m, 'ot': ns_o}
+    for case in recipe256.CASES:
+        cls = namespaces[case['where']][case['cls']]
+        mod = cls(dropout=0.0, **case['cfg']).eval()
+        if hasattr(mod, 'vis_attention'):
+            mod.vis_attention = lambda *a, **k: None   # debug code, transformer.py:1817-1830
+        recipe256.randomise(mod, case['param_seed'])
+        inp = recipe256.make_inputs(case)
+        leaves = {k: v.clone().requires_grad_(True) for k, v in inp.items()
+                  if k in ('query', 'value', 'query_pos')}
+        value = leaves.get('value')
+        if value is not None and case.get('cuda_like'):
+            value = value.as_subclass(_CudaLike)
+        out = mod(leaves['query'], None, value, query_pos=leaves.get('query_pos'),
+                  key_padding_mask=inp.get('key_padding_mask'),
+                  reference_points=inp['reference_points'], spatial_shapes=inp['spatial_shapes'],
+                  level_start_index=lsi_of(inp['spatial_shapes']))
+        out = out.as_subclass(torch.Tensor)
+        grad_out = recipe256.grad_output(case, out.shape)
+        out.backward(grad_out)
+        name = case['name']
+        store[name + '.out'] = out.detach().numpy()
+        for k, v in leaves.items():
+            store['%s.grad_in.%s' % (name, k)] = v.grad.as_subclass(torch.Tensor).numpy()
+        for pname, p in sorted(mod.named_parameters()):
+            g = p.grad
+            if g.dim() == 1:
+                store['%s.grad_param.%s' % (name, pname)] = g.numpy()
+            else:
+                u, v = recipe256.projection_vectors(case, pname, g.shape)
+                store['%s.grad_param_u.%s' % (name, pname)] = (u @ g).numpy()
+                store['%s.grad_param_v.%s' % (name, pname)] = (g @ v).numpy()
+        store[name + '.checksum'] = recipe256.checksum(mod, inp).numpy()
+    np.savez_compressed(os.path.join(OUT, 'module_golden_256.npz'), **store)
+    print('module_golden_256.npz: %d arrays' % len(store))
+
+
 if __name__ == '__main__':
     torch.set_num_threads(4)
     gen_op_golden()
     gen_module_golden()
+    gen_module_golden_256()

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), 'missing export: ' + name
     assert sorted(_capi.EXPORTED_SYMBOLS) == declared
-    assert lib.msda_abi_version() == 1
+    assert lib.msda_abi_version() == 2
 
 
 def test_library_has_sm100a_code():

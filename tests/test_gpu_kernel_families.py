@@ -1,0 +1,220 @@
+"""GPU parity of every kernel FAMILY behind the dispatcher, each forced through
+`msda_set_option` and checked against the C oracle, with the library's per-family launch
+counters asserting that the family under test is the one that ran (a silent fallback to
+another kernel would otherwise pass).
+
+Families (include/pavenet_msda.h, msda_launch_count_family): rows (large Q), flat (small Q:
+persistent grid over flattened (row, 32-sample chunk) space), generic (any D / fp64), each
+forward + backward, plain and fused-prologue.
+Tolerances: fp32 outputs <= 1e-4, gradients <= 1e-3 (max|a-b| / max|b|), as BASELINE.json.
+"""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import msda_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+MID = [(28, 40), (14, 20), (7, 10), (4, 5)]
+
+
+@pytest.fixture()
+def lib_options():
+    """Set kernel-selection knobs for one test and restore the defaults afterwards."""
+    from pavenet_b200 import _capi
+    touched = []
+
+    def set_(name, value):
+        touched.append(name)
+        _capi.set_option(name, value)
+
+    yield set_
+    defaults = {'flat': 1, 'force_generic': 0, 'fwd_split': 0, 'bwd_split': 0,
+                'bwd_variant': 0, 'fwd_variant': 0}
+    for name in touched:
+        _capi.set_option(name, defaults[name])
+
+
+def _problem(seed, B, Q, M, D, P, shapes, spread=0.15):
+    g = torch.Generator().manual_seed(seed)
+    shapes_t = torch.tensor(shapes, dtype=torch.long)
+    L = len(shapes)
+    S = int(shapes_t.prod(1).sum())
+    value = torch.randn(B, S, M, D, generator=g)
+    loc = torch.rand(B, Q, M, L, P, 2, generator=g) * (1 + 2 * spread) - spread
+    aw = torch.softmax(torch.randn(B, Q, M, L * P, generator=g), -1).view(B, Q, M, L, P)
+    go = torch.randn(B, Q, M * D, generator=g)
+    return value, shapes_t, O.level_start_index(shapes_t), loc, aw, go
+
+
+def _run(value, shapes, lsi, loc, aw, go, value_dtype=torch.float32):
+    import pavenet_b200
+    fn = pavenet_b200.MultiScaleDeformableAttnFunction.apply
+    v = value.cuda().to(value_dtype).requires_grad_()
+    l = loc.cuda().requires_grad_()
+    a = aw.cuda().requires_grad_()
+    out = fn(v, shapes.cuda(), lsi.cuda(), l, a, 64)
+    out.backward(go.cuda())
+    return out.detach(), v.grad, l.grad, a.grad
+
+
+def _delta(before, after):
+    return {k: after[k] - before[k] for k in after if after[k] != before[k]}
+
+
+FLAT_SHAPES = [
+    # B, Q, M, D, P, levels
+    (1, 300, 8, 32, 17, MID),            # PETR pose attention: L*P = 68 (2 chunks + 4 samples)
+    (1, 60, 8, 32, 17, MID * 5),         # T=5 fused pose decoder: L*P = 340
+    (2, 37, 8, 32, 15, MID * 3),         # T=3: L*P = 180
+    (1, 5, 2, 32, 3, MID),               # L*P = 12: one partial chunk per row
+    (2, 9, 3, 32, 8, MID),               # L*P = 32: exactly one chunk
+    (1, 2500, 8, 32, 4, MID),            # many rows, 16 samples: more chunks than warps
+    (1, 40, 4, 16, 9, MID),              # D = 16
+    (1, 33, 2, 64, 11, MID[1:]),         # D = 64
+    (3, 1, 1, 32, 1, [(1, 1)]),          # degenerate
+]
+
+
+@pytest.mark.parametrize('B,Q,M,D,P,shapes', FLAT_SHAPES)
+def test_flat_kernels_match_oracle(lib_options, B, Q, M, D, P, shapes):
+    from pavenet_b200 import _capi
+    lib_options('flat', 2)
+    prob = _problem(7 * Q + D, B, Q, M, D, P, shapes)
+    before = _capi.family_counts()
+    out, gv, gl, ga = _run(*prob)
+    ran = _delta(before, _capi.family_counts())
+    assert ran == {'fwd_flat': 1, 'bwd_flat': 1}, ran
+    value, shapes_t, lsi, loc, aw, go = prob
+    ref = O.c_forward(value, shapes_t, lsi, loc, aw)
+    rgv, rgl, rga = O.c_backward(value, shapes_t, lsi, loc, aw, go)
+    assert rel_err(out, ref) < 1e-4 and rel_err(out, ref) < 5e-6
+    assert rel_err(gv, rgv) < 1e-3
+    assert rel_err(gl, rgl) < 1e-3 and rel_err(gl, rgl) < 5e-5
+    assert rel_err(ga, rga) < 1e-3
+
+
+@pytest.mark.parametrize('B,Q,M,D,P,shapes', FLAT_SHAPES[:4] + FLAT_SHAPES[6:8])
+def test_rows_kernels_forced_on_the_same_shapes(lib_options, B, Q, M, D, P, shapes):
+    from pavenet_b200 import _capi
+    lib_options('flat', 0)
+    prob = _problem(7 * Q + D, B, Q, M, D, P, shapes)
+    before = _capi.family_counts()
+    out, gv, gl, ga = _run(*prob)
+    ran = _delta(before, _capi.family_counts())
+    assert ran == {'fwd_rows': 1, 'bwd_rows': 1}, ran
+    value, shapes_t, lsi, loc, aw, go = prob
+    assert rel_err(out, O.c_forward(value, shapes_t, lsi, loc, aw)) < 5e-6
+    rgv, rgl, rga = O.c_backward(value, shapes_t, lsi, loc, aw, go)
+    assert rel_err(gv, rgv) < 1e-3 and rel_err(gl, rgl) < 5e-5 and rel_err(ga, rga) < 1e-3
+
+
+@pytest.mark.parametrize('D,Q,P', [(32, 300, 17), (16, 120, 9), (64, 50, 11)])
+def test_flat_kernels_bf16_value(lib_options, D, Q, P):
+    """bf16 value storage through the flat family: against the oracle run on the same
+    rounded value (tight), fp32 gradient accumulation."""
+    from pavenet_b200 import _capi
+    lib_options('flat', 2)
+    value, shapes_t, lsi, loc, aw, go = _problem(11 + D, 1, Q, 4, D, P, MID)
+    v16 = value.to(torch.bfloat16)
+    before = _capi.family_counts()
+    out, gv, gl, ga = _run(v16.float(), shapes_t, lsi, loc, aw, go, value_dtype=torch.bfloat16)
+    assert _delta(before, _capi.family_counts()) == {'fwd_flat': 1, 'bwd_flat': 1}
+    ref = O.c_forward(v16.float(), shapes_t, lsi, loc, aw)
+    rgv, rgl, rga = O.c_backward(v16.float(), shapes_t, lsi, loc, aw, go)
+    assert rel_err(out, ref) < 2e-5
+    assert rel_err(gl, rgl) < 1e-3 and rel_err(ga, rga) < 1e-3
+    assert gv.dtype == torch.bfloat16 and rel_err(gv.float(), rgv) < 4e-3   # one rounding to bf16
+
+
+def test_forward_clear_zero_fills_the_buffer(lib_options):
+    """msda_forward_clear: the buffer handed to the forward comes back all zeros, for the flat
+    family (fill folded into the kernel) and the rows family (memset), any size / tail."""
+    from pavenet_b200.functional import ms_deform_attn_forward
+    value, shapes_t, lsi, loc, aw, _ = _problem(3, 1, 60, 8, 32, 17, MID * 2)
+    args = (value.cuda(), shapes_t.cuda(), lsi.cuda(), loc.cuda(), aw.cuda())
+    ref = O.c_forward(value, shapes_t, lsi, loc, aw)
+    for flat in (2, 0):
+        lib_options('flat', flat)
+        for n in (4, 1024, 4 * 1000 * 1000 + 4, 12345 * 4):
+            buf = torch.full((n,), 3.0, device='cuda')
+            guard = torch.full((64,), 5.0, device='cuda')
+            out = ms_deform_attn_forward(*args, 64, clear=buf)
+            assert float(buf.abs().max()) == 0.0, (flat, n)
+            assert float(guard.min()) == 5.0
+            assert rel_err(out, ref) < 5e-6
+
+
+def test_function_reuses_the_cleared_buffer_once():
+    """The autograd Function zero-fills grad_value during the forward call; a second backward
+    through a retained graph must not reuse the dirty buffer."""
+    import pavenet_b200
+    fn = pavenet_b200.MultiScaleDeformableAttnFunction.apply
+    value, shapes_t, lsi, loc, aw, go = _problem(5, 1, 50, 8, 32, 17, MID)
+    v = value.cuda().requires_grad_()
+    out = fn(v, shapes_t.cuda(), lsi.cuda(), loc.cuda(), aw.cuda(), 64)
+    out.backward(go.cuda(), retain_graph=True)
+    g1 = v.grad.clone()
+    v.grad = None
+    out.backward(go.cuda())
+    assert rel_err(v.grad, g1) < 1e-6
+    rgv, _, _ = O.c_backward(value, shapes_t, lsi, loc, aw, go)
+    assert rel_err(g1, rgv) < 1e-3
+
+
+@pytest.mark.parametrize('flat', [2, 0])
+@pytest.mark.parametrize('Q,P,levels,R,with_scale', [
+    (40, 17, MID * 3, 17, True),      # pose decoder: one reference per point, box scale
+    (300, 4, MID, 1, False),          # encoder style: one reference per level, / (W, H)
+    (7, 15, MID * 5, 15, True),
+])
+def test_fused_kernels_match_unfused_chain(lib_options, flat, Q, P, levels, R, with_scale):
+    """softmax + location transform in the kernel (flat and rows families) against the
+    op-by-op chain run through autograd on the plain op, all gradients."""
+    import pavenet_b200
+    from pavenet_b200 import _capi
+    from pavenet_b200.functional import FusedMultiScaleDeformableAttnFunction
+    lib_options('flat', flat)
+    g = torch.Generator().manual_seed(Q + P)
+    shapes_t = torch.tensor(levels, dtype=torch.long)
+    L, B, M, D = len(levels), 2, 8, 32
+    S = int(shapes_t.prod(1).sum())
+    lsi = O.level_start_index(shapes_t)
+    dev = 'cuda'
+    value = torch.randn(B, S, M, D, generator=g).to(dev)
+    off = (torch.randn(B, Q, M, L, P, 2, generator=g) * (0.1 if with_scale else 2.0)).to(dev)
+    logit = torch.randn(B, Q, M, L * P, generator=g).to(dev)
+    ref = torch.rand(B, Q, L, R, 2, generator=g).to(dev)
+    scale = (torch.rand(B, Q, L, 2, generator=g) * 0.5).to(dev) if with_scale else None
+    go = torch.randn(B, Q, M * D, generator=g).to(dev)
+
+    def leaves():
+        return [t.detach().clone().requires_grad_() if t is not None else None
+                for t in (value, off, logit, ref, scale)]
+
+    v, o, lg, r, sc = leaves()
+    before = _capi.family_counts()
+    out = FusedMultiScaleDeformableAttnFunction.apply(v, shapes_t.to(dev), lsi.to(dev), o, lg, r, sc)
+    out.backward(go)
+    ran = _delta(before, _capi.family_counts())
+    fam = 'flat' if flat == 2 else 'rows'
+    assert ran == {'fwd_%s_fused' % fam: 1, 'bwd_%s_fused' % fam: 1}, ran
+
+    v2, o2, lg2, r2, sc2 = leaves()
+    w = torch.softmax(lg2, -1).view(B, Q, M, L, P)
+    if sc2 is not None:
+        loc = r2[:, :, None] + o2 * sc2[:, :, None, :, None, :]
+    else:
+        norm = torch.stack([shapes_t[:, 1], shapes_t[:, 0]], -1).float().to(dev)
+        loc = r2[:, :, None] + o2 / norm[None, None, None, :, None, :]
+    out2 = pavenet_b200.MultiScaleDeformableAttnFunction.apply(
+        v2, shapes_t.to(dev), lsi.to(dev), loc.contiguous(), w.contiguous(), 64)
+    out2.backward(go)
+    assert rel_err(out, out2) < 1e-5
+    assert rel_err(v.grad, v2.grad) < 2e-4
+    assert rel_err(o.grad, o2.grad) < 2e-4
+    assert rel_err(lg.grad, lg2.grad) < 2e-4
+    assert rel_err(r.grad, r2.grad) < 2e-4
+    if sc is not None:
+        assert rel_err(sc.grad, sc2.grad) < 2e-4

@@ -578,6 +578,12 @@ def test_fused_function_matches_unfused_chain(Q, P, shapes, R, with_scale):
     out.backward(go.cuda())
     assert rel_err(out, ref_out) < FWD_TOL_F32
     for a, b, name in zip(cu, leaves, ('value', 'offsets', 'logits', 'ref_points')):
+        if name == 'logits' and float(b.grad.abs().max()) == 0.0:
+            # one sample per row: softmax over one logit has an identically zero gradient; the
+            # kernel forms it as w * (gw - <grad_out, out>), two fp32 roundings of the same number
+            scale_gw = float(go.abs().max() * value.abs().max()) * value.shape[-1]
+            assert float(a.grad.abs().max()) < 1e-5 * scale_gw, name
+            continue
         assert rel_err(a.grad, b.grad) < BWD_TOL_F32, name
     if scale is not None:
         assert rel_err(sc_cu.grad, sc.grad) < BWD_TOL_F32
@@ -1037,7 +1043,7 @@ def test_loaded_library_is_in_tree():
         torch.rand(1, 1, 1, 1, 1, 2, device='cuda'), torch.rand(1, 1, 1, 1, 1, device='cuda'))
     assert pavenet_b200._capi.launch_count() == before + 1
     assert os.path.dirname(pavenet_b200._build.LIB_PATH).endswith(os.path.join('pavenet_b200', 'lib'))
-    assert lib.msda_abi_version() == 1
+    assert lib.msda_abi_version() == 2
 
 
 @pytest.mark.parametrize('shape', [(1, 256), (7, 3, 256), (3, 22223, 256), (300, 1, 256)])

@@ -188,17 +188,18 @@ def test_c_oracle_structural_properties():
                     reason='needs the read-only reference checkout (build container only)')
 def test_golden_fixtures_regenerate_from_the_reference(tmp_path):
     """The committed fixtures ARE the reference's outputs: re-running the generator against the
-    reference checkout (where it exists) reproduces both .npz files bit for bit."""
+    reference checkout (where it exists) reproduces all three .npz files bit for bit."""
     import shutil
     import subprocess
     import sys
     import numpy as np
     here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
     script = shutil.copy(os.path.join(here, 'gen_golden.py'), str(tmp_path))
+    shutil.copy(os.path.join(here, 'recipe256.py'), str(tmp_path))
     proc = subprocess.run([sys.executable, script, '/root/reference'], capture_output=True, text=True,
                           timeout=900, cwd=str(tmp_path))
     assert proc.returncode == 0, proc.stderr[-2000:]
-    for name in ('op_golden.npz', 'module_golden.npz'):
+    for name in ('op_golden.npz', 'module_golden.npz', 'module_golden_256.npz'):
         new = np.load(os.path.join(str(tmp_path), name), allow_pickle=True)
         old = np.load(os.path.join(here, name), allow_pickle=True)
         assert sorted(new.files) == sorted(old.files)
