@@ -241,10 +241,10 @@ def cpu_reference_step(prob_cpu):
     return time.perf_counter() - t0
 
 
-def cpu_sample_problem(wl, frames=1, queries=None):
+def cpu_sample_problem(wl, frames=1, queries=None, seed=1234):
     """A bounded sample of the workload for the CPU legs: `frames` batch
     entries and (optionally) the first `queries` queries of each."""
-    prob = make_problem(wl, seed=1234, device='cpu', frames=frames)
+    prob = make_problem(wl, seed=seed, device='cpu', frames=frames)
     if queries is not None and queries < prob['dims']['Q']:
         for k in ('loc', 'aw', 'grad_out'):
             prob[k] = prob[k][:, :queries].contiguous()
@@ -302,42 +302,68 @@ def dist_setup(gpus):
     return world, rank, local
 
 
+def workload_config(wl, dims, sets, world):
+    """The `config` object of an op workload -- built by ONE function for both arms (ours and
+    --impl reference), so that the two lines describe the same job key for key."""
+    cfg = WORKLOADS[wl]
+    return {'workload': wl, 'description': cfg['desc'], 'dims': dict(dims),
+            'queries_per_step': dims['B'] * dims['Q'],
+            'l2_policy': 'inputs larger than L2: %d distinct clips rotated per step' % sets,
+            'parallelism': 'clip-sharded x%d, no data-path collective' % world}
+
+
 def run_reference_arm(args, world, rank):
     """--impl reference: the reference's CPU implementation of the path (the
     oracle port; the Python reference itself cannot travel to the GPU box),
-    all host threads, rank 0 only."""
+    all host threads, rank 0 only.
+
+    Same job as our arm: every step is one fwd+bwd over ALL batch entries and ALL queries of
+    the workload, `--sets` distinct clips rotated.  Only if that would take more than ~5 minutes
+    for steps + warmup on this host is a step cut down to a bounded sample (first batch
+    entries / first queries), and the line says so (`cpu_baseline.sample`)."""
     if rank != 0:
         return
-    use_all_host_threads()
+    cores = use_all_host_threads()
     wl = args.workload
     cfg = WORKLOADS[wl]
     full_q = sum(h * w for h, w in cfg['levels']) if cfg['kind'] == 'encoder' else cfg['Q']
-    # size the per-step sample so the whole run stays within ~2 minutes
+    full_b = args.frames or cfg['B']
     probe = cpu_sample_problem(wl, frames=1, queries=min(full_q, 2048))
-    t = cpu_reference_step(probe)
+    cpu_reference_step(probe)
+    t = min(cpu_reference_step(probe) for _ in range(2))
     per_query = t / probe['dims']['Q']
-    budget = 120.0 / max(1, args.steps + args.warmup)
-    q = int(max(32, min(full_q, budget / max(per_query, 1e-9))))
-    prob = cpu_sample_problem(wl, frames=1, queries=q)
-    for _ in range(args.warmup):
-        cpu_reference_step(prob)
+    n_steps = max(1, args.steps + args.warmup)
+    est_full = per_query * full_q * full_b * n_steps
+    if est_full <= 300.0:
+        frames, q = full_b, full_q
+    else:                                    # bounded sample: ~2 minutes in all
+        per_step = 120.0 / n_steps
+        frames = max(1, min(full_b, int(per_step / (per_query * full_q))))
+        q = full_q if frames > 1 or per_query * full_q <= per_step else \
+            int(max(32, per_step / per_query))
+    n_sets = max(1, min(args.sets, 4 if frames * q * 16 * 8 * 12 < 2e8 else 2))
+    probs = [cpu_sample_problem(wl, frames=frames, queries=q, seed=1234 + i) for i in range(n_sets)]
+    for i in range(args.warmup):
+        cpu_reference_step(probs[i % n_sets])
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_reference_step(prob)
+    for i in range(args.steps):
+        cpu_reference_step(probs[i % n_sets])
     dt = time.perf_counter() - t0
-    qps = q * args.steps / dt
-    sample = '1 batch entry x %d of %d queries per step' % (q, full_q)
+    q_step = frames * q
+    qps = q_step * args.steps / dt
+    full = frames == full_b and q == full_q
+    sample = ('the full workload: %d batch entries x %d queries per step' % (frames, q) if full else
+              'bounded sample: %d of %d batch entries x %d of %d queries per step'
+              % (frames, full_b, q, full_q))
+    dims = dict(probs[0]['dims'], B=full_b, Q=full_q)
     line = {
         'impl': 'reference', 'metric': 'deform-attn fwd+bwd queries/s', 'value': qps,
         'unit': 'queries/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': wl, 'description': cfg['desc'],
-                   'dims': dict(prob['dims'], B=cfg['B'], Q=full_q),      # the full workload ...
-                   'queries_per_step': cfg['B'] * full_q,
-                   'sample': sample,                                       # ... and what one CPU step covers
-                   'parallelism': 'host threads of rank 0 only'},
-        'cpu_baseline': {'value': qps, 'unit': 'queries/s', 'cores': torch.get_num_threads(),
+        'config': workload_config(wl, dims, args.sets, 1),
+        'same_job_as_ours': full, 'queries_timed_per_step': q_step,
+        'cpu_baseline': {'value': qps, 'unit': 'queries/s', 'cores': cores,
                          'kind': 'port', 'sample': sample},
         'e2e': {'value': qps, 'unit': 'queries/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
@@ -346,17 +372,16 @@ def run_reference_arm(args, world, rank):
     emit(json.dumps(line))
 
 
-def run_model_step(args, world, rank, local):
-    """BASELINE config 4: clip-sharded PAVE-Net R-50 training step (1 clip per
-    GPU as in the reference, configs/_base_/datasets/posetrack17_video_keypoint.py:88),
-    NCCL gradient all-reduce through DDP.  Metric: clips/s."""
+def measure_model_step(args, world, rank, local, steps, warmup):
+    """BASELINE config 4: clip-sharded PAVE-Net R-50 training step (1 clip per GPU as in the
+    reference, configs/_base_/datasets/posetrack17_video_keypoint.py:88): forward + backward +
+    NCCL gradient all-reduce (bucketed by stage and overlapped with the backward,
+    clip_model.FlatGradients) + grad-clip + AdamW.  The process group must exist already when
+    world > 1.  Returns the record on every rank (timings are max over ranks)."""
     import torch.distributed as dist
     from torch.nn.parallel import DistributedDataParallel as DDP
     from pavenet_b200 import _capi, clip_model, clip_sharding
-    torch.cuda.set_device(local)
     device = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=device)
     torch.manual_seed(0)
     vdt = None if args.value_dtype == 'f32' else torch.bfloat16
     model = clip_model.PaveNetR50(value_dtype=vdt).to(device).train()
@@ -370,12 +395,14 @@ def run_model_step(args, world, rank, local):
         if world > 1:                                  # same initial weights on every rank
             for p in model.parameters():
                 dist.broadcast(p.data, 0)
-        flat = clip_model.FlatGradients(model)
+        flat = clip_model.FlatGradients(model, overlap=args.grad_exchange == 'overlap')
     opt = clip_model.build_optimizer(model)
     clips_per_gpu = 1
     batches = [clip_model.synthetic_clip_batch(clips_per_gpu, device, seed=100 * rank + i)
                for i in range(2)]
-    for i in range(args.warmup):
+    # two alternating synthetic batches; a graphed stage captures a signature the second time
+    # it sees it, so every graph exists after 2 x 2 steps (+ the capture's own warm-up runs)
+    for i in range(max(warmup, 6)):
         clip_model.train_step(model, opt, *batches[i % 2], ddp_model=ddp, flat_grads=flat)
     torch.cuda.synchronize()
     if world > 1:
@@ -384,34 +411,102 @@ def run_model_step(args, world, rank, local):
     clocks.start()
     launches0 = _capi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    exposed = []
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         loss = clip_model.train_step(model, opt, *batches[i % 2], ddp_model=ddp, flat_grads=flat)
+        if flat is not None and flat.exposed_events is not None:
+            exposed.append(flat.exposed_events)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clock_info = clocks.stop()
     ms = clip_sharding.max_over_ranks(e0.elapsed_time(e1), device)
-    clips = clip_sharding.sum_over_ranks(clips_per_gpu * args.steps, device)
+    clips = clip_sharding.sum_over_ranks(clips_per_gpu * steps, device)
+    exposed_ms = (sum(a.elapsed_time(b) for a, b in exposed) / len(exposed)) if exposed else 0.0
+    exposed_ms = clip_sharding.max_over_ranks(exposed_ms, device)
+    n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    rec = {
+        'metric': 'PAVE-Net R-50 training clips/s', 'value': clips / (ms * 1e-3), 'unit': 'clips/s',
+        'n_gpus': world, 'steps': steps, 'warmup': max(warmup, 6), 'ms_per_step': ms / steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32 (TF32 convolutions, fp32 GEMMs)' + ('' if vdt is None else ', bf16 value storage'),
+        'data': 'synthetic',
+        'config': {'workload': 'pavenet_step', 'description': 'PAVE-Net R-50, T=3 frames at 800x1333, '
+                   '1 clip per GPU, forward + backward + gradient all-reduce (NCCL) + grad-clip + AdamW',
+                   'trainable_params': n_params, 'parallelism': 'clip-sharded data parallel x%d' % world,
+                   'cuda_graphs': bool(args.graphs), 'grad_exchange': args.grad_exchange,
+                   'l2_policy': 'inputs larger than L2 (activations of a 3x800x1333 clip)'},
+        'collective': {'backend': 'nccl' if world > 1 else None, 'ranks': world,
+                       'bytes_all_reduced_per_step': 4 * n_params if world > 1 else 0,
+                       'exposed_all_reduce_ms': exposed_ms,
+                       'buckets': None if flat is None else [b - a for a, b in flat.ranges]},
+        'clocks': clock_info, 'gpu_launches': int(_capi.launch_count() - launches0),
+        'final_loss': float(loss)}
+    del model, opt, flat, ddp, batches
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_model_step(args, world, rank, local):
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    rec = measure_model_step(args, world, rank, local, args.steps, args.warmup)
+    rec.update({'roofline': None, 'cpu_baseline': None, 'e2e': None})
     if rank == 0:
-        n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
-        emit(json.dumps({
-            'metric': 'PAVE-Net R-50 training clips/s', 'value': clips / (ms * 1e-3), 'unit': 'clips/s',
-            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32 (TF32 convolutions, fp32 GEMMs)' + ('' if vdt is None else ', bf16 value storage'),
-            'data': 'synthetic',
-            'config': {'workload': 'pavenet_step', 'description': 'PAVE-Net R-50, T=3 frames at 800x1333, '
-                       '1 clip per GPU, forward + backward + gradient all-reduce (NCCL) + grad-clip + AdamW',
-                       'trainable_params': n_params, 'parallelism': 'clip-sharded data parallel x%d' % world,
-                       'cuda_graphs': bool(args.graphs), 'grad_exchange': args.grad_exchange,
-                       'l2_policy': 'inputs larger than L2 (activations of a 3x800x1333 clip)'},
-            'roofline': None, 'cpu_baseline': None, 'e2e': None,
-            'clocks': clock_info, 'gpu_launches': int(_capi.launch_count() - launches0),
-            'final_loss': float(loss)}))
+        emit(json.dumps(rec))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_gpu_baseline(probs, bufs, dims, q_per_step, steps):
+    """The reference's own CUDA kernels (ms_deform_attn_cuda_kernel.cuh recompiled for sm_100a,
+    oracle/_ref/libmsda_refcuda.so) on the same device tensors, launched as the reference's host
+    code launches them; the zero-fills its Python wrapper performs (output, three gradients,
+    multi_scale_deform_attn.py:72-74, ms_deform_attn_cuda.cu:247) are timed as their own item."""
+    from oracle import msda_oracle as O
+    if not O.refcuda_available():
+        return {'unavailable': 'oracle/_ref/libmsda_refcuda.so not built (make -C oracle refcuda, '
+                               'needs the reference checkout)'}
+    outs = [torch.empty((dims['B'], dims['Q'], dims['M'] * dims['D']), device=p['value'].device)
+            for p in probs]
+
+    def step(i, ev=None):
+        p, b, o = probs[i % len(probs)], bufs[i % len(probs)], outs[i % len(probs)]
+        if ev:
+            ev[0].record()
+        O.refcuda_forward(p['value'], p['shapes'], p['lsi'], p['loc'], p['aw'], out=o)
+        if ev:
+            ev[1].record()
+        b['grad_value'].zero_()
+        b['grad_loc'].zero_()
+        b['grad_aw'].zero_()
+        if ev:
+            ev[2].record()
+        O.refcuda_backward(p['value'], p['shapes'], p['lsi'], p['loc'], p['aw'], p['grad_out'],
+                           b['grad_value'], b['grad_loc'], b['grad_aw'])
+        if ev:
+            ev[3].record()
+
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    for i in range(steps):
+        step(i, evs[i])
+    torch.cuda.synchronize()
+    fwd = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
+    zero = sum(e[1].elapsed_time(e[2]) for e in evs) / steps
+    bwd = sum(e[2].elapsed_time(e[3]) for e in evs) / steps
+    total = evs[0][0].elapsed_time(evs[-1][3]) / steps
+    return {'kind': 'reference CUDA kernels (ms_deform_attn_cuda_kernel.cuh) recompiled for sm_100a, '
+                    'same tensors, same GPU',
+            'kernel_ms': {'fwd': fwd, 'grad_zero_fill': zero, 'bwd': bwd},
+            'ms_per_step': total, 'value': q_per_step / (total * 1e-3), 'unit': 'queries/s',
+            'steps': steps}
 
 
 def load_peak():
@@ -444,10 +539,18 @@ def main():
     ap.add_argument('--workload', default='encoder_cfg2',
                     choices=sorted(WORKLOADS) + list(MODEL_WORKLOADS))
     ap.add_argument('--value-dtype', default='f32', choices=['f32', 'bf16'])
-    ap.add_argument('--grad-exchange', default='flat', choices=['flat', 'ddp'], help='pavenet_step: one all-reduce of a flat gradient bucket, or torch DDP')
+    ap.add_argument('--grad-exchange', default='overlap', choices=['overlap', 'flat', 'ddp'],
+                    help='pavenet_step: stage buckets all-reduced underneath the backward (default), one all-reduce '
+                         'of the flat gradient buffer after the backward, or torch DDP')
+    ap.add_argument('--model-steps', type=int, default=-1,
+                    help='op workloads: also time this many steps of the clip-sharded PAVE-Net R-50 training step '
+                         '(BASELINE config 4, NCCL gradient all-reduce) and append it as `pavenet_step`; '
+                         '-1 = 10 for the default workload, 0 for the others; 0 = skip')
     ap.add_argument('--graphs', type=int, default=1, help='pavenet_step: run backbone, encoder and pose decoder as CUDA graphs (fwd + bwd)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-gpu-baseline', action='store_true',
+                    help='skip timing the reference CUDA kernels (oracle/_ref/libmsda_refcuda.so)')
     ap.add_argument('--sets', type=int, default=4, help='distinct input sets rotated per step')
     ap.add_argument('--frames', type=int, default=0, help='override the batch entries (frames) per step of an op workload: the batch sweep of BASELINE config 5')
     ap.add_argument('--fused', action='store_true', help='time the fused-prologue kernels (offsets/logits in, softmax + location transform in-kernel) on the same problem')
@@ -673,6 +776,20 @@ def main():
         e2e_autograd['api'] = ('MultiScaleDeformableAttnFunction.apply + backward, pinned host '
                                'tensors, one stream (no overlap)')
 
+    # ---- the reference's own CUDA kernels on the same tensors (oracle/_ref, bench infrastructure) ----
+    gpu_baseline = None
+    if rank == 0 and not args.no_gpu_baseline and vdt == torch.float32:
+        gpu_baseline = measure_gpu_baseline(probs, bufs, dims, q_per_step, min(args.steps, 50))
+
+    # ---- BASELINE config 4 in the same run: the clip-sharded training step, NCCL all-reduce on ----
+    model_step = None
+    n_model = args.model_steps if args.model_steps >= 0 else (10 if wl == 'encoder_cfg2' and not args.fused else 0)
+    if n_model > 0:
+        try:
+            model_step = measure_model_step(args, world, rank, local, n_model, 6)
+        except Exception as exc:  # noqa: BLE001 - the op line must still be printed
+            model_step = {'error': '%s: %s' % (type(exc).__name__, exc)}
+
     if rank == 0:
         peak, peak_src = load_peak()
         vb = 4 if vdt == torch.float32 else 2
@@ -711,11 +828,9 @@ def main():
             'ms_per_step': elapsed_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32' if vdt == torch.float32 else 'f32 (bf16 value storage)',
             'data': 'synthetic',
-            'config': {'workload': wl, 'description': cfg['desc'], 'dims': dims,
-                       'queries_per_step': q_per_step, 'kernel': kname + (' + fused prologue' if args.fused else ''),
-                       'l2_policy': 'inputs larger than L2: %d distinct clips rotated per step, '
-                                    '%.2f GB footprint per GPU' % (args.sets, footprint / 1e9),
-                       'parallelism': 'clip-sharded x%d, no data-path collective' % world},
+            'config': workload_config(wl, dims, args.sets, world),
+            'kernel': kname + (' + fused prologue' if args.fused else ''),
+            'footprint_gb_per_gpu': footprint / 1e9,
             'roofline': roof(ab['bwd'], bwd_ms, 'msda_bwd_rows_kernel'),
             'roofline_fwd': roof(ab['fwd'], fwd_ms, 'msda_fwd_rows_kernel'),
             'roofline_step': roof(ab['fwd'] + ab['bwd'], fwd_ms + zero_ms + bwd_ms, 'step'),
@@ -729,7 +844,14 @@ def main():
             'options': args.option,
             'clocks': clock_info, 'gpu_launches': int(launches), 'e2e': e2e,
             'e2e_autograd': e2e_autograd,
+            'gpu_baseline': gpu_baseline,
+            'pavenet_step': model_step,
         }
+        if gpu_baseline:
+            gpu_baseline['speedup'] = {
+                'fwd': gpu_baseline['kernel_ms']['fwd'] / fwd_ms,
+                'bwd': gpu_baseline['kernel_ms']['bwd'] / bwd_ms,
+                'step': gpu_baseline['ms_per_step'] / (fwd_ms + zero_ms + bwd_ms)}
         if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N = 1 only
             line['cpu_baseline'] = measure_cpu_baseline(wl)
         emit(json.dumps(line))

@@ -283,3 +283,81 @@ def mulframes_joint_attention_ref(state, cfg, query, value, identity=None, query
     z_all = sum(zs)
     fused = sum(o * (z / z_all) for o, z in zip(outs, zs)).flatten(-2)
     return _lin(state, 'output_proj', fused).permute(1, 0, 2) + identity
+
+
+# ---------------------------------------------------------------------------
+# the REFERENCE's own CUDA kernels (oracle/_ref/libmsda_refcuda.so)
+# ---------------------------------------------------------------------------
+_REFCUDA_PATH = os.path.join(_HERE, '_ref', 'libmsda_refcuda.so')
+_refcuda = None
+
+
+def build_refcuda(reference='/root/reference', force=False):
+    """Compile the reference's `ms_deform_attn_cuda_kernel.cuh` (from the reference checkout,
+    nothing copied) behind `refcuda_driver.cu` into oracle/_ref/.  Build container only; on
+    the GPU box the prebuilt library travels with the snapshot.  Returns the path or None when
+    there is no reference checkout."""
+    hdr = os.path.join(reference, 'third_party/mmcv/mmcv/ops/csrc/common/cuda/'
+                                  'ms_deform_attn_cuda_kernel.cuh')
+    if not os.path.exists(hdr):
+        return _REFCUDA_PATH if os.path.exists(_REFCUDA_PATH) else None
+    drv = os.path.join(_HERE, 'refcuda_driver.cu')
+    if (not force and os.path.exists(_REFCUDA_PATH)
+            and os.path.getmtime(_REFCUDA_PATH) >= os.path.getmtime(drv)):
+        return _REFCUDA_PATH
+    proc = subprocess.run(['make', '-C', _HERE, '-B', 'refcuda', 'REF=' + reference],
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError('building the reference CUDA kernels failed:\n' + proc.stdout)
+    return _REFCUDA_PATH
+
+
+def refcuda_available():
+    return os.path.exists(_REFCUDA_PATH)
+
+
+def _load_refcuda():
+    global _refcuda
+    if _refcuda is None:
+        lib = ctypes.CDLL(_REFCUDA_PATH)
+        lib.refcuda_forward.restype = ctypes.c_int
+        lib.refcuda_forward.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int] * 8 + [ctypes.c_void_p]
+        lib.refcuda_backward.restype = ctypes.c_int
+        lib.refcuda_backward.argtypes = [ctypes.c_void_p] * 9 + [ctypes.c_int] * 8 + [ctypes.c_void_p]
+        _refcuda = lib
+    return _refcuda
+
+
+def _refcuda_dims(value, loc):
+    B, S, M, D = value.shape
+    _, Q, _, L, P, _ = loc.shape
+    code = {torch.float32: 0, torch.float64: 1}[value.dtype]
+    return (B, S, M, D, L, Q, P, code)
+
+
+def refcuda_forward(value, shapes, lsi, loc, aw, out=None):
+    """The reference's forward kernel (ms_deformable_im2col_gpu_kernel) on CUDA tensors,
+    launched as the reference's host code does; enqueued on torch's current stream."""
+    lib = _load_refcuda()
+    B, S, M, D, L, Q, P, code = _refcuda_dims(value, loc)
+    if out is None:
+        out = torch.empty((B, Q, M * D), dtype=value.dtype, device=value.device)
+    rc = lib.refcuda_forward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), loc.data_ptr(),
+                             aw.data_ptr(), out.data_ptr(), B, S, M, D, L, Q, P, code,
+                             torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise RuntimeError('refcuda_forward: CUDA error %d' % -rc)
+    return out
+
+
+def refcuda_backward(value, shapes, lsi, loc, aw, grad_out, grad_value, grad_loc, grad_aw):
+    """The reference's backward kernel (ms_deformable_col2im_gpu_kernel_*, picked by channel count
+    as ms_deform_attn_cuda.cu:63-206 does); ACCUMULATES into all three caller-zeroed gradients."""
+    lib = _load_refcuda()
+    B, S, M, D, L, Q, P, code = _refcuda_dims(value, loc)
+    rc = lib.refcuda_backward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), loc.data_ptr(),
+                              aw.data_ptr(), grad_out.data_ptr(), grad_value.data_ptr(),
+                              grad_loc.data_ptr(), grad_aw.data_ptr(), B, S, M, D, L, Q, P, code,
+                              torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise RuntimeError('refcuda_backward: CUDA error %d' % -rc)

@@ -383,9 +383,39 @@ class PaveNetR50(nn.Module):
             backbone=graphs.GraphedStage(self._stage_backbone, mods_backbone),
             encoder=graphs.GraphedStage(self._stage_encoder, [self.encoder], [self.level_embeds]),
             decoder=graphs.GraphedStage(self._stage_decoder, mods_decoder),
+            # keyed on the per-clip matched-person counts (data dependent): capture a count pattern
+            # only when it comes back, keep a handful of graphs, run eagerly otherwise
             joint=graphs.GraphedStage(self._stage_joint, [self.refine_decoder, self.refine_kpt, self.refine_sigma,
-                                                          self.refine_query_embedding]))
+                                                          self.refine_query_embedding],
+                                      max_graphs=6, capture_after=2))
         return self
+
+    #: set by FlatGradients(model, overlap=True): gradient buckets are all-reduced from autograd
+    #: hooks as the backward pass completes them
+    grad_exchange = None
+
+    def gradient_buckets(self):
+        """Trainable parameters in the order the backward pass completes their gradients:
+        [everything after the encoder (pose decoder, heads, joint decoder) | encoder | backbone]."""
+        backbone = [self.stem, self.layer1, self.layer2, self.layer3, self.layer4, self.lateral, self.extra]
+        in_backbone = {id(p) for m in backbone for p in m.parameters()}
+        in_encoder = {id(p) for p in self.encoder.parameters()} | {id(self.level_embeds)}
+        late, enc, back = [], [], []
+        for p in self.parameters():
+            if not p.requires_grad:
+                continue
+            (back if id(p) in in_backbone else enc if id(p) in in_encoder else late).append(p)
+        return [late, enc, back]
+
+    def _exchange_hook(self, tensor, n_buckets):
+        """When the gradient of `tensor` (a stage boundary) is ready, the stages behind it have
+        finished their backward: their gradient buckets can go out."""
+        ex = self.grad_exchange
+        if ex is not None and tensor.requires_grad and torch.is_grad_enabled():
+            def hook(grad, ex=ex, n=n_buckets):
+                ex.launch_through(n)
+                return None
+            tensor.register_hook(hook)
 
     def _run_stage(self, name, fn, *args):
         graphed = getattr(self, '_graphed', None)
@@ -404,8 +434,10 @@ class PaveNetR50(nn.Module):
             raise RuntimeError('backbone produced %r, expected %r'
                                % ([tuple(f.shape[-2:]) for f in feats], geo['shapes_list']))
         self._mark('backbone+neck')
+        self._exchange_hook(feats[0], 2)       # backward reaches the backbone: decoders + encoder done
         x = self._run_stage('encoder', self._stage_encoder, *feats, *geo['pos_sine'], mask_flat,
                             geo['ref_enc'], shapes, lsi)
+        self._exchange_hook(x, 1)              # backward reaches the encoder: decoders done
         memory = x.transpose(0, 1)             # (S, Bc*T, 256) view: what the decoders' modules take
         self._mark('encoder')
         outs = self._run_stage('decoder', self._stage_decoder, x, geo['proposals'], mask_flat, shapes, lsi)
@@ -614,28 +646,81 @@ def synthetic_clip_batch(clips, device, seed, height=800, width=1333, num_frames
 
 
 class FlatGradients(object):
-    """Every trainable parameter's .grad is a view into ONE flat fp32 buffer, so the clip-sharded
-    step needs a single NCCL all-reduce (190 MB over NVLink, ~1 ms) after backward instead of
-    DDP's hooks and buckets -- which also keeps the step compatible with the CUDA-graphed stages
-    (autograd accumulates into the views in place; nothing is registered on the parameters).
-    The reference's equivalent is MMDistributedDataParallel (opera/apis/train.py:153-162)."""
+    """Every trainable parameter's .grad is a view into ONE flat fp32 buffer, laid out in the
+    order in which the backward pass completes the gradients: [joint decoder + pose decoder +
+    heads | encoder | backbone].  The clip-sharded step exchanges the buffer bucket by bucket
+    with NCCL all-reduces on a side stream, each launched from an autograd hook the moment the
+    stage before it (in backward order) has finished, so the exchange of the decoders' and the
+    encoder's gradients runs underneath the encoder's / backbone's backward and only the last
+    bucket is exposed.  No hooks or buckets on the parameters themselves, which keeps the step
+    compatible with the CUDA-graphed stages (autograd accumulates into the views in place).
+    The reference's equivalent is MMDistributedDataParallel, i.e. torch DDP's bucketed,
+    backward-overlapped all-reduce (opera/apis/train.py:153-162,
+    third_party/mmcv/mmcv/parallel/distributed.py:11-85)."""
 
-    def __init__(self, model):
-        self.params = [p for p in model.parameters() if p.requires_grad]
+    def __init__(self, model, overlap=True):
+        buckets = model.gradient_buckets() if hasattr(model, 'gradient_buckets') else \
+            [[p for p in model.parameters() if p.requires_grad]]
+        self.params = [p for b in buckets for p in b]
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=self.params[0].dtype, device=self.params[0].device)
-        offset = 0
-        for p in self.params:
-            p.grad = self.flat[offset:offset + p.numel()].view_as(p)
-            offset += p.numel()
+        offset, self.ranges = 0, []
+        for b in buckets:
+            start = offset
+            for p in b:
+                p.grad = self.flat[offset:offset + p.numel()].view_as(p)
+                offset += p.numel()
+            self.ranges.append((start, offset))
+        self.overlap = overlap
+        self._side = None
+        self._pending, self._launched = [], 0
+        self.exposed_events = None          # (start, end) CUDA events around the exposed wait of the last step
+        if overlap and hasattr(model, 'grad_exchange'):
+            model.grad_exchange = self
+
+    def _distributed(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
     def zero(self):
         self.flat.zero_()
+        self._pending, self._launched = [], 0
+
+    def launch_through(self, n_buckets):
+        """All-reduce (mean) buckets [launched, n_buckets) on the side stream, behind everything
+        the current stream has been given so far.  Called from the autograd hooks."""
+        if not (self.overlap and self._distributed()):
+            return
+        cur = torch.cuda.current_stream(self.flat.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.flat.device)
+        while self._launched < min(n_buckets, len(self.ranges)):
+            a, b = self.ranges[self._launched]
+            self._launched += 1
+            if b == a:
+                continue
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            self._side.wait_event(ready)
+            with torch.cuda.stream(self._side):
+                self._pending.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.AVG, async_op=True))
 
     def all_reduce_mean(self):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat)
-            self.flat.div_(dist.get_world_size())
+        """Finish the exchange: whatever has not been launched yet goes now (exposed), then the
+        current stream waits for the side stream."""
+        if not self._distributed():
+            return
+        dev = self.flat.device
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(torch.cuda.current_stream(dev))
+        if self.overlap:
+            self.launch_through(len(self.ranges))
+            for work in self._pending:
+                work.wait()                      # current stream waits for the collective
+            self._pending = []
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+        ev1.record(torch.cuda.current_stream(dev))
+        self.exposed_events = (ev0, ev1)
 
 
 def train_step(model, optimizer, images, gt_kpts, gt_areas, ddp_model=None, flat_grads=None):

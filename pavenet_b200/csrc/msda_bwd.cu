@@ -27,11 +27,42 @@ namespace msda {
 constexpr int kRowsThreads = 256;
 constexpr int kRowsWarps = kRowsThreads / 32;
 
-template <int D, typename VT, typename GT, class IO>
+// "Warp-aggregated atomics" (variant 2 of the large-Q backward, BASELINE.json north_star): the
+// NG lane groups of a warp process the same sample index of NG consecutive queries; when two
+// of them are about to reduce into the SAME value row (same pixel, same head) their weighted
+// rows are added with shuffles and only the lowest group issues the red.  match.any finds the
+// coincidences; the shuffle pass runs only in steps where the warp has one.
+template <int G, int VEC, typename GT>
+__device__ __forceinline__ void scatter_corner_aggregated(bool valid, int row_off, GT* ptr,
+                                                          const float (&t)[VEC], int grp, int gl) {
+  constexpr int NG = 32 / G;
+  const int key = valid ? row_off : (-1 - grp);          // invalid corners match nobody
+  const unsigned same = __match_any_sync(0xffffffffu, key);
+  if (__any_sync(0xffffffffu, __popc(same) > G)) {
+    float sum[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) sum[i] = t[i];
+#pragma unroll
+    for (int dgrp = 1; dgrp < NG; ++dgrp) {
+      const int partner = ((grp + dgrp) % NG) * G + gl;
+      const int pkey = __shfl_sync(0xffffffffu, key, partner);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float pv = __shfl_sync(0xffffffffu, t[i], partner);
+        sum[i] += (pkey == key) ? pv : 0.f;
+      }
+    }
+    if (valid && (__ffs(same) - 1) / G == grp) red_add_row(ptr, sum);
+  } else if (valid) {
+    red_add_row(ptr, t);
+  }
+}
+
+template <int D, typename VT, typename GT, class IO, int AGG = 0>
 __global__ void __launch_bounds__(kRowsThreads, IO::kFused ? 2 : 0)
 msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, IO io, const float* __restrict__ grad_out,
-                     GT* __restrict__ grad_value, Dims d, int nsplit) {
+                     GT* __restrict__ grad_value, Dims d, int nsplit, int agg_min_level) {
   using VL = BwdVec<VT, GT>;
   constexpr int VEC = VL::VEC;
   constexpr int G = D / VEC;
@@ -166,10 +197,25 @@ msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     _Pragma("unroll") for (int c = 0; c < VEC; ++c) t[c] = (WK) * a * g[c]; \
     red_add_row(PTR, t);                                             \
   }
-        MSDA_SCATTER(1, w1, gp)
-        MSDA_SCATTER(2, w2, gp + MD)
-        MSDA_SCATTER(4, w3, gp + rs)
-        MSDA_SCATTER(8, w4, gp + rs + MD)
+        // the level of sample s0 + j is the same in every group of the warp (nsplit == 1), dead
+        // groups included, so the warp-wide match / shuffles below are executed convergently
+        if (AGG && level_of(s0 + j) >= agg_min_level) {
+#define MSDA_SCATTER_AGG(BIT, WK, OFF)                                                   \
+  {                                                                                      \
+    _Pragma("unroll") for (int c = 0; c < VEC; ++c) t[c] = (WK) * a * g[c];              \
+    scatter_corner_aggregated<G, VEC, GT>((meta & BIT) != 0, q.x + (OFF), gp + (OFF), t, grp, gl); \
+  }
+          MSDA_SCATTER_AGG(1, w1, 0)
+          MSDA_SCATTER_AGG(2, w2, MD)
+          MSDA_SCATTER_AGG(4, w3, rs)
+          MSDA_SCATTER_AGG(8, w4, rs + MD)
+#undef MSDA_SCATTER_AGG
+        } else {
+          MSDA_SCATTER(1, w1, gp)
+          MSDA_SCATTER(2, w2, gp + MD)
+          MSDA_SCATTER(4, w3, gp + rs)
+          MSDA_SCATTER(8, w4, gp + rs + MD)
+        }
 #undef MSDA_SCATTER
       }
     }
@@ -291,8 +337,20 @@ static cudaError_t launch_bwd_rows(const void* value, const int64_t* shapes, con
   const int qpb = GPB / nsplit;
   const int64_t blocks = static_cast<int64_t>(d.B) * ((d.Q + qpb - 1) / qpb) * d.M;
   if (blocks >= (int64_t(1) << 31)) return cudaErrorInvalidConfiguration;
+  // variant 2: warp-aggregated atomics (the benchmark's kernel only; rows not split)
+  if constexpr (D == 32 && std::is_same<VT, float>::value && std::is_same<GT, float>::value &&
+                !IO::kFused) {
+    if (tuning().bwd_variant == 2 && nsplit == 1) {
+      msda_bwd_rows_kernel<D, VT, GT, IO, 1><<<static_cast<unsigned>(blocks), kRowsThreads, 0, st>>>(
+          static_cast<const VT*>(value), shapes, lsi, io, go, static_cast<GT*>(gv), d, nsplit,
+          tuning().agg_min_level);
+      note_launches(1);
+      note_kernel(KF_BWD_ROWS);
+      return cudaGetLastError();
+    }
+  }
   msda_bwd_rows_kernel<D, VT, GT, IO><<<static_cast<unsigned>(blocks), kRowsThreads, 0, st>>>(
-      static_cast<const VT*>(value), shapes, lsi, io, go, static_cast<GT*>(gv), d, nsplit);
+      static_cast<const VT*>(value), shapes, lsi, io, go, static_cast<GT*>(gv), d, nsplit, 0);
   note_launches(1);
   note_kernel(IO::kFused ? KF_BWD_ROWS_FUSED : KF_BWD_ROWS);
   return cudaGetLastError();

@@ -157,6 +157,9 @@ int msda_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "fwd_split")) slot = &t.fwd_split;
   else if (!std::strcmp(name, "bwd_split")) slot = &t.bwd_split;
   else if (!std::strcmp(name, "flat")) slot = &t.flat;
+  else if (!std::strcmp(name, "agg_min_level")) slot = &t.agg_min_level;
+  else if (!std::strcmp(name, "flat_fwd_cfg")) slot = &t.flat_fwd_cfg;
+  else if (!std::strcmp(name, "flat_bwd_cfg")) slot = &t.flat_bwd_cfg;
   else if (!std::strcmp(name, "l2_prefetch")) slot = &t.l2_prefetch;
   else if (!std::strcmp(name, "l2_prefetch_mb")) slot = &t.l2_prefetch_mb;
   else if (!std::strcmp(name, "bwd_variant")) slot = &t.bwd_variant;

@@ -79,8 +79,8 @@ __device__ __forceinline__ void l2_prefetch_share(const void* base, long long by
 // --------------------------------------------------------------------------
 // forward
 // --------------------------------------------------------------------------
-template <int D, typename VT, class SRC, int BATCH>
-__global__ void __launch_bounds__(kFlatThreads, kFlatBlocksPerSM)
+template <int D, typename VT, class SRC, int BATCH, int MINB>
+__global__ void __launch_bounds__(kFlatThreads, MINB)
 msda_fwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, SRC src0, float* __restrict__ out, Dims d,
                      int C, long long NC, uint4* __restrict__ clear, long long clear_n16,
@@ -227,8 +227,8 @@ msda_fwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
 // --------------------------------------------------------------------------
 // backward
 // --------------------------------------------------------------------------
-template <int D, typename VT, typename GT, class IO, int BATCH>
-__global__ void __launch_bounds__(kFlatThreads, kFlatBlocksPerSM)
+template <int D, typename VT, typename GT, class IO, int BATCH, int MINB>
+__global__ void __launch_bounds__(kFlatThreads, MINB)
 msda_bwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, IO io0, const float* __restrict__ grad_out,
                      GT* __restrict__ grad_value, Dims d, int C, long long NC,
@@ -430,12 +430,29 @@ static cudaError_t launch_fwd_flat(const void* value, const int64_t* shapes, con
   const long long NC = R * C;
   cudaError_t e = cudaMemsetAsync(out, 0, static_cast<size_t>(R) * D * sizeof(float), st);
   if (e != cudaSuccess) return e;
-  const unsigned grid = static_cast<unsigned>(sm_count * kFlatBlocksPerSM);
   constexpr int G = D / Vec16<VT>::VEC;
   constexpr int BATCH = G >= 4 ? 4 : G;
-  msda_fwd_flat_kernel<D, VT, SRC, BATCH><<<grid, kFlatThreads, 0, st>>>(
-      static_cast<const VT*>(value), shapes, lsi, src, out, d, C, NC, static_cast<uint4*>(clear),
-      static_cast<long long>(clear_bytes / 16), prefetch_bytes_for<VT>(d, 1));
+  const long long clear_n16 = static_cast<long long>(clear_bytes / 16);
+  const long long pf = prefetch_bytes_for<VT>(d, 1);
+#define MSDA_FWD_FLAT_LAUNCH(BATCH_, MINB_)                                                       \
+  msda_fwd_flat_kernel<D, VT, SRC, BATCH_, MINB_>                                                 \
+      <<<static_cast<unsigned>(sm_count * MINB_), kFlatThreads, 0, st>>>(                         \
+          static_cast<const VT*>(value), shapes, lsi, src, out, d, C, NC,                         \
+          static_cast<uint4*>(clear), clear_n16, pf)
+  // tuning sweep (knob flat_fwd_cfg), instantiated for the benchmark's kernel only
+  if constexpr (D == 32 && std::is_same<VT, float>::value && std::is_same<SRC, PlainSource>::value) {
+    switch (tuning().flat_fwd_cfg) {
+      case 1: MSDA_FWD_FLAT_LAUNCH(2, 4); break;
+      case 2: MSDA_FWD_FLAT_LAUNCH(2, 3); break;
+      case 3: MSDA_FWD_FLAT_LAUNCH((G >= 8 ? 8 : G), 1); break;
+      case 4: MSDA_FWD_FLAT_LAUNCH(1, 4); break;
+      case 5: MSDA_FWD_FLAT_LAUNCH(4, 3); break;
+      default: MSDA_FWD_FLAT_LAUNCH(BATCH, kFlatBlocksPerSM); break;
+    }
+  } else {
+    MSDA_FWD_FLAT_LAUNCH(BATCH, kFlatBlocksPerSM);
+  }
+#undef MSDA_FWD_FLAT_LAUNCH
   note_launches(1);
   note_kernel(std::is_same<SRC, FusedSource>::value ? KF_FWD_FLAT_FUSED : KF_FWD_FLAT);
   return cudaGetLastError();
@@ -448,12 +465,26 @@ static cudaError_t launch_bwd_flat(const void* value, const int64_t* shapes, con
   const int LP = d.L * d.P;
   const int C = (LP + 31) / 32;
   const long long NC = static_cast<long long>(d.B) * d.Q * d.M * C;
-  const unsigned grid = static_cast<unsigned>(sm_count * kFlatBlocksPerSM);
   constexpr int G = D / BwdVec<VT, GT>::VEC;
   constexpr int BATCH = G >= 2 ? 2 : 1;
-  msda_bwd_flat_kernel<D, VT, GT, IO, BATCH><<<grid, kFlatThreads, 0, st>>>(
-      static_cast<const VT*>(value), shapes, lsi, io, go, static_cast<GT*>(gv), d, C, NC,
-      prefetch_bytes_for<VT>(d, 2));
+  const long long pf = prefetch_bytes_for<VT>(d, 2);
+#define MSDA_BWD_FLAT_LAUNCH(BATCH_, MINB_)                                                       \
+  msda_bwd_flat_kernel<D, VT, GT, IO, BATCH_, MINB_>                                              \
+      <<<static_cast<unsigned>(sm_count * MINB_), kFlatThreads, 0, st>>>(                         \
+          static_cast<const VT*>(value), shapes, lsi, io, go, static_cast<GT*>(gv), d, C, NC, pf)
+  if constexpr (D == 32 && std::is_same<VT, float>::value && std::is_same<IO, PlainIO>::value) {
+    switch (tuning().flat_bwd_cfg) {
+      case 1: MSDA_BWD_FLAT_LAUNCH(1, 3); break;
+      case 2: MSDA_BWD_FLAT_LAUNCH(2, 3); break;
+      case 3: MSDA_BWD_FLAT_LAUNCH(4, 1); break;
+      case 4: MSDA_BWD_FLAT_LAUNCH(1, 4); break;
+      case 5: MSDA_BWD_FLAT_LAUNCH(4, 2); break;
+      default: MSDA_BWD_FLAT_LAUNCH(BATCH, kFlatBlocksPerSM); break;
+    }
+  } else {
+    MSDA_BWD_FLAT_LAUNCH(BATCH, kFlatBlocksPerSM);
+  }
+#undef MSDA_BWD_FLAT_LAUNCH
   note_launches(1);
   note_kernel(IO::kFused ? KF_BWD_FLAT_FUSED : KF_BWD_FLAT);
   return cudaGetLastError();

@@ -17,6 +17,7 @@
 //    end) so small-Q pose-decoder shapes still fill the machine.
 //  * generic<T,VT>: any D, fp32/fp64 — the parity path for the shapes the
 //    reference's tests use (D = 2, 4, 30, 71, 1025, double precision).
+#include <atomic>
 #include <type_traits>
 
 #include "msda_kernels.h"
@@ -90,10 +91,28 @@ constexpr int kRowsWarps = kRowsThreads / 32;
 // which are latency bound (measured on B200: pose cfg3 58 -> 48 us).
 constexpr int fwd_min_blocks(int split) { return split > 1 ? 3 : 4; }
 
+// Shared-memory state of one rows block.
+template <int D, typename VT, int SPLIT>
+struct FwdRowsSmem {
+  static constexpr int VEC = Vec16<VT>::VEC;
+  static constexpr int G = D / VEC;
+  static constexpr int NGW = 32 / G;
+  static constexpr int WSPLIT = SPLIT < NGW ? SPLIT : NGW;
+  static constexpr int XSPLIT = SPLIT / WSPLIT;
+  LevelInfo lvl[kMaxSmemLevels];
+  int4 board[kRowsWarps][G * (2 * (32 / G) + 1)];
+  float part[XSPLIT > 1 ? kRowsWarps : 1][D];   // per-warp partial rows (XSPLIT > 1)
+};
+
+// One work item of the rows family: (batch entry b, chunk of consecutive queries, head m).
+// All rows of an item belong to ONE head and to neighbouring queries, so when neighbouring
+// queries look at neighbouring pixels (the encoder) their bilinear corners are the same
+// 128-byte rows and hit in L1.
 template <int D, typename VT, int SPLIT, class SRC>
-__global__ void __launch_bounds__(kRowsThreads, fwd_min_blocks(SPLIT))
-msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
-                     const int64_t* __restrict__ lsi, SRC src, float* __restrict__ out, Dims d) {
+__device__ __forceinline__ void fwd_rows_item(const VT* __restrict__ value, SRC src,
+                                              float* __restrict__ out, const Dims& d,
+                                              FwdRowsSmem<D, VT, SPLIT>& sm, int m, int chunk,
+                                              int64_t b) {
   constexpr int VEC = Vec16<VT>::VEC;
   constexpr int G = D / VEC;  // lanes per row
   static_assert(D % VEC == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0, "bad D");
@@ -101,31 +120,15 @@ msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   constexpr int WSPLIT = SPLIT < NGW ? SPLIT : NGW;      // splits combined by shuffles inside a warp
   constexpr int XSPLIT = SPLIT / WSPLIT;                 // ... and across warps through shared memory
   static_assert(SPLIT * G <= kRowsThreads && (SPLIT & (SPLIT - 1)) == 0, "bad SPLIT");
-
-  __shared__ LevelInfo s_lvl[kMaxSmemLevels];
-  __shared__ int4 s_board[kRowsWarps][G * (2 * (32 / G) + 1)];
-  __shared__ float s_part[XSPLIT > 1 ? kRowsWarps : 1][D];   // per-warp partial rows (XSPLIT > 1)
-
+  auto& s_lvl = sm.lvl;
+  auto& s_board = sm.board;
+  auto& s_part = sm.part;
   const int MD = d.M * D;
-  for (int l = threadIdx.x; l < d.L; l += blockDim.x) s_lvl[l] = load_level(shapes, lsi, l, MD);
-  __syncthreads();
-
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int gl = lane & (G - 1);        // lane within the row group
   const int grp = lane / G;             // group within the warp
-
-  // Block -> (batch entry b, chunk of consecutive queries, head m).  All rows
-  // of a block belong to ONE head and to neighbouring queries, so when
-  // neighbouring queries look at neighbouring pixels (the encoder) their
-  // bilinear corners are the same 128-byte rows and hit in L1.
   constexpr int QPB = kRowsThreads / G / SPLIT;  // queries per block
-  const int n_chunks = (d.Q + QPB - 1) / QPB;
-  int blk = blockIdx.x;
-  const int m = blk % d.M;
-  blk /= d.M;
-  const int chunk = blk % n_chunks;
-  const int64_t b = blk / n_chunks;
   const int gib = threadIdx.x / G;      // group within the block
   const int split = gib % SPLIT;
   int q_idx = chunk * QPB + gib / SPLIT;
@@ -247,9 +250,72 @@ msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   }
 }
 
+template <int D, typename VT, int SPLIT, class SRC>
+__global__ void __launch_bounds__(kRowsThreads, fwd_min_blocks(SPLIT))
+msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                     const int64_t* __restrict__ lsi, SRC src, float* __restrict__ out, Dims d) {
+  __shared__ FwdRowsSmem<D, VT, SPLIT> sm;
+  const int MD = d.M * D;
+  for (int l = threadIdx.x; l < d.L; l += blockDim.x) sm.lvl[l] = load_level(shapes, lsi, l, MD);
+  __syncthreads();
+  constexpr int QPB = kRowsThreads / (D / Vec16<VT>::VEC) / SPLIT;
+  const int n_chunks = (d.Q + QPB - 1) / QPB;
+  int blk = blockIdx.x;
+  const int m = blk % d.M;
+  blk /= d.M;
+  fwd_rows_item<D, VT, SPLIT, SRC>(value, src, out, d, sm, m, blk % n_chunks, blk / n_chunks);
+}
+
+// Forward variant 2 (large Q): persistent blocks, head-affine.  Every block of an SM serves
+// the SAME head -- head = %smid mod M -- pulling (batch entry, query chunk) items of that head
+// from a per-head counter in global memory and helping the other heads when its own is done.
+// The coarse levels of one head (35 + 134 KB in fp32 for R-50 at 800x1333) then stay resident
+// in that SM's L1 instead of competing with the other seven heads' copies.
+__device__ int g_head_queue[256][64];   // [slot][head]: a launch zeroes and uses one slot
+
+template <int D, typename VT, class SRC>
+__global__ void __launch_bounds__(kRowsThreads, fwd_min_blocks(1))
+msda_fwd_rows_affine_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                            const int64_t* __restrict__ lsi, SRC src, float* __restrict__ out,
+                            Dims d, int slot) {
+  __shared__ FwdRowsSmem<D, VT, 1> sm;
+  __shared__ int s_item;
+  const int MD = d.M * D;
+  for (int l = threadIdx.x; l < d.L; l += blockDim.x) sm.lvl[l] = load_level(shapes, lsi, l, MD);
+  constexpr int QPB = kRowsThreads / (D / Vec16<VT>::VEC);
+  const int n_chunks = (d.Q + QPB - 1) / QPB;
+  const int per_head = n_chunks * d.B;
+  unsigned smid;
+  asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  const int home = static_cast<int>(smid % static_cast<unsigned>(d.M));
+  int* queue = g_head_queue[slot];
+  for (;;) {
+    __syncthreads();                      // level table ready / previous item fully consumed
+    if (threadIdx.x == 0) {
+      int item = -1;
+      for (int t = 0, h = home; t < d.M; ++t, h = (h + 1 == d.M ? 0 : h + 1)) {
+        const int c = atomicAdd(&queue[h], 1);
+        if (c < per_head) {
+          item = h * per_head + c;
+          break;
+        }
+      }
+      s_item = item;
+    }
+    __syncthreads();
+    const int item = s_item;
+    if (item < 0) break;
+    const int m = item / per_head;
+    const int c = item - m * per_head;
+    fwd_rows_item<D, VT, 1, SRC>(value, src, out, d, sm, m, c % n_chunks, c / n_chunks);
+  }
+}
+
 // --------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------
+static thread_local int g_fwd_sm_count = 148;   // set by launch_forward* before dispatch
+
 template <int D, typename VT, int SPLIT, class SRC>
 static cudaError_t launch_rows_split(const void* value, const int64_t* shapes, const int64_t* lsi,
                                      const SRC& src, float* out, const Dims& d, cudaStream_t st) {
@@ -257,6 +323,23 @@ static cudaError_t launch_rows_split(const void* value, const int64_t* shapes, c
   constexpr int QPB = kRowsThreads / G / SPLIT;
   const int64_t blocks = static_cast<int64_t>(d.B) * ((d.Q + QPB - 1) / QPB) * d.M;
   if (blocks >= (int64_t(1) << 31)) return cudaErrorInvalidConfiguration;
+  if constexpr (SPLIT == 1) {
+    const int resident = g_fwd_sm_count * fwd_min_blocks(1);
+    if (tuning().fwd_variant == 2 && d.M <= 64 && blocks > 2 * resident) {
+      static std::atomic<unsigned> next_slot{0};
+      const int slot = static_cast<int>(next_slot.fetch_add(1) % 256u);
+      int* q = nullptr;
+      cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&q), g_head_queue);
+      if (e != cudaSuccess) return e;
+      e = cudaMemsetAsync(q + slot * 64, 0, 64 * sizeof(int), st);
+      if (e != cudaSuccess) return e;
+      msda_fwd_rows_affine_kernel<D, VT, SRC><<<static_cast<unsigned>(resident), kRowsThreads, 0, st>>>(
+          static_cast<const VT*>(value), shapes, lsi, src, out, d, slot);
+      note_launches(1);
+      note_kernel(std::is_same<SRC, FusedSource>::value ? KF_FWD_ROWS_FUSED : KF_FWD_ROWS);
+      return cudaGetLastError();
+    }
+  }
   msda_fwd_rows_kernel<D, VT, SPLIT, SRC><<<static_cast<unsigned>(blocks), kRowsThreads, 0, st>>>(
       static_cast<const VT*>(value), shapes, lsi, src, out, d);
   note_launches(1);
@@ -310,6 +393,7 @@ cudaError_t launch_forward(const void* value, const int64_t* shapes, const int64
                            const void* loc, const void* aw, void* out, const Dims& d, int dtype,
                            int value_dtype, int sm_count, int force_generic, void* clear,
                            size_t clear_bytes, cudaStream_t st) {
+  g_fwd_sm_count = sm_count;
   if (dtype == MSDA_F32 && !force_generic && d.L <= kMaxSmemLevels &&
       rows_supported(d.D, value_dtype)) {
     PlainSource src;
@@ -370,6 +454,7 @@ cudaError_t launch_forward(const void* value, const int64_t* shapes, const int64
 cudaError_t launch_forward_fused(const void* value, const int64_t* shapes, const int64_t* lsi,
                                  const FusedSource& src, float* out, const Dims& d, int value_dtype,
                                  int sm_count, void* clear, size_t clear_bytes, cudaStream_t st) {
+  g_fwd_sm_count = sm_count;
   if (d.D != 32 || d.L > kMaxSmemLevels) return cudaErrorNotSupported;
   if (value_dtype != MSDA_F32 && value_dtype != MSDA_BF16) return cudaErrorNotSupported;
   if (flat_preferred(d, value_dtype == MSDA_F32 ? 8 : 4, sm_count))

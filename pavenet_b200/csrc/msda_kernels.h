@@ -20,8 +20,11 @@ struct Tuning {
   int linear_bm = 0;  // rows per CTA: 128 (default, also 0) or 256
   int copy_streams = 1;  // host-buffer entry points: upload / download streams per direction (1..4)
   int flat = 1;          // flat small-Q kernels (msda_flat.cu): 0 never, 1 heuristic, 2 whenever legal
+  int flat_fwd_cfg = 0;    // tuning sweep of the flat kernels (batch, blocks per SM), 0 = default
+  int flat_bwd_cfg = 0;
   int l2_prefetch = 0;     // flat kernels stream value into L2 first: bit 0 forward, bit 1 backward
   int l2_prefetch_mb = 120;  // ... when value is at most this many MiB
+  int agg_min_level = 0;   // bwd_variant 2: aggregate from this level on (0 = every level)
   int bwd_variant = 0;   // large-Q backward: 0 default, 1 plain rows, 2 warp-aggregated, 3 tile
   int fwd_variant = 0;   // large-Q forward: 0 default, 1 plain rows, 2 ...
 };

@@ -322,11 +322,36 @@ class HostWorkspace(object):
                 raise RuntimeError('%s tensor has to be contiguous' % name)
         if shapes.dtype != torch.int64 or lsi.dtype != torch.int64:
             raise RuntimeError('spatial_shapes and level_start_index must be int64 tensors')
+        if value.dim() != 4 or loc.dim() != 6 or loc.shape[-1] != 2:
+            raise RuntimeError('value must be (bs, keys, heads, dim) and sampling_locations '
+                               '(bs, queries, heads, levels, points, 2), got %s / %s'
+                               % (tuple(value.shape), tuple(loc.shape)))
         B, S, M, D = value.shape
-        _, Q, _, L, P, _ = loc.shape
+        Bq, Q, Mq, L, P, _ = loc.shape
         if min(B, S, M, D, L, Q, P) <= 0:
             raise RuntimeError('host-buffer entry points need non-empty tensors')
+        if (Bq, Mq) != (B, M) or tuple(aw.shape) != (B, Q, M, L, P):
+            raise RuntimeError('inconsistent shapes: value %s sampling_locations %s attention_weights %s'
+                               % (tuple(value.shape), tuple(loc.shape), tuple(aw.shape)))
+        if tuple(shapes.shape) != (L, 2) or tuple(lsi.shape) != (L,):
+            raise RuntimeError('spatial_shapes must be (%d, 2) and level_start_index (%d,)' % (L, L))
+        if loc.dtype not in (torch.float32, torch.float64) or aw.dtype != loc.dtype:
+            raise RuntimeError('sampling_locations / attention_weights must share float32 or float64')
+        if value.dtype != loc.dtype and not (value.dtype == torch.bfloat16
+                                             and loc.dtype == torch.float32):
+            raise RuntimeError('value dtype %s incompatible with %s' % (value.dtype, loc.dtype))
         return B, S, M, D, L, Q, P
+
+    @staticmethod
+    def _check_result(name, t, shape, dtype):
+        """A caller-supplied result / gradient buffer the library will write with async copies."""
+        if not isinstance(t, torch.Tensor) or t.is_cuda:
+            raise RuntimeError('%s must be a CPU tensor' % name)
+        if not t.is_contiguous():
+            raise RuntimeError('%s tensor has to be contiguous' % name)
+        if tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            raise RuntimeError('%s must be %s %s, got %s %s'
+                               % (name, tuple(shape), dtype, tuple(t.shape), t.dtype))
 
     def forward(self, value, spatial_shapes, level_start_index, sampling_locations,
                 attention_weights, out=None):
@@ -334,6 +359,7 @@ class HostWorkspace(object):
                                                sampling_locations, attention_weights)
         if out is None:
             out = torch.empty((B, Q, M * D), dtype=sampling_locations.dtype)
+        self._check_result('out', out, (B, Q, M * D), sampling_locations.dtype)
         status = self._lib.msda_forward_host(
             self._ws, value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             sampling_locations.data_ptr(), attention_weights.data_ptr(), out.data_ptr(),
@@ -359,6 +385,12 @@ class HostWorkspace(object):
             grad_attn_weight = torch.empty_like(attention_weights)
         if grad_value.dtype != dt:
             raise RuntimeError('grad_value is returned in %s' % dt)
+        self._check_result('out', out, (B, Q, M * D), dt)
+        self._check_result('grad_value', grad_value, value.shape, dt)
+        self._check_result('grad_sampling_loc', grad_sampling_loc, sampling_locations.shape, dt)
+        self._check_result('grad_attn_weight', grad_attn_weight, attention_weights.shape, dt)
+        if grad_output.is_cuda or grad_output.dtype != dt or grad_output.numel() != B * Q * M * D:
+            raise RuntimeError('grad_output must be a CPU %s tensor of %d elements' % (dt, B * Q * M * D))
         grad_output = grad_output.contiguous()
         status = self._lib.msda_forward_backward_host(
             self._ws, value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
@@ -552,14 +584,21 @@ class _DeviceSeed(object):
 
 
 class device_dropout_seed(object):
-    def __init__(self, seed_tensor):
+    """`salt`: where this context's dropout sites start in seed space.  Contexts that share one
+    seed tensor (the graphed stages of a step) must use different salts, or site k of every
+    context would draw the same mask; `graphs.GraphedStage` passes one per captured graph."""
+    _SITE_STRIDE = 0x9E3779B97F4A7C15 % (2 ** 40)      # sites far apart in seed space
+
+    def __init__(self, seed_tensor, salt=0):
         if not (seed_tensor.is_cuda and seed_tensor.dtype == torch.int64 and seed_tensor.numel() == 1):
             raise ValueError('device_dropout_seed needs a 1-element int64 CUDA tensor')
         self.tensor = seed_tensor
+        # 2^20 sites per context before two contexts could meet
+        self.start = (int(salt) * (self._SITE_STRIDE << 20)) % (2 ** 62)
 
     def __enter__(self):
         self.saved = (_DeviceSeed.tensor, _DeviceSeed.next_offset)
-        _DeviceSeed.tensor, _DeviceSeed.next_offset = self.tensor, 0
+        _DeviceSeed.tensor, _DeviceSeed.next_offset = self.tensor, self.start
         return self
 
     def __exit__(self, *exc):
@@ -570,7 +609,7 @@ class device_dropout_seed(object):
 def _draw_seed():
     """-> (host seed, device seed tensor or None) for one dropout site."""
     if _DeviceSeed.tensor is not None:
-        _DeviceSeed.next_offset += 0x9E3779B97F4A7C15 % (2 ** 40)      # sites far apart in seed space
+        _DeviceSeed.next_offset += device_dropout_seed._SITE_STRIDE
         return _DeviceSeed.next_offset % (2 ** 62), _DeviceSeed.tensor
     return _next_dropout_seed(), None
 

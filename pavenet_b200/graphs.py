@@ -18,20 +18,35 @@ What makes the attention modules of this package capturable:
 
 Call `refresh_seed()` once per step before the first graphed stage.
 """
+import collections
+import contextlib
+import itertools
+
 import torch
 import torch.nn as nn
 
 from .functional import device_dropout_seed
 
-# capture runs on a side stream, so the parameters' AccumulateGrad nodes (created earlier on the
-# default stream) see gradients produced on another stream; autograd inserts the event wait it
-# needs and warns once per process -- the wait is intended here
-if hasattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch'):
-    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
-
 __all__ = ['GraphedStage', 'refresh_seed']
 
 _SEED = {}
+_SALT = itertools.count(1)      # one dropout-seed salt per captured graph, process wide
+
+
+@contextlib.contextmanager
+def _quiet_accumulate_grad_stream_warning():
+    """Capture runs on a side stream, so the parameters' AccumulateGrad nodes (created earlier on
+    the default stream) see gradients produced on another stream; autograd inserts the event
+    wait it needs and warns -- the wait is intended here.  Silenced for the capture only."""
+    setter = getattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch', None)
+    if setter is None:
+        yield
+        return
+    setter(False)
+    try:
+        yield
+    finally:
+        setter(True)
 
 
 def _seed_tensor(device):
@@ -54,14 +69,16 @@ class _Stage(nn.Module):
     """fn(*tensors) with the modules / parameters it touches registered, so the capture
     sees their parameters as graph inputs and returns their gradients."""
 
-    def __init__(self, fn, modules, params, seed, static):
+    def __init__(self, fn, modules, params, seed, static, salt):
         super().__init__()
         self.mods = nn.ModuleList(modules)
         self.extra = nn.ParameterList(params)
-        self._fn, self._seed, self._static = fn, seed, static
+        self._fn, self._seed, self._static, self._salt = fn, seed, static, salt
 
     def forward(self, *args):
-        with device_dropout_seed(self._seed):
+        # the salt keeps the dropout sites of this graph apart from those of every other graph
+        # that reads the same per-device seed tensor
+        with device_dropout_seed(self._seed, salt=self._salt):
             if self._static is not None:
                 return self._fn(*args, static=self._static)
             return self._fn(*args)
@@ -78,12 +95,21 @@ class GraphedStage(object):
     the listed modules / parameters.  The first call with a new signature (shapes, dtypes,
     requires_grad, training mode) runs warm-up iterations and captures; later calls replay.
     Not an nn.Module on purpose: it must not re-register the wrapped modules in the model's
-    own module tree."""
+    own module tree.
 
-    def __init__(self, fn, modules=(), params=(), warmup_iters=3):
+    Every captured graph pins a private memory pool with its saved activations, and a new
+    signature costs `warmup_iters` eager runs plus a capture, so the cache is bounded: at most
+    `max_graphs` graphs are kept (least recently used evicted), and a signature is only captured
+    once it has been seen `capture_after` times -- before that (data-dependent `static` keys that
+    rarely repeat, e.g. per-clip person counts) the stage runs eagerly."""
+
+    def __init__(self, fn, modules=(), params=(), warmup_iters=3, max_graphs=8, capture_after=1):
         self.fn, self.modules, self.params = fn, list(modules), list(params)
         self.warmup_iters = warmup_iters
-        self._graphs = {}
+        self.max_graphs, self.capture_after = max(1, int(max_graphs)), max(1, int(capture_after))
+        self._graphs = collections.OrderedDict()
+        self._seen = collections.Counter()
+        self.stats = {'captures': 0, 'evictions': 0, 'eager_calls': 0, 'replays': 0}
 
     def _signature(self, args, static):
         training = tuple(m.training for m in self.modules)
@@ -98,12 +124,29 @@ class GraphedStage(object):
                 raise RuntimeError('GraphedStage takes CUDA tensors only, got %r' % (type(a),))
         key = self._signature(args, static)
         graphed = self._graphs.get(key)
-        if graphed is None:
-            stage = _Stage(self.fn, self.modules, self.params, _seed_tensor(args[0].device), static)
-            # make_graphed_callables keys its replay on the wrapper's training flag; the wrapped
-            # modules keep their own modes (frozen BatchNorm stays in eval)
-            sample = tuple(a.detach().clone().requires_grad_(a.requires_grad) for a in args)
+        if graphed is not None:
+            self._graphs.move_to_end(key)
+            self.stats['replays'] += 1
+            return graphed(*args)
+        self._seen[key] += 1
+        if len(self._seen) > 64 * self.max_graphs:      # the counter itself stays bounded
+            self._seen = collections.Counter({k: v for k, v in self._seen.most_common(8 * self.max_graphs)})
+        if self._seen[key] < self.capture_after:
+            self.stats['eager_calls'] += 1
+            if static is not None:
+                return self.fn(*args, static=static)
+            return self.fn(*args)
+        while len(self._graphs) >= self.max_graphs:
+            self._graphs.popitem(last=False)             # frees that graph's memory pool
+            self.stats['evictions'] += 1
+        stage = _Stage(self.fn, self.modules, self.params, _seed_tensor(args[0].device), static,
+                       next(_SALT))
+        # make_graphed_callables keys its replay on the wrapper's training flag; the wrapped
+        # modules keep their own modes (frozen BatchNorm stays in eval)
+        sample = tuple(a.detach().clone().requires_grad_(a.requires_grad) for a in args)
+        with _quiet_accumulate_grad_stream_warning():
             graphed = torch.cuda.make_graphed_callables(stage, sample, num_warmup_iters=self.warmup_iters,
                                                         allow_unused_input=True)
-            self._graphs[key] = graphed
+        self._graphs[key] = graphed
+        self.stats['captures'] += 1
         return graphed(*args)

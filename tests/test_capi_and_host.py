@@ -344,3 +344,77 @@ def test_integration_md_ctypes_stub_matches_the_abi():
     assert callable(ns['ext_module'].ms_deform_attn_backward)
     assert ns['_DT'] == {torch.float32: pavenet_b200._capi.MSDA_F32, torch.float64: pavenet_b200._capi.MSDA_F64,
                          torch.bfloat16: pavenet_b200._capi.MSDA_BF16}
+
+
+def test_install_patches_a_live_mmcv_and_opera_tree(tmp_path, monkeypatch):
+    """`pavenet_b200.install()` against a stub of the reference's package layout: the five things
+    a maintainer needs swapped are swapped — `mmcv.ops.multi_scale_deform_attn.ext_module`
+    and `.MultiScaleDeformableAttnFunction` (what third_party/mmcv/mmcv/utils/ext_loader.py:12-16
+    and multi_scale_deform_attn.py:16-17,20 provide), the Function name imported into
+    `opera.models.utils.transformer` (transformer.py:14), and the class names in mmcv's
+    ATTENTION / FEEDFORWARD_NETWORK registries and opera's ATTENTION registry
+    (mmcv/cnn/bricks/registry.py, opera/models/utils/builder.py:11-17)."""
+    import importlib
+    import sys
+    import textwrap
+    registry_src = textwrap.dedent('''
+        class Registry(object):
+            def __init__(self, name):
+                self.name, self.module_dict = name, {}
+            def register_module(self, name=None, force=False, module=None):
+                if not force and name in self.module_dict:
+                    raise KeyError(name)
+                self.module_dict[name] = module
+                return module
+            def get(self, key):
+                return self.module_dict.get(key)
+    ''')
+    files = {
+        'mmcv/__init__.py': '',
+        'mmcv/ops/__init__.py': '',
+        'mmcv/ops/multi_scale_deform_attn.py':
+            'ext_module = "ORIGINAL_EXT"\nclass MultiScaleDeformableAttnFunction(object):\n    pass\n',
+        'mmcv/cnn/__init__.py': '',
+        'mmcv/cnn/bricks/__init__.py': '',
+        'mmcv/cnn/bricks/registry.py': registry_src + 'ATTENTION = Registry("attention")\n'
+                                       'FEEDFORWARD_NETWORK = Registry("feed-forward Network")\n'
+                                       'ATTENTION.register_module(name="MultiScaleDeformableAttention", module=object)\n',
+        'opera/__init__.py': '',
+        'opera/models/__init__.py': '',
+        'opera/models/utils/__init__.py': '',
+        'opera/models/utils/transformer.py':
+            'from mmcv.ops.multi_scale_deform_attn import MultiScaleDeformableAttnFunction\n',
+        'opera/models/utils/builder.py': registry_src + 'ATTENTION = Registry("attention")\n',
+    }
+    for rel, src in files.items():
+        path = tmp_path / rel
+        path.parent.mkdir(parents=True, exist_ok=True)
+        path.write_text(src)
+    monkeypatch.syspath_prepend(str(tmp_path))
+    for name in [m for m in sys.modules if m == 'mmcv' or m.startswith('mmcv.')
+                 or m == 'opera' or m.startswith('opera.')]:
+        monkeypatch.delitem(sys.modules, name)
+    import pavenet_b200
+    from pavenet_b200 import functional, modules
+    try:
+        patched = pavenet_b200.install()
+        msda = importlib.import_module('mmcv.ops.multi_scale_deform_attn')
+        assert msda.ext_module is functional.ext_module
+        assert msda.MultiScaleDeformableAttnFunction is functional.MultiScaleDeformableAttnFunction
+        ot = importlib.import_module('opera.models.utils.transformer')
+        assert ot.MultiScaleDeformableAttnFunction is functional.MultiScaleDeformableAttnFunction
+        reg = importlib.import_module('mmcv.cnn.bricks.registry')
+        assert reg.ATTENTION.get('MultiScaleDeformableAttention') is modules.MultiScaleDeformableAttention
+        for cls in modules.MMCV_SCOPE_CLASSES:
+            assert reg.ATTENTION.get(cls.__name__) is cls
+        assert reg.FEEDFORWARD_NETWORK.get('FFN') is modules.FFN
+        opera_reg = importlib.import_module('opera.models.utils.builder').ATTENTION
+        for cls in modules.OPERA_SCOPE_CLASSES:
+            assert opera_reg.get(cls.__name__) is cls
+        assert {'mmcv.ops.multi_scale_deform_attn', 'opera.models.utils.transformer',
+                'mmcv.FFN'} <= set(patched)
+        assert 'opera.MulFramesMultiScaleDeformablePoseAttentionNumFrames3' in patched
+    finally:
+        for name in [m for m in sys.modules if m == 'mmcv' or m.startswith('mmcv.')
+                     or m == 'opera' or m.startswith('opera.')]:
+            sys.modules.pop(name, None)

@@ -218,3 +218,47 @@ def test_fused_kernels_match_unfused_chain(lib_options, flat, Q, P, levels, R, w
     assert rel_err(r.grad, r2.grad) < 2e-4
     if sc is not None:
         assert rel_err(sc.grad, sc2.grad) < 2e-4
+
+
+ENC_LEVELS = [(50, 84), (25, 42), (13, 21), (7, 11)]
+
+
+@pytest.mark.parametrize('variant', [('fwd_variant', 2), ('bwd_variant', 2)])
+def test_large_q_kernel_variants_match_oracle(lib_options, variant):
+    """Encoder-shaped problem (queries = pixels, coherent locations so neighbouring queries DO
+    collide on value rows) through the alternative large-Q kernels: the head-affine persistent
+    forward (fwd_variant 2) and the warp-aggregated-atomics backward (bwd_variant 2)."""
+    from pavenet_b200 import _capi
+    name, val = variant
+    lib_options(name, val)
+    lib_options('flat', 0)
+    g = torch.Generator().manual_seed(77)
+    shapes_t = torch.tensor(ENC_LEVELS, dtype=torch.long)
+    lsi = O.level_start_index(shapes_t)
+    S = int(shapes_t.prod(1).sum())
+    B, M, D, L, P, Q = 2, 8, 32, 4, 4, S
+    ref = []
+    for h, w in ENC_LEVELS:
+        ys = (torch.arange(h, dtype=torch.float32) + 0.5) / h
+        xs = (torch.arange(w, dtype=torch.float32) + 0.5) / w
+        yy, xx = torch.meshgrid(ys, xs, indexing='ij')
+        ref.append(torch.stack([xx.reshape(-1), yy.reshape(-1)], -1))
+    ref = torch.cat(ref)
+    norm = torch.tensor([[w, h] for h, w in ENC_LEVELS], dtype=torch.float32)
+    loc = ref[None, :, None, None, None, :] + torch.randn(B, Q, M, L, P, 2, generator=g) * 0.6 / \
+        norm[None, None, None, :, None, :]
+    value = torch.randn(B, S, M, D, generator=g)
+    aw = torch.softmax(torch.randn(B, Q, M, L * P, generator=g), -1).view(B, Q, M, L, P)
+    go = torch.randn(B, Q, M * D, generator=g)
+    before = _capi.family_counts()
+    out, gv, gl, ga = _run(value, shapes_t, lsi, loc, aw, go)
+    assert _delta(before, _capi.family_counts()) == {'fwd_rows': 1, 'bwd_rows': 1}
+    assert rel_err(out, O.c_forward(value, shapes_t, lsi, loc, aw)) < 5e-6
+    rgv, rgl, rga = O.c_backward(value, shapes_t, lsi, loc, aw, go)
+    assert rel_err(gv, rgv) < 1e-3 and rel_err(gv, rgv) < 2e-5
+    assert rel_err(gl, rgl) < 1e-3 and rel_err(ga, rga) < 1e-3
+    # elementwise, not only max-normalised (floor: a thousandth of the tensor's rms; both sides
+    # accumulate in fp32 in different orders)
+    b = rgv.double()
+    err = (gv.cpu().double() - b).abs() / (b.abs() + 1e-3 * float(b.pow(2).mean().sqrt()))
+    assert float(err.max()) < 1e-3
