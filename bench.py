@@ -229,6 +229,33 @@ def use_all_host_threads():
     return torch.get_num_threads()
 
 
+def bind_to_gpu_numa(index):
+    """Restrict this process to the CPUs NVML reports as local to GPU `index`, so that pinned
+    host buffers allocated afterwards are first-touched on that GPU's NUMA node.  Returns what
+    was done (for the JSON line); never fatal."""
+    info = {'bound': False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        info.update(gpu_local_cpus=len(cpus), allowed_cpus=len(allowed), usable=len(use))
+        try:
+            info['numa_node'] = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:  # noqa: BLE001 - older NVML
+            pass
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            info['bound'] = True
+    except Exception as exc:  # noqa: BLE001
+        info['note'] = '%s: %s' % (type(exc).__name__, exc)
+    return info
+
+
 def cpu_reference_step(prob_cpu):
     """One fwd+bwd of the reference CPU algorithm on CPU tensors; returns seconds."""
     from oracle import msda_oracle as O
@@ -704,6 +731,8 @@ def main():
     e2e = None
     e2e_autograd = None
     if not args.no_e2e:
+        # pinned buffers on the NUMA node of this rank's GPU (matters when N ranks share a host)
+        host_affinity = bind_to_gpu_numa(local) if world > 1 else {'bound': False}
         p = probs[0]
         host = {k: torch.empty(p[k].shape, dtype=p[k].dtype).pin_memory()
                 for k in ('value', 'loc', 'aw', 'grad_out')}
@@ -753,6 +782,7 @@ def main():
                                  grad_sampling_loc=gl_h, grad_attn_weight=ga_h)
 
         e2e = timed(e2e_capi)
+        e2e['host_affinity'] = host_affinity
         e2e['api'] = ('msda_forward_backward_host (C ABI, pinned host buffers; upload / kernels / '
                       'download pipelined over batch entries x query chunks)')
         hws.close()
@@ -804,20 +834,22 @@ def main():
                     'frac_of_8TBs_nominal': gbs / 8000.0}
 
         # Secondary, on-chip rooflines (SURVEY.md section 8d asks for the L1 / L2 limiter next to HBM):
-        # the op gathers / reduces 4*L*P value rows per output row, all of them L2-resident, so what
-        # bounds the kernels is the rate at which an SM can gather 128-byte rows through L1 (forward)
-        # and push reductions into L2 (backward).  Peaks: micro-benchmarks on this pool's B200 --
-        # tools/microbench_gather.cu (profiles/r01_microbench_gather_rows.txt): ld.v4.f32 of random
-        # L2-resident rows 157.6 G rows/s (1.84 clocks per row and SM; 259.6 when the rows sit in L1);
-        # tools/microbench_red.cu (profiles/r01_microbench_scatter_rows.txt): red.add.v4.f32 54.0 G rows/s
-        # = the SM -> L2 write path (st.v4 peaks at 8.6 TB/s, ~30 bytes per clock and SM).
+        # the op gathers / reduces 4*L*P value rows per output row, so what bounds the kernels is
+        # what an SM can move per clock, not HBM.  Forward peak: the L1 data path, one 128-byte
+        # wavefront (= one fp32 value row) per clock and SM at the SM clock sampled during the run
+        # (hardware figure; rows that miss L1 are further limited by the 64 B/clk/SM fill path from
+        # L2, measured at 1.84 clocks per row, profiles/r01_microbench_gather_rows.txt).  Backward
+        # peak: the rate at which the SMs can issue 128-byte reductions into L2, measured
+        # (red.global.add.v4.f32 54.0 G rows/s = 5.4 clocks per row and SM; the TMA path
+        # cp.reduce.async.bulk reaches the same 49-50 G rows/s, profiles/r02_microbench_tma_reduce.txt).
         corner_rows = 4.0 * dims['B'] * dims['Q'] * dims['M'] * dims['L'] * dims['P']
+        n_sms = torch.cuda.get_device_properties(device).multi_processor_count
 
         def onchip(ms, peak_rows, what, source, **extra):
             rate = corner_rows / (ms * 1e-3) / 1e9
             out = {'bound': what, 'achieved': rate, 'peak': peak_rows, 'unit': 'G rows/s (128-byte value rows)',
                    'frac': rate / peak_rows, 'rows_per_launch': corner_rows,
-                   'peak_source': 'micro-benchmark, ' + source}
+                   'peak_source': source}
             out.update(extra)
             return out
 
@@ -835,9 +867,12 @@ def main():
             'roofline_fwd': roof(ab['fwd'], fwd_ms, 'msda_fwd_rows_kernel'),
             'roofline_step': roof(ab['fwd'] + ab['bwd'], fwd_ms + zero_ms + bwd_ms, 'step'),
             'roofline_onchip': None if vdt != torch.float32 else {   # the peaks are fp32-row figures
-                'bwd': onchip(bwd_ms, 53.97, 'sm_to_l2_reduction', 'profiles/r01_microbench_scatter_rows.txt'),
-                'fwd': onchip(fwd_ms, 157.63, 'l1_gather', 'profiles/r01_microbench_gather_rows.txt',
-                              peak_if_l1_resident=259.55)},
+                'bwd': onchip(bwd_ms, 53.97, 'sm_to_l2_reduction',
+                              'micro-benchmark, profiles/r01_microbench_scatter_rows.txt'),
+                'fwd': onchip(fwd_ms, n_sms * (clock_info.get('sm_mhz') or 1965) * 1e-3, 'l1_data_path',
+                              'hardware: 128 B per clock and SM x %d SMs x sampled SM clock' % n_sms,
+                              measured_random_row_gather={'l2_resident': 157.63, 'l1_resident': 259.55,
+                                                          'source': 'profiles/r01_microbench_gather_rows.txt'})},
             'kernel_ms': {'fwd': fwd_ms, 'grad_value_zero_fill': zero_ms, 'bwd': bwd_ms,
                           'grad_value_zero_fill_folded_into_fwd': bool(fold_clear)},
             'kernel_families': {k: v for k, v in _capi.family_counts().items() if v},

@@ -690,19 +690,25 @@ class FlatGradients(object):
         the current stream has been given so far.  Called from the autograd hooks."""
         if not (self.overlap and self._distributed()):
             return
-        cur = torch.cuda.current_stream(self.flat.device)
-        if self._side is None:
-            self._side = torch.cuda.Stream(self.flat.device)
+        on_gpu = self.flat.is_cuda
+        if on_gpu:
+            cur = torch.cuda.current_stream(self.flat.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.flat.device)
         while self._launched < min(n_buckets, len(self.ranges)):
             a, b = self.ranges[self._launched]
             self._launched += 1
             if b == a:
                 continue
-            ready = torch.cuda.Event()
-            ready.record(cur)
-            self._side.wait_event(ready)
-            with torch.cuda.stream(self._side):
-                self._pending.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.AVG, async_op=True))
+            if on_gpu:
+                ready = torch.cuda.Event()
+                ready.record(cur)
+                self._side.wait_event(ready)
+                with torch.cuda.stream(self._side):
+                    self._pending.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.AVG,
+                                                         async_op=True))
+            else:       # CPU tensors (gloo, tests): no streams, no AVG — sum now, divide at the end
+                self._pending.append(dist.all_reduce(self.flat[a:b], async_op=True))
 
     def all_reduce_mean(self):
         """Finish the exchange: whatever has not been launched yet goes now (exposed), then the
@@ -710,6 +716,16 @@ class FlatGradients(object):
         if not self._distributed():
             return
         dev = self.flat.device
+        if not self.flat.is_cuda:
+            if self.overlap:
+                self.launch_through(len(self.ranges))
+                for work in self._pending:
+                    work.wait()
+                self._pending = []
+            else:
+                dist.all_reduce(self.flat)
+            self.flat.div_(dist.get_world_size())
+            return
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(torch.cuda.current_stream(dev))
         if self.overlap:

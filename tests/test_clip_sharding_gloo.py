@@ -114,3 +114,76 @@ def test_flat_gradient_bucket_all_reduce_gloo(tmp_path):
         assert r['views_ok'] and r['n'] == 6 * 5 + 5 * 2 + 2 == r['reduced'].numel()
         assert torch.allclose(r['reduced'], mean, rtol=1e-6, atol=1e-7)
     assert not torch.allclose(res[0]['local'], res[1]['local'])
+
+
+class _ThreeStageNet(torch.nn.Module):
+    """backbone -> encoder -> head, with the stage-boundary hooks of clip_model.PaveNetR50."""
+    grad_exchange = None
+
+    def __init__(self):
+        super().__init__()
+        self.backbone = torch.nn.Linear(6, 8)
+        self.encoder = torch.nn.Linear(8, 8)
+        self.head = torch.nn.Linear(8, 3)
+        self.launch_log = []
+
+    def gradient_buckets(self):
+        return [list(self.head.parameters()), list(self.encoder.parameters()),
+                list(self.backbone.parameters())]
+
+    def _hook(self, tensor, n):
+        ex = self.grad_exchange
+
+        def hook(grad):
+            self.launch_log.append((n, ex._launched))
+            ex.launch_through(n)
+        tensor.register_hook(hook)
+
+    def forward(self, x):
+        f = torch.relu(self.backbone(x))
+        self._hook(f, 2)                  # backward reaches the backbone: head + encoder done
+        e = torch.relu(self.encoder(f))
+        self._hook(e, 1)                  # backward reaches the encoder: head done
+        return self.head(e)
+
+
+def _bucket_worker(rank, world, port, out_dir):
+    """Stage buckets all-reduced from autograd hooks while the backward is still running
+    (clip_model.FlatGradients(overlap=True)); the result must equal the plain mean."""
+    from pavenet_b200 import clip_model
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port),
+                      RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        net = _ThreeStageNet()
+        flat = clip_model.FlatGradients(net, overlap=True)
+        assert net.grad_exchange is flat and len(flat.ranges) == 3
+        x = torch.randn(4, 6) * (rank + 1)
+        for _ in range(2):
+            flat.zero()
+            net.launch_log.clear()
+            net(x).square().sum().backward()
+            launched_in_backward = flat._launched
+            flat.all_reduce_mean()
+        ref = _ThreeStageNet()
+        ref.load_state_dict(net.state_dict())
+        ref.grad_exchange = type('No', (), {'_launched': 0, 'launch_through': lambda self, n: None})()
+        ref(x).square().sum().backward()
+        local = torch.cat([p.grad.reshape(-1) for b in ref.gradient_buckets() for p in b])
+        torch.save(dict(local=local, reduced=flat.flat.clone(), log=list(net.launch_log),
+                        launched_in_backward=launched_in_backward), os.path.join(out_dir, 'b%d.pt' % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_stage_buckets_overlap_gradient_exchange_gloo(tmp_path):
+    world = 2
+    mp.spawn(_bucket_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(os.path.join(str(tmp_path), 'b%d.pt' % r)) for r in range(world)]
+    mean = (res[0]['local'] + res[1]['local']) / 2
+    for r in res:
+        assert torch.allclose(r['reduced'], mean, rtol=1e-6, atol=1e-7)
+        # the head's bucket went out when the backward reached the encoder, the encoder's when it
+        # reached the backbone; only the backbone's bucket was left for after the backward
+        assert r['log'] == [(1, 0), (2, 1)] and r['launched_in_backward'] == 2

@@ -1,15 +1,25 @@
-"""Host<->device link bandwidth of this box: each direction alone, and both at once.
+"""Host<->device link bandwidth of this box: each direction alone, and both at once — for one
+GPU, or for all ranks of a torchrun launch AT THE SAME TIME (what the N-GPU `e2e` leg of bench.py
+does to the host: N x 239 MB up and N x 239 MB down per step through one host memory system).
 
-The end-to-end (`e2e`) bench number moves 239 MB up and 239 MB down per step; this tells how
-close its 6.5 ms is to what the link can do.  Pinned host memory, cudaMemcpyAsync on two streams.
+    python tools/pcie_duplex.py
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/pcie_duplex.py [--bind]
+
+--bind: pin each rank to the CPUs NVML reports as local to its GPU before allocating the pinned
+buffers (first touch then places them on that NUMA node), as bench.py does for its e2e leg.
+Pinned host memory, cudaMemcpyAsync on two streams; wall clock between barriers.
 """
+import os
+import sys
 import time
+
 import torch
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 MB = 1 << 20
 
 
-def run(nbytes, up, down, reps=10):
+def run(nbytes, up, down, barrier, reps=8):
     h_up = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
     h_dn = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
     d_up = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
@@ -18,6 +28,7 @@ def run(nbytes, up, down, reps=10):
     best = 1e9
     for _ in range(reps + 2):
         torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         if up:
             with torch.cuda.stream(s1):
@@ -31,7 +42,28 @@ def run(nbytes, up, down, reps=10):
 
 
 if __name__ == '__main__':
-    for mb in (12, 64, 239):
+    import bench
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    affinity = bench.bind_to_gpu_numa(local) if '--bind' in sys.argv else {'bound': False}
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        barrier = dist.barrier
+    else:
+        barrier = lambda: None     # noqa: E731
+    rows = []
+    for mb in (12, 239):
         n = mb * MB
-        print('%4d MiB  H2D alone %5.1f GB/s   D2H alone %5.1f GB/s   duplex %5.1f GB/s each way' %
-              (mb, run(n, True, False), run(n, False, True), run(n, True, True)), flush=True)
+        rows.append((mb, run(n, True, False, barrier), run(n, False, True, barrier),
+                     run(n, True, True, barrier)))
+    for r in range(world):
+        barrier()
+        if r == rank:
+            for mb, u, d, x in rows:
+                print('rank %d/%d  %4d MiB  H2D alone %5.1f GB/s   D2H alone %5.1f GB/s   duplex %5.1f GB/s each way   %s'
+                      % (rank, world, mb, u, d, x, affinity), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
