@@ -436,7 +436,7 @@ def measure_model_step(args, world, rank, local, steps, warmup):
         dist.barrier()
     clocks = ClockSampler(local)
     clocks.start()
-    launches0 = _capi.launch_count()
+    launches0 = _capi.launch_count() + model.library_launches_replayed()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     exposed = []
     e0.record()
@@ -469,7 +469,9 @@ def measure_model_step(args, world, rank, local, steps, warmup):
                        'bytes_all_reduced_per_step': 4 * n_params if world > 1 else 0,
                        'exposed_all_reduce_ms': exposed_ms,
                        'buckets': None if flat is None else [b - a for a, b in flat.ranges]},
-        'clocks': clock_info, 'gpu_launches': int(_capi.launch_count() - launches0),
+        # kernels of this repository's library: launched directly + replayed from CUDA graphs
+        'clocks': clock_info,
+        'gpu_launches': int(_capi.launch_count() + model.library_launches_replayed() - launches0),
         'final_loss': float(loss)}
     del model, opt, flat, ddp, batches
     torch.cuda.empty_cache()

@@ -417,6 +417,12 @@ class PaveNetR50(nn.Module):
                 return None
             tensor.register_hook(hook)
 
+    def library_launches_replayed(self):
+        """Kernels of libpavenet_msda.so launched through CUDA-graph replays so far (the
+        library's own counter only sees launches made outside graphs)."""
+        graphed = getattr(self, '_graphed', None) or {}
+        return sum(st.stats['library_launches_replayed'] for st in graphed.values())
+
     def _run_stage(self, name, fn, *args):
         graphed = getattr(self, '_graphed', None)
         if graphed is not None and self.training and torch.is_grad_enabled():
@@ -753,7 +759,12 @@ def train_step(model, optimizer, images, gt_kpts, gt_areas, ddp_model=None, flat
         flat_grads.zero()
     else:
         optimizer.zero_grad(set_to_none=True)
-    loss.backward()
+    if getattr(model, '_graphed', None) is not None:
+        from . import graphs
+        with graphs.quiet_accumulate_grad_stream_warning():
+            loss.backward()
+    else:
+        loss.backward()
     if flat_grads is not None:
         flat_grads.all_reduce_mean()
         torch.nn.utils.clip_grad_norm_(flat_grads.params, 0.1)

@@ -79,13 +79,14 @@ __device__ __forceinline__ void l2_prefetch_share(const void* base, long long by
 // --------------------------------------------------------------------------
 // forward
 // --------------------------------------------------------------------------
-template <int D, typename VT, class SRC, int BATCH, int MINB>
+template <int D, typename VT, class SRC, int BATCH, int MINB, int LB = 16>
 __global__ void __launch_bounds__(kFlatThreads, MINB)
 msda_fwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, SRC src0, float* __restrict__ out, Dims d,
                      int C, long long NC, uint4* __restrict__ clear, long long clear_n16,
                      long long prefetch_bytes) {
-  constexpr int VEC = Vec16<VT>::VEC;
+  using VLD = RowLoad<VT, LB>;
+  constexpr int VEC = VLD::VEC;
   constexpr int G = D / VEC;     // lanes per row
   constexpr int NG = 32 / G;     // row groups per warp: one chunk = NG groups x G samples = 32 samples
   static_assert(G >= BATCH && G % BATCH == 0, "BATCH must divide the group size");
@@ -114,7 +115,7 @@ msda_fwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   }
 
   const int LP = d.L * d.P;
-  const uint32_t lane_b = gl * 16;
+  const uint32_t lane_b = gl * LB;
   const uint32_t MDb = MD * sizeof(VT);
   int4* board = s_board[warp];
   auto unit_of = [](int j, int grp_, int half) { return j * (2 * NG + 1) + 2 * grp_ + half; };
@@ -183,10 +184,10 @@ msda_fwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
             const uint32_t xs = (q[t].y >> 31) & MDb;
             const char* sp = alive ? vrow : reinterpret_cast<const char*>(g_zero_row);
             const uint32_t o1 = (alive ? static_cast<uint32_t>(q[t].x) : 0u) + lane_b;
-            Vec16<VT>::load(reinterpret_cast<const VT*>(sp + o1), v[t][0]);
-            Vec16<VT>::load(reinterpret_cast<const VT*>(sp + (o1 + xs)), v[t][1]);
-            Vec16<VT>::load(reinterpret_cast<const VT*>(sp + (o1 + rs)), v[t][2]);
-            Vec16<VT>::load(reinterpret_cast<const VT*>(sp + (o1 + rs + xs)), v[t][3]);
+            VLD::load(reinterpret_cast<const VT*>(sp + o1), v[t][0]);
+            VLD::load(reinterpret_cast<const VT*>(sp + (o1 + xs)), v[t][1]);
+            VLD::load(reinterpret_cast<const VT*>(sp + (o1 + rs)), v[t][2]);
+            VLD::load(reinterpret_cast<const VT*>(sp + (o1 + rs + xs)), v[t][3]);
           }
 #pragma unroll
           for (int t = 0; t < BATCH; ++t) {
@@ -447,6 +448,16 @@ static cudaError_t launch_fwd_flat(const void* value, const int64_t* shapes, con
       case 3: MSDA_FWD_FLAT_LAUNCH((G >= 8 ? 8 : G), 1); break;
       case 4: MSDA_FWD_FLAT_LAUNCH(1, 4); break;
       case 5: MSDA_FWD_FLAT_LAUNCH(4, 3); break;
+      case 6:     // 256-bit value loads: 4 lanes per row, 8 rows per warp instruction
+        if ((reinterpret_cast<uintptr_t>(value) & 31u) == 0) {
+          msda_fwd_flat_kernel<D, VT, SRC, 2, 2, 32>
+              <<<static_cast<unsigned>(sm_count * 2), kFlatThreads, 0, st>>>(
+                  static_cast<const VT*>(value), shapes, lsi, src, out, d, C, NC,
+                  static_cast<uint4*>(clear), clear_n16, pf);
+          break;
+        }
+        MSDA_FWD_FLAT_LAUNCH(BATCH, kFlatBlocksPerSM);
+        break;
       default: MSDA_FWD_FLAT_LAUNCH(BATCH, kFlatBlocksPerSM); break;
     }
   } else {

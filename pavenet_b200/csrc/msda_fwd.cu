@@ -92,9 +92,9 @@ constexpr int kRowsWarps = kRowsThreads / 32;
 constexpr int fwd_min_blocks(int split) { return split > 1 ? 3 : 4; }
 
 // Shared-memory state of one rows block.
-template <int D, typename VT, int SPLIT>
+template <int D, typename VT, int SPLIT, int LB = 16>
 struct FwdRowsSmem {
-  static constexpr int VEC = Vec16<VT>::VEC;
+  static constexpr int VEC = RowLoad<VT, LB>::VEC;
   static constexpr int G = D / VEC;
   static constexpr int NGW = 32 / G;
   static constexpr int WSPLIT = SPLIT < NGW ? SPLIT : NGW;
@@ -108,12 +108,13 @@ struct FwdRowsSmem {
 // All rows of an item belong to ONE head and to neighbouring queries, so when neighbouring
 // queries look at neighbouring pixels (the encoder) their bilinear corners are the same
 // 128-byte rows and hit in L1.
-template <int D, typename VT, int SPLIT, class SRC>
+template <int D, typename VT, int SPLIT, class SRC, int LB = 16>
 __device__ __forceinline__ void fwd_rows_item(const VT* __restrict__ value, SRC src,
                                               float* __restrict__ out, const Dims& d,
-                                              FwdRowsSmem<D, VT, SPLIT>& sm, int m, int chunk,
+                                              FwdRowsSmem<D, VT, SPLIT, LB>& sm, int m, int chunk,
                                               int64_t b) {
-  constexpr int VEC = Vec16<VT>::VEC;
+  using VL = RowLoad<VT, LB>;
+  constexpr int VEC = VL::VEC;
   constexpr int G = D / VEC;  // lanes per row
   static_assert(D % VEC == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0, "bad D");
   constexpr int NGW = 32 / G;                            // row groups per warp
@@ -138,7 +139,7 @@ __device__ __forceinline__ void fwd_rows_item(const VT* __restrict__ value, SRC 
 
   // block-uniform base (batch entry, head) + this lane's 16-byte slot
   const char* vrow = reinterpret_cast<const char*>(value + b * d.S * MD + m * D);
-  const uint32_t lane_b = gl * 16;
+  const uint32_t lane_b = gl * LB;
   const uint32_t MDb = MD * sizeof(VT);
   const int LP = d.L * d.P;
   src.bind(unit, LP, d.M, b * d.Q + q_idx);
@@ -205,10 +206,10 @@ __device__ __forceinline__ void fwd_rows_item(const VT* __restrict__ value, SRC 
       const char* src = alive ? vrow : reinterpret_cast<const char*>(g_zero_row);
       const uint32_t o1 = (alive ? static_cast<uint32_t>(q.x) : 0u) + lane_b;
       float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
-      Vec16<VT>::load(reinterpret_cast<const VT*>(src + o1), v1);
-      Vec16<VT>::load(reinterpret_cast<const VT*>(src + (o1 + xs)), v2);
-      Vec16<VT>::load(reinterpret_cast<const VT*>(src + (o1 + rs)), v3);
-      Vec16<VT>::load(reinterpret_cast<const VT*>(src + (o1 + rs + xs)), v4);
+      VL::load(reinterpret_cast<const VT*>(src + o1), v1);
+      VL::load(reinterpret_cast<const VT*>(src + (o1 + xs)), v2);
+      VL::load(reinterpret_cast<const VT*>(src + (o1 + rs)), v3);
+      VL::load(reinterpret_cast<const VT*>(src + (o1 + rs + xs)), v4);
       const float w1 = __int_as_float(q.z), w2 = __int_as_float(q.w);
 #pragma unroll
       for (int c = 0; c < VEC; ++c) {
@@ -250,20 +251,20 @@ __device__ __forceinline__ void fwd_rows_item(const VT* __restrict__ value, SRC 
   }
 }
 
-template <int D, typename VT, int SPLIT, class SRC>
-__global__ void __launch_bounds__(kRowsThreads, fwd_min_blocks(SPLIT))
+template <int D, typename VT, int SPLIT, class SRC, int LB = 16>
+__global__ void __launch_bounds__(kRowsThreads, LB == 32 ? 3 : fwd_min_blocks(SPLIT))
 msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, SRC src, float* __restrict__ out, Dims d) {
-  __shared__ FwdRowsSmem<D, VT, SPLIT> sm;
+  __shared__ FwdRowsSmem<D, VT, SPLIT, LB> sm;
   const int MD = d.M * D;
   for (int l = threadIdx.x; l < d.L; l += blockDim.x) sm.lvl[l] = load_level(shapes, lsi, l, MD);
   __syncthreads();
-  constexpr int QPB = kRowsThreads / (D / Vec16<VT>::VEC) / SPLIT;
+  constexpr int QPB = kRowsThreads / (D / RowLoad<VT, LB>::VEC) / SPLIT;
   const int n_chunks = (d.Q + QPB - 1) / QPB;
   int blk = blockIdx.x;
   const int m = blk % d.M;
   blk /= d.M;
-  fwd_rows_item<D, VT, SPLIT, SRC>(value, src, out, d, sm, m, blk % n_chunks, blk / n_chunks);
+  fwd_rows_item<D, VT, SPLIT, SRC, LB>(value, src, out, d, sm, m, blk % n_chunks, blk / n_chunks);
 }
 
 // Forward variant 2 (large Q): persistent blocks, head-affine.  Every block of an SM serves
@@ -323,6 +324,18 @@ static cudaError_t launch_rows_split(const void* value, const int64_t* shapes, c
   constexpr int QPB = kRowsThreads / G / SPLIT;
   const int64_t blocks = static_cast<int64_t>(d.B) * ((d.Q + QPB - 1) / QPB) * d.M;
   if (blocks >= (int64_t(1) << 31)) return cudaErrorInvalidConfiguration;
+  // variant 3: 256-bit value loads (fp32, 32-byte aligned rows), 8 rows per warp instruction
+  if constexpr (SPLIT == 1 && std::is_same<VT, float>::value && D >= 32) {
+    if (tuning().fwd_variant == 3 && (reinterpret_cast<uintptr_t>(value) & 31u) == 0) {
+      constexpr int QPBW = kRowsThreads / (D / 8);
+      const int64_t wblocks = static_cast<int64_t>(d.B) * ((d.Q + QPBW - 1) / QPBW) * d.M;
+      msda_fwd_rows_kernel<D, VT, 1, SRC, 32><<<static_cast<unsigned>(wblocks), kRowsThreads, 0, st>>>(
+          static_cast<const VT*>(value), shapes, lsi, src, out, d);
+      note_launches(1);
+      note_kernel(std::is_same<SRC, FusedSource>::value ? KF_FWD_ROWS_FUSED : KF_FWD_ROWS);
+      return cudaGetLastError();
+    }
+  }
   if constexpr (SPLIT == 1) {
     const int resident = g_fwd_sm_count * fwd_min_blocks(1);
     if (tuning().fwd_variant == 2 && d.M <= 64 && blocks > 2 * resident) {

@@ -27,17 +27,18 @@ import torch.nn as nn
 
 from .functional import device_dropout_seed
 
-__all__ = ['GraphedStage', 'refresh_seed']
+__all__ = ['GraphedStage', 'refresh_seed', 'quiet_accumulate_grad_stream_warning']
 
 _SEED = {}
 _SALT = itertools.count(1)      # one dropout-seed salt per captured graph, process wide
 
 
 @contextlib.contextmanager
-def _quiet_accumulate_grad_stream_warning():
+def quiet_accumulate_grad_stream_warning():
     """Capture runs on a side stream, so the parameters' AccumulateGrad nodes (created earlier on
     the default stream) see gradients produced on another stream; autograd inserts the event
-    wait it needs and warns -- the wait is intended here.  Silenced for the capture only."""
+    wait it needs and warns -- the wait is intended here.  Silenced for the capture and for the
+    backward passes that replay captured stages (clip_model.train_step), not process wide."""
     setter = getattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch', None)
     if setter is None:
         yield
@@ -109,7 +110,9 @@ class GraphedStage(object):
         self.max_graphs, self.capture_after = max(1, int(max_graphs)), max(1, int(capture_after))
         self._graphs = collections.OrderedDict()
         self._seen = collections.Counter()
-        self.stats = {'captures': 0, 'evictions': 0, 'eager_calls': 0, 'replays': 0}
+        self.stats = {'captures': 0, 'evictions': 0, 'eager_calls': 0, 'replays': 0,
+                      'library_launches_replayed': 0}
+        self._launches = {}           # signature -> library kernel launches per forward+backward replay
 
     def _signature(self, args, static):
         training = tuple(m.training for m in self.modules)
@@ -127,6 +130,7 @@ class GraphedStage(object):
         if graphed is not None:
             self._graphs.move_to_end(key)
             self.stats['replays'] += 1
+            self.stats['library_launches_replayed'] += self._launches.get(key, 0)
             return graphed(*args)
         self._seen[key] += 1
         if len(self._seen) > 64 * self.max_graphs:      # the counter itself stays bounded
@@ -137,16 +141,21 @@ class GraphedStage(object):
                 return self.fn(*args, static=static)
             return self.fn(*args)
         while len(self._graphs) >= self.max_graphs:
-            self._graphs.popitem(last=False)             # frees that graph's memory pool
+            old, _ = self._graphs.popitem(last=False)    # frees that graph's memory pool
+            self._launches.pop(old, None)
             self.stats['evictions'] += 1
         stage = _Stage(self.fn, self.modules, self.params, _seed_tensor(args[0].device), static,
                        next(_SALT))
         # make_graphed_callables keys its replay on the wrapper's training flag; the wrapped
         # modules keep their own modes (frozen BatchNorm stays in eval)
         sample = tuple(a.detach().clone().requires_grad_(a.requires_grad) for a in args)
-        with _quiet_accumulate_grad_stream_warning():
+        from . import _capi
+        before = _capi.launch_count()
+        with quiet_accumulate_grad_stream_warning():
             graphed = torch.cuda.make_graphed_callables(stage, sample, num_warmup_iters=self.warmup_iters,
                                                         allow_unused_input=True)
+        # the warm-up iterations and the capture each ran the stage's forward + backward once
+        self._launches[key] = (_capi.launch_count() - before) // (self.warmup_iters + 1)
         self._graphs[key] = graphed
         self.stats['captures'] += 1
         return graphed(*args)

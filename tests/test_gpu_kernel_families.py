@@ -261,3 +261,18 @@ def test_large_q_kernel_variants_match_oracle(lib_options, variant):
     b = rgv.double()
     err = (gv.cpu().double() - b).abs() / (b.abs() + float(b.pow(2).mean().sqrt()))
     assert float(err.max()) < 1e-3
+
+
+def test_wide_load_forward_variants_match_oracle(lib_options):
+    """256-bit value loads (ld.global.nc.v8.f32): rows family (fwd_variant 3) on an encoder-like
+    problem, D = 32 and 64."""
+    from pavenet_b200 import _capi
+    lib_options('fwd_variant', 3)
+    lib_options('flat', 0)
+    for D, Q in ((32, 1111), (64, 700)):
+        prob = _problem(100 + D, 2, Q, 4, D, 4, MID)
+        before = _capi.family_counts()
+        out, gv, gl, ga = _run(*prob)
+        assert _delta(before, _capi.family_counts()) == {'fwd_rows': 1, 'bwd_rows': 1}
+        value, shapes_t, lsi, loc, aw, go = prob
+        assert rel_err(out, O.c_forward(value, shapes_t, lsi, loc, aw)) < 5e-6

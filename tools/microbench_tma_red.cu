@@ -18,6 +18,7 @@ constexpr int kRowsPerStage = 16;    // rows a warp stages per round (one lane i
 constexpr int kStages = 4;
 
 // MODE 0: red.global.add.v4.f32 (LSU)   1: TMA reduce, BYTES per op   2: TMA plain store
+// MODE 3: both at once -- every round a warp reduces 16 rows through the LSU AND 16 through the TMA
 template <int MODE, int BYTES>
 __global__ void __launch_bounds__(256) k(float* buf, uint32_t n_rows, uint32_t hot_rows, int rounds) {
   extern __shared__ __align__(128) float smem[];
@@ -26,7 +27,7 @@ __global__ void __launch_bounds__(256) k(float* buf, uint32_t n_rows, uint32_t h
   constexpr int kRowFloats = BYTES / 4;
   float* stage0 = smem + warp * (kStages * kRowsPerStage * kRowFloats);
   for (int it = 0; it < rounds; ++it) {
-    if (MODE == 0) {
+    if (MODE == 0 || MODE == 3) {
       // 16 rows per round like the TMA modes: 4 instructions x 4 rows
 #pragma unroll
       for (int j = 0; j < kRowsPerStage / 4; ++j) {
@@ -36,7 +37,8 @@ __global__ void __launch_bounds__(256) k(float* buf, uint32_t n_rows, uint32_t h
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row), "f"(1.f), "f"(2.f),
                      "f"(3.f), "f"(4.f) : "memory");
       }
-    } else {
+    }
+    if (MODE != 0) {
       float* stage = stage0 + (it % kStages) * (kRowsPerStage * kRowFloats);
       if (it >= kStages) {   // the bulk op that last read this stage must have finished reading
         if (lane < kRowsPerStage)
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(256) k(float* buf, uint32_t n_rows, uint32_t h
         if (BYTES > 128) r = r / (BYTES / 128) * (BYTES / 128);
         float* row = buf + (size_t)r * 32;
         const uint32_t s = (uint32_t)__cvta_generic_to_shared(stage + lane * kRowFloats);
-        if (MODE == 1)
+        if (MODE == 1 || MODE == 3)
           asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
                        ::"l"(row), "r"(s), "n"(BYTES) : "memory");
         else
@@ -69,15 +71,16 @@ __global__ void __launch_bounds__(256) k(float* buf, uint32_t n_rows, uint32_t h
 }
 
 template <int MODE, int BYTES>
-void run(const char* name, float* buf, uint32_t n_rows, uint32_t hot, int blocks_per_sm) {
+void run(const char* name, float* buf, uint32_t n_rows, uint32_t hot, int blocks_per_sm, int sm_div = 1) {
   int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  sms /= sm_div;     // sm_div > 1: only a fraction of the SMs issue (is the limit per SM or in L2?)
   const int block = 256, warps = block / 32;
   const size_t smem = (size_t)warps * kStages * kRowsPerStage * BYTES;
   cudaFuncSetAttribute(k<MODE, BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const unsigned grid = sms * blocks_per_sm;
   const long rows_total = 1L << 25;
   const int rounds = (int)(rows_total / ((long)grid * warps * kRowsPerStage));
-  const double rows_done = (double)rounds * grid * warps * kRowsPerStage * (BYTES / 128.0);
+  const double rows_done = (double)rounds * grid * warps * kRowsPerStage * (BYTES / 128.0) * (MODE == 3 ? 2 : 1);
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   k<MODE, BYTES><<<grid, block, smem>>>(buf, n_rows, hot, rounds);
   cudaError_t e = cudaDeviceSynchronize();
@@ -89,8 +92,8 @@ void run(const char* name, float* buf, uint32_t n_rows, uint32_t hot, int blocks
     cudaEventRecord(b); cudaEventSynchronize(b);
     float ms; cudaEventElapsedTime(&ms, a, b); if (ms < best) best = ms;
   }
-  printf("%-40s hot=%-6u blocks/SM=%d  %8.3f ms  %7.2f G rows(128B)/s  %8.1f GB/s payload  %5.2f clk/row/SM\n",
-         name, hot, blocks_per_sm, best, rows_done / best * 1e-6, rows_done * 128.0 / best * 1e-6,
+  printf("%-40s hot=%-6u SMs=%3d blocks/SM=%d  %8.3f ms  %7.2f G rows(128B)/s  %8.1f GB/s payload  %5.2f clk/row/SM\n",
+         name, hot, sms, blocks_per_sm, best, rows_done / best * 1e-6, rows_done * 128.0 / best * 1e-6,
          best * 1e-3 * 1.965e9 * sms / rows_done);
 }
 
@@ -103,9 +106,16 @@ int main() {
     for (int bps : {1, 2, 4}) {
       run<0, 128>("red.global.add.v4.f32 (LSU)", buf, n_rows, hot, bps);
       run<1, 128>("cp.reduce.async.bulk add.f32 128 B", buf, n_rows, hot, bps);
-      run<1, 512>("cp.reduce.async.bulk add.f32 512 B", buf, n_rows, hot, bps);
+      run<3, 128>("LSU red + TMA reduce together", buf, n_rows, hot, bps);
       run<2, 128>("cp.async.bulk store 128 B", buf, n_rows, hot, bps);
     }
+  }
+  // the same with half / a quarter of the SMs issuing: a per-SM limit halves the total, an L2-side
+  // limit leaves it where it was
+  for (int div : {2, 4}) {
+    run<0, 128>("red.global.add.v4.f32 (LSU)", buf, n_rows, 0u, 2, div);
+    run<1, 128>("cp.reduce.async.bulk add.f32 128 B", buf, n_rows, 0u, 2, div);
+    run<3, 128>("LSU red + TMA reduce together", buf, n_rows, 0u, 2, div);
   }
   return 0;
 }
