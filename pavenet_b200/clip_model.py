@@ -272,13 +272,22 @@ class PaveNetR50(nn.Module):
 
     # ------------------------------------------------------------------ graph
     def extract_feat(self, images):                   # (Bc, T, 3, H, W) -> 4 levels of (Bc*T, 256, h, w)
+        return list(self._stage_top(*self._stage_trunk(images)))
+
+    # The backbone is two stages so that the gradient exchange can overlap with it: when the
+    # backward leaves `top` (layer4 + neck, 71 % of the backbone's parameters) that bucket is
+    # all-reduced underneath the backward of `trunk` (layer2-3 over the full-resolution maps).
+    def _stage_trunk(self, images):                   # -> c3 (stride 8), c4 (stride 16)
         x = images.flatten(0, 1).contiguous(memory_format=torch.channels_last)
         with torch.no_grad():
             x = self._res_layer(self.layer1, self._stem(x))
         c3 = self._res_layer(self.layer2, x)
         c4 = self._res_layer(self.layer3, c3)
+        return c3, c4
+
+    def _stage_top(self, c3, c4):                     # -> the 4 levels of (Bc*T, 256, h, w)
         c5 = self._res_layer(self.layer4, c4)
-        return [l(c) for l, c in zip(self.lateral, (c3, c4, c5))] + [self.extra(c5)]
+        return tuple([l(c) for l, c in zip(self.lateral, (c3, c4, c5))] + [self.extra(c5)])
 
     @staticmethod
     def reference_grid(shapes_list, device):
@@ -321,9 +330,6 @@ class PaveNetR50(nn.Module):
         return geo
 
     # ---- the three static-shape stages (eager, or one CUDA graph each: enable_graphs) ----
-    def _stage_backbone(self, images):
-        return tuple(self.extract_feat(images))
-
     def _stage_encoder(self, f0, f1, f2, f3, p0, p1, p2, p3, mask_flat, ref_enc, shapes, lsi):
         feats, pos_sine = (f0, f1, f2, f3), (p0, p1, p2, p3)
         pos = torch.cat([(p + self.level_embeds[i].view(1, -1, 1, 1)).flatten(2)
@@ -375,12 +381,14 @@ class PaveNetR50(nn.Module):
         if not enabled:
             self._graphed = None
             return self
-        mods_backbone = [self.stem, self.layer1, self.layer2, self.layer3, self.layer4, self.lateral, self.extra]
+        mods_trunk = [self.stem, self.layer1, self.layer2, self.layer3]
+        mods_top = [self.layer4, self.lateral, self.extra]
         mods_decoder = [self.enc_output, self.enc_output_norm, self.cls_branches, self.kpt_branches,
                         self.sigma_branches, self.pre_kpt_branches, self.next_kpt_branches, self.decoder,
                         self.query_embedding]
         self._graphed = dict(
-            backbone=graphs.GraphedStage(self._stage_backbone, mods_backbone),
+            trunk=graphs.GraphedStage(self._stage_trunk, mods_trunk),
+            top=graphs.GraphedStage(self._stage_top, mods_top),
             encoder=graphs.GraphedStage(self._stage_encoder, [self.encoder], [self.level_embeds]),
             decoder=graphs.GraphedStage(self._stage_decoder, mods_decoder),
             # keyed on the per-clip matched-person counts (data dependent): capture a count pattern
@@ -396,16 +404,18 @@ class PaveNetR50(nn.Module):
 
     def gradient_buckets(self):
         """Trainable parameters in the order the backward pass completes their gradients:
-        [everything after the encoder (pose decoder, heads, joint decoder) | encoder | backbone]."""
-        backbone = [self.stem, self.layer1, self.layer2, self.layer3, self.layer4, self.lateral, self.extra]
-        in_backbone = {id(p) for m in backbone for p in m.parameters()}
+        [everything after the encoder (pose decoder, heads, joint decoder) | encoder |
+         backbone top (layer4 + neck) | backbone trunk (layer2-3)]."""
+        in_trunk = {id(p) for m in (self.stem, self.layer1, self.layer2, self.layer3) for p in m.parameters()}
+        in_top = {id(p) for m in (self.layer4, self.lateral, self.extra) for p in m.parameters()}
         in_encoder = {id(p) for p in self.encoder.parameters()} | {id(self.level_embeds)}
-        late, enc, back = [], [], []
+        late, enc, top, trunk = [], [], [], []
         for p in self.parameters():
             if not p.requires_grad:
                 continue
-            (back if id(p) in in_backbone else enc if id(p) in in_encoder else late).append(p)
-        return [late, enc, back]
+            (trunk if id(p) in in_trunk else top if id(p) in in_top else enc if id(p) in in_encoder
+             else late).append(p)
+        return [late, enc, top, trunk]
 
     def _exchange_hook(self, tensor, n_buckets):
         """When the gradient of `tensor` (a stage boundary) is ready, the stages behind it have
@@ -435,7 +445,9 @@ class PaveNetR50(nn.Module):
         T = self.T
         geo = self._geometry(images)
         shapes, lsi, mask_flat = geo['shapes'], geo['lsi'], geo['mask_flat']
-        feats = self._run_stage('backbone', self._stage_backbone, images)
+        c3, c4 = self._run_stage('trunk', self._stage_trunk, images)
+        self._exchange_hook(c4, 3)             # backward reaches the trunk: decoders, encoder, top done
+        feats = self._run_stage('top', self._stage_top, c3, c4)
         if [tuple(f.shape[-2:]) for f in feats] != geo['shapes_list']:
             raise RuntimeError('backbone produced %r, expected %r'
                                % ([tuple(f.shape[-2:]) for f in feats], geo['shapes_list']))
@@ -654,11 +666,11 @@ def synthetic_clip_batch(clips, device, seed, height=800, width=1333, num_frames
 class FlatGradients(object):
     """Every trainable parameter's .grad is a view into ONE flat fp32 buffer, laid out in the
     order in which the backward pass completes the gradients: [joint decoder + pose decoder +
-    heads | encoder | backbone].  The clip-sharded step exchanges the buffer bucket by bucket
+    heads | encoder | backbone top | backbone trunk].  The clip-sharded step exchanges the buffer bucket by bucket
     with NCCL all-reduces on a side stream, each launched from an autograd hook the moment the
-    stage before it (in backward order) has finished, so the exchange of the decoders' and the
-    encoder's gradients runs underneath the encoder's / backbone's backward and only the last
-    bucket is exposed.  No hooks or buckets on the parameters themselves, which keeps the step
+    stage before it (in backward order) has finished, so the exchange of the decoders', the
+    encoder's and the backbone top's gradients runs underneath the rest of the backward and only
+    the last bucket (layer2-3, 17 % of the bytes) is exposed.  No hooks or buckets on the parameters themselves, which keeps the step
     compatible with the CUDA-graphed stages (autograd accumulates into the views in place).
     The reference's equivalent is MMDistributedDataParallel, i.e. torch DDP's bucketed,
     backward-overlapped all-reduce (opera/apis/train.py:153-162,

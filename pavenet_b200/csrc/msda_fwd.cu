@@ -251,8 +251,8 @@ __device__ __forceinline__ void fwd_rows_item(const VT* __restrict__ value, SRC 
   }
 }
 
-template <int D, typename VT, int SPLIT, class SRC, int LB = 16>
-__global__ void __launch_bounds__(kRowsThreads, LB == 32 ? 3 : fwd_min_blocks(SPLIT))
+template <int D, typename VT, int SPLIT, class SRC, int LB = 16, int MINB = (LB == 32 ? 3 : fwd_min_blocks(SPLIT))>
+__global__ void __launch_bounds__(kRowsThreads, MINB)
 msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, SRC src, float* __restrict__ out, Dims d) {
   __shared__ FwdRowsSmem<D, VT, SPLIT, LB> sm;
@@ -326,11 +326,16 @@ static cudaError_t launch_rows_split(const void* value, const int64_t* shapes, c
   if (blocks >= (int64_t(1) << 31)) return cudaErrorInvalidConfiguration;
   // variant 3: 256-bit value loads (fp32, 32-byte aligned rows), 8 rows per warp instruction
   if constexpr (SPLIT == 1 && std::is_same<VT, float>::value && D >= 32) {
-    if (tuning().fwd_variant == 3 && (reinterpret_cast<uintptr_t>(value) & 31u) == 0) {
+    if ((tuning().fwd_variant == 3 || tuning().fwd_variant == 4) &&
+        (reinterpret_cast<uintptr_t>(value) & 31u) == 0) {
       constexpr int QPBW = kRowsThreads / (D / 8);
       const int64_t wblocks = static_cast<int64_t>(d.B) * ((d.Q + QPBW - 1) / QPBW) * d.M;
-      msda_fwd_rows_kernel<D, VT, 1, SRC, 32><<<static_cast<unsigned>(wblocks), kRowsThreads, 0, st>>>(
-          static_cast<const VT*>(value), shapes, lsi, src, out, d);
+      if (tuning().fwd_variant == 4)      // 64 registers, four blocks per SM
+        msda_fwd_rows_kernel<D, VT, 1, SRC, 32, 4><<<static_cast<unsigned>(wblocks), kRowsThreads, 0, st>>>(
+            static_cast<const VT*>(value), shapes, lsi, src, out, d);
+      else
+        msda_fwd_rows_kernel<D, VT, 1, SRC, 32, 3><<<static_cast<unsigned>(wblocks), kRowsThreads, 0, st>>>(
+            static_cast<const VT*>(value), shapes, lsi, src, out, d);
       note_launches(1);
       note_kernel(std::is_same<SRC, FusedSource>::value ? KF_FWD_ROWS_FUSED : KF_FWD_ROWS);
       return cudaGetLastError();
