@@ -1,60 +1,71 @@
 """Run under torchrun (N >= 2): the stage-bucketed, backward-overlapped gradient exchange
 (clip_model.FlatGradients(overlap=True)) gives the same averaged gradients as ONE all-reduce of
 the flat buffer after the backward, on the real clip model (small images), eager and graphed.
+One configuration per process (CUDA-graph capture does not like a process that has already run
+other models' collectives on the legacy stream); rank 0 compares the saved buffers at the end.
 
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_overlap.py
+    TR="python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1"
+    for m in flat_eager overlap_eager overlap_graphs flat_graphs; do $TR tools/check_overlap.py $m; done
+    python tools/check_overlap.py compare
 """
+import glob
 import os
 import sys
 
 import torch
-import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+OUT = '/tmp/check_overlap'
+mode = sys.argv[1] if len(sys.argv) > 1 else 'compare'
+
+if mode == 'compare':
+    ref = torch.load(os.path.join(OUT, 'flat_eager_r0.pt'))
+    ok = True
+    for f in sorted(glob.glob(os.path.join(OUT, '*_r0.pt'))):
+        d = torch.load(f)
+        err = float((d['flat'] - ref['flat']).abs().max() / ref['flat'].abs().max())
+        name = os.path.basename(f)[:-6]
+        expect = d['buckets'] - 1 if name.startswith('overlap') else 0
+        # run-to-run noise of the step itself (floating-point atomics) is ~3e-3 of the largest gradient
+        good = err < 1e-2 and d['launched'] == expect
+        ok = ok and good
+        print('%-16s buckets launched inside the backward: %d of %d   max err vs flat/eager %.2e   %s'
+              % (name, d['launched'], d['buckets'], err, 'ok' if good else 'MISMATCH'))
+    print('OK' if ok else 'MISMATCH')
+    sys.exit(0 if ok else 1)
+
+import torch.distributed as dist  # noqa: E402
 from pavenet_b200 import clip_model  # noqa: E402
 
+overlap, graphs = mode.startswith('overlap'), mode.endswith('graphs')
 rank, local = int(os.environ['RANK']), int(os.environ['LOCAL_RANK'])
 torch.cuda.set_device(local)
-dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 dev = torch.device('cuda', local)
-
-
-def grads(overlap, graphs):
-    torch.manual_seed(0)
-    model = clip_model.PaveNetR50(num_query=50).to(dev).train()
-    for m in model.modules():
-        if isinstance(m, torch.nn.Dropout):
-            m.p = 0.0
-        if isinstance(m, torch.nn.MultiheadAttention):
-            m.dropout = 0.0
-        if hasattr(m, 'ffn_drop'):
-            m.ffn_drop = 0.0
-    for p in model.parameters():
-        dist.broadcast(p.data, 0)
-    if graphs:
-        model.enable_graphs()
-    flat = clip_model.FlatGradients(model, overlap=overlap)
-    batch = clip_model.synthetic_clip_batch(1, dev, seed=7 + rank, height=256, width=352)
-    for _ in range(4 if graphs else 1):          # graphed: let every stage capture first
-        flat.zero()
-        losses = model(*batch)
-        sum(losses.values()).backward()
-        launched = flat._launched
-        flat.all_reduce_mean()
-    torch.cuda.synchronize()
-    return flat.flat.clone(), launched, len(flat.ranges) - 1
-
-
-ref, _, _ = grads(False, False)
-ok = True
-for overlap, graphs in ((True, False), (True, True), (False, True)):
-    g, launched, expect = grads(overlap, graphs)
-    err = float((g - ref).abs().max() / ref.abs().max())
-    print('rank %d overlap=%s graphs=%s  buckets launched inside backward: %d   max err vs flat/eager %.2e'
-          % (rank, overlap, graphs, launched, err), flush=True)
-    # run-to-run noise of the step itself (floating-point atomics) is ~3e-3 of the largest gradient
-    ok = ok and err < 1e-2 and (launched == expect if overlap else launched == 0)
-if rank == 0:
-    print('OK' if ok else 'MISMATCH', flush=True)
+dist.init_process_group('nccl', device_id=dev)
+torch.manual_seed(0)
+model = clip_model.PaveNetR50(num_query=50).to(dev).train()
+for m in model.modules():
+    if isinstance(m, torch.nn.Dropout):
+        m.p = 0.0
+    if isinstance(m, torch.nn.MultiheadAttention):
+        m.dropout = 0.0
+    if hasattr(m, 'ffn_drop'):
+        m.ffn_drop = 0.0
+for p in model.parameters():
+    dist.broadcast(p.data, 0)
+if graphs:
+    model.enable_graphs()
+flat = clip_model.FlatGradients(model, overlap=overlap)
+batch = clip_model.synthetic_clip_batch(1, dev, seed=7 + rank, height=256, width=352)
+for _ in range(4 if graphs else 1):          # graphed: let every stage capture first
+    flat.zero()
+    losses = model(*batch)
+    sum(losses.values()).backward()
+    launched = flat._launched
+    flat.all_reduce_mean()
+torch.cuda.synchronize()
+os.makedirs(OUT, exist_ok=True)
+torch.save(dict(flat=flat.flat.cpu(), launched=launched, buckets=len(flat.ranges)),
+           os.path.join(OUT, '%s_r%d.pt' % (mode, rank)))
+dist.barrier()
 dist.destroy_process_group()
-sys.exit(0 if ok else 1)
