@@ -568,9 +568,10 @@ def main():
     ap.add_argument('--workload', default='encoder_cfg2',
                     choices=sorted(WORKLOADS) + list(MODEL_WORKLOADS))
     ap.add_argument('--value-dtype', default='f32', choices=['f32', 'bf16'])
-    ap.add_argument('--grad-exchange', default='overlap', choices=['overlap', 'flat', 'ddp'],
-                    help='pavenet_step: stage buckets all-reduced underneath the backward (default), one all-reduce '
-                         'of the flat gradient buffer after the backward, or torch DDP')
+    ap.add_argument('--grad-exchange', default='flat', choices=['flat', 'overlap', 'ddp'],
+                    help='pavenet_step: one all-reduce of the flat gradient buffer after the backward (default: '
+                         'measured fastest at N=8, profiles/r02_multi_gpu.txt), stage buckets all-reduced '
+                         'underneath the backward, or torch DDP')
     ap.add_argument('--model-steps', type=int, default=-1,
                     help='op workloads: also time this many steps of the clip-sharded PAVE-Net R-50 training step '
                          '(BASELINE config 4, NCCL gradient all-reduce) and append it as `pavenet_step`; '

@@ -94,7 +94,7 @@ int msda_set_option(const char *name, int value);
  * to check is the one that ran.  Families: 0 generic forward, 1 generic backward, 2 rows
  * forward, 3 rows backward, 4 / 5 the same with the fused prologue, 6 flat (small-Q)
  * forward, 7 flat backward, 8 / 9 the same fused, 10 tcgen05 linear, 11 its weight
- * gradient, 12 column sums, 13 LayerNorm, 14 tile-aggregating backward.  Unknown codes: 0. */
+ * gradient, 12 column sums, 13 LayerNorm, 14 tile-staged (shared-memory) forward.  Unknown codes: 0. */
 uint64_t msda_launch_count_family(int family);
 
 /* Name of the kernel family the dispatcher would use for this problem

@@ -137,7 +137,7 @@ def launch_count():
 #: kernel families of msda_launch_count_family (include/pavenet_msda.h)
 KERNEL_FAMILIES = ('fwd_generic', 'bwd_generic', 'fwd_rows', 'bwd_rows', 'fwd_rows_fused',
                    'bwd_rows_fused', 'fwd_flat', 'bwd_flat', 'fwd_flat_fused', 'bwd_flat_fused',
-                   'linear', 'linear_wgrad', 'colsum', 'layernorm', 'bwd_tile')
+                   'linear', 'linear_wgrad', 'colsum', 'layernorm', 'fwd_tile')
 
 
 def family_counts():

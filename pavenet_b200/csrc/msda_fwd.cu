@@ -418,6 +418,11 @@ cudaError_t launch_forward(const void* value, const int64_t* shapes, const int64
     src.loc = static_cast<const float*>(loc);
     src.aw = static_cast<const float*>(aw);
     float* outf = static_cast<float*>(out);
+    if (tile_forward_eligible(d, dtype, value_dtype) && (reinterpret_cast<uintptr_t>(value) & 15u) == 0) {
+      const cudaError_t ce = clear_by_memset(clear, clear_bytes, st);
+      if (ce != cudaSuccess) return ce;
+      return launch_forward_tile(value, shapes, lsi, loc, aw, out, d, sm_count, st);
+    }
     if (flat_preferred(d, d.D / (value_dtype == MSDA_F32 ? 4 : 8), sm_count))
       return launch_forward_flat(value, shapes, lsi, src, outf, d, value_dtype, sm_count,
                                  (clear_bytes % 16 == 0) ? clear : nullptr, clear_bytes, st) ;

@@ -26,7 +26,7 @@ struct Tuning {
   int l2_prefetch_mb = 120;  // ... when value is at most this many MiB
   int agg_min_level = 0;   // bwd_variant 2: aggregate from this level on (0 = every level)
   int bwd_variant = 0;   // large-Q backward: 0 default, 1 plain rows, 2 warp-aggregated, 3 tile
-  int fwd_variant = 0;   // large-Q forward: 0 default, 1 plain rows, 2 ...
+  int fwd_variant = 0;   // large-Q forward: 0 default, 2 head-affine, 3 / 4 256-bit loads, 5 shared-memory tiles
 };
 const Tuning& tuning();
 
@@ -38,7 +38,7 @@ int choose_split(const Dims& d, int G, int sm_count);
 enum KernelFamily {
   KF_FWD_GENERIC = 0, KF_BWD_GENERIC, KF_FWD_ROWS, KF_BWD_ROWS, KF_FWD_ROWS_FUSED,
   KF_BWD_ROWS_FUSED, KF_FWD_FLAT, KF_BWD_FLAT, KF_FWD_FLAT_FUSED, KF_BWD_FLAT_FUSED,
-  KF_LINEAR, KF_LINEAR_WGRAD, KF_COLSUM, KF_LAYERNORM, KF_BWD_TILE, KF_COUNT
+  KF_LINEAR, KF_LINEAR_WGRAD, KF_COLSUM, KF_LAYERNORM, KF_FWD_TILE, KF_COUNT
 };
 void note_kernel(int family);
 
@@ -48,6 +48,12 @@ cudaError_t launch_forward(const void* value, const int64_t* shapes, const int64
                            const void* loc, const void* aw, void* out, const Dims& d, int dtype,
                            int value_dtype, int sm_count, int force_generic, void* clear,
                            size_t clear_bytes, cudaStream_t st);
+
+// tile-staged encoder forward (msda_fwd_tile.cu)
+bool tile_forward_eligible(const Dims& d, int dtype, int value_dtype);
+cudaError_t launch_forward_tile(const void* value, const int64_t* shapes, const int64_t* lsi,
+                                const void* loc, const void* aw, void* out, const Dims& d,
+                                int sm_count, cudaStream_t st);
 
 // flat small-Q family (msda_flat.cu)
 bool flat_preferred(const Dims& d, int G, int sm_count);

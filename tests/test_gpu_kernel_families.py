@@ -276,3 +276,36 @@ def test_wide_load_forward_variants_match_oracle(lib_options):
         assert _delta(before, _capi.family_counts()) == {'fwd_rows': 1, 'bwd_rows': 1}
         value, shapes_t, lsi, loc, aw, go = prob
         assert rel_err(out, O.c_forward(value, shapes_t, lsi, loc, aw)) < 5e-6
+
+
+@pytest.mark.parametrize('levels', [[(50, 84), (25, 42), (13, 21), (7, 11)], [(37, 53), (19, 27), (10, 14), (5, 7)],
+                                    [(64, 64), (32, 32)]])
+def test_tile_staged_forward_matches_oracle(lib_options, levels):
+    """fwd_variant 5: level windows staged in shared memory (msda_fwd_tile.cu).  Encoder geometry
+    (queries = pixels), coherent locations with offsets up to ~12 px so that part of the samples
+    falls outside the staged windows (global-memory path) and part outside the maps."""
+    from pavenet_b200 import _capi
+    lib_options('fwd_variant', 5)
+    lib_options('flat', 0)
+    g = torch.Generator().manual_seed(len(levels))
+    shapes_t = torch.tensor(levels, dtype=torch.long)
+    lsi = O.level_start_index(shapes_t)
+    S = int(shapes_t.prod(1).sum())
+    B, M, D, L, P, Q = 2, 8, 32, len(levels), 4, S
+    ref = []
+    for h, w in levels:
+        ys = (torch.arange(h, dtype=torch.float32) + 0.5) / h
+        xs = (torch.arange(w, dtype=torch.float32) + 0.5) / w
+        yy, xx = torch.meshgrid(ys, xs, indexing='ij')
+        ref.append(torch.stack([xx.reshape(-1), yy.reshape(-1)], -1))
+    ref = torch.cat(ref)
+    norm = torch.tensor([[w, h] for h, w in levels], dtype=torch.float32)
+    off = torch.randn(B, Q, M, L, P, 2, generator=g) * 3.0
+    loc = ref[None, :, None, None, None, :] + off / norm[None, None, None, :, None, :]
+    value = torch.randn(B, S, M, D, generator=g)
+    aw = torch.softmax(torch.randn(B, Q, M, L * P, generator=g), -1).view(B, Q, M, L, P)
+    go = torch.randn(B, Q, M * D, generator=g)
+    before = _capi.family_counts()
+    out, gv, gl, ga = _run(value, shapes_t, lsi, loc, aw, go)
+    assert _delta(before, _capi.family_counts()) == {'fwd_tile': 1, 'bwd_rows': 1}
+    assert rel_err(out, O.c_forward(value, shapes_t, lsi, loc, aw)) < 5e-6

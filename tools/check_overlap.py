@@ -5,7 +5,7 @@ One configuration per process (CUDA-graph capture does not like a process that h
 other models' collectives on the legacy stream); rank 0 compares the saved buffers at the end.
 
     TR="python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1"
-    for m in flat_eager overlap_eager overlap_graphs flat_graphs; do $TR tools/check_overlap.py $m; done
+    for m in flat_eager overlap_eager; do $TR tools/check_overlap.py $m; done
     python tools/check_overlap.py compare
 """
 import glob
