@@ -280,12 +280,14 @@ def test_wide_load_forward_variants_match_oracle(lib_options):
 
 @pytest.mark.parametrize('levels', [[(50, 84), (25, 42), (13, 21), (7, 11)], [(37, 53), (19, 27), (10, 14), (5, 7)],
                                     [(64, 64), (32, 32)]])
-def test_tile_staged_forward_matches_oracle(lib_options, levels):
-    """fwd_variant 5: level windows staged in shared memory (msda_fwd_tile.cu).  Encoder geometry
-    (queries = pixels), coherent locations with offsets up to ~12 px so that part of the samples
-    falls outside the staged windows (global-memory path) and part outside the maps."""
+@pytest.mark.parametrize('variant', [5, 6])
+def test_tile_staged_forward_matches_oracle(lib_options, levels, variant):
+    """fwd_variant 5: level windows staged in shared memory (msda_fwd_tile.cu); 6: the same
+    patch-per-block walk on cached global loads.  Encoder geometry (queries = pixels), coherent
+    locations with offsets up to ~12 px so that part of the samples falls outside the staged
+    windows (global-memory path) and part outside the maps."""
     from pavenet_b200 import _capi
-    lib_options('fwd_variant', 5)
+    lib_options('fwd_variant', variant)
     lib_options('flat', 0)
     g = torch.Generator().manual_seed(len(levels))
     shapes_t = torch.tensor(levels, dtype=torch.long)
