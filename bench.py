@@ -2,7 +2,7 @@
 """bench.py — throughput of the multi-scale deformable attention hot path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload encoder_cfg2|pose_cfg3|pose_cfg3_t3|petr_cfg1|stress_cfg5]
+                    [--workload encoder_cfg2|pose_cfg3|pose_cfg3_t3|petr_cfg1|stress_cfg5|stress_cfg5_big]
                     [--value-dtype f32|bf16]
 
 A "step" is one forward + backward pass of the op over one clip of synthetic,
@@ -60,6 +60,8 @@ WORKLOADS = {
                       Q=300, P=17, levels=R50_LEVELS, kind='pose'),
     'stress_cfg5': dict(desc='encoder stress: 8 frames at 800x1333, 4 levels x 4 points', B=8, T=1,
                         Q=None, P=4, levels=R50_LEVELS, kind='encoder'),
+    'stress_cfg5_big': dict(desc='encoder stress: 8 frames at 1200x2000 (Swin-L high-res), 4 levels x 4 points',
+                            B=8, T=1, Q=None, P=4, levels=BIG_LEVELS, kind='encoder'),
 }
 M_HEADS, D_HEAD = 8, 32
 MODEL_WORKLOADS = ('pavenet_step',)

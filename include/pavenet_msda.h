@@ -156,7 +156,7 @@ int msda_backward(const void *d_value, const int64_t *d_spatial_shapes,
  *   d_ref_points (B,Q,L,R,2)    reference points, R = ref_points_per_level = 1 or P
  *   d_scale      (B,Q,L,2)      offset scale, or NULL for 1/(W_l, H_l)
  * and the kernels compute  loc = ref + off * scale  and  w = softmax(logits)
- * over L*P themselves.  fp32 only; channels must be 32 (MSDA_ERR_UNSUPPORTED
+ * over L*P themselves.  fp32 only; channels must be 16, 32 or 64 (MSDA_ERR_UNSUPPORTED
  * otherwise — callers then fall back to msda_forward / msda_backward).
  * d_softmax_stats (B,Q,M,2) is written by the forward (row max, 1/sum) and
  * read by the backward, which also takes the forward's d_output: the softmax

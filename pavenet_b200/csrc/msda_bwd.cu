@@ -434,14 +434,13 @@ cudaError_t launch_backward(const void* value, const int64_t* shapes, const int6
   return cudaGetLastError();
 }
 
-// fused epilogue: D = 32, fp32 gradients, fp32 or bf16 value
+// fused epilogue: D in {16, 32, 64}, fp32 gradients, fp32 or bf16 value
 cudaError_t launch_backward_fused(const void* value, const int64_t* shapes, const int64_t* lsi,
                                   const FusedSource& src, const float* out, const float* grad_out,
                                   float* grad_value, float* grad_off, float* grad_logit,
                                   float* grad_loc, const Dims& d, int value_dtype, int sm_count,
                                   cudaStream_t st) {
-  if (d.D != 32 || d.L > kMaxSmemLevels || !out) return cudaErrorNotSupported;
-  if (value_dtype != MSDA_F32 && value_dtype != MSDA_BF16) return cudaErrorNotSupported;
+  if (!rows_supported(d.D, value_dtype) || d.L > kMaxSmemLevels || !out) return cudaErrorNotSupported;
   FusedIO io;
   io.out = out;
   io.src = src;
@@ -450,15 +449,25 @@ cudaError_t launch_backward_fused(const void* value, const int64_t* shapes, cons
   io.grad_logit = grad_logit;
   io.grad_loc = grad_loc;
   io.dot = 0.f;
-  if (flat_preferred(d, 8, sm_count))
+  const int G = d.D / 4;     // fp32 gradients: 4 channels per lane whatever the value type
+  if (flat_preferred(d, G, sm_count))
     return launch_backward_flat_fused(value, shapes, lsi, io, grad_out, grad_value, d, value_dtype,
                                       sm_count, st);
-  if (value_dtype == MSDA_F32)
-    return launch_bwd_rows<32, float, float, FusedIO>(value, shapes, lsi, io, grad_out, grad_value,
-                                                      d, choose_bwd_split(d, 8, sm_count), st);
-  if (value_dtype == MSDA_BF16)
-    return launch_bwd_rows<32, __nv_bfloat16, float, FusedIO>(
-        value, shapes, lsi, io, grad_out, grad_value, d, choose_bwd_split(d, 8, sm_count), st);
+  const int split = choose_bwd_split(d, G, sm_count);
+#define MSDA_FUSED_CASE(DD)                                                                          \
+  case DD:                                                                                           \
+    return value_dtype == MSDA_F32                                                                   \
+               ? launch_bwd_rows<DD, float, float, FusedIO>(value, shapes, lsi, io, grad_out,        \
+                                                            grad_value, d, split, st)                \
+               : launch_bwd_rows<DD, __nv_bfloat16, float, FusedIO>(value, shapes, lsi, io, grad_out, \
+                                                                    grad_value, d, split, st);
+  switch (d.D) {
+    MSDA_FUSED_CASE(16)
+    MSDA_FUSED_CASE(32)
+    MSDA_FUSED_CASE(64)
+    default: break;
+  }
+#undef MSDA_FUSED_CASE
   return cudaErrorNotSupported;
 }
 

@@ -298,7 +298,7 @@ int msda_fused_forward(const void* d_value, const int64_t* d_spatial_shapes,
                                              d_output, d, value_dtype, sms, d_clear, clear_bytes,
                                              static_cast<cudaStream_t>(stream));
   if (e == cudaErrorNotSupported)
-    return fail(MSDA_ERR_UNSUPPORTED, "msda_fused_forward: only channels == 32 and <= %d levels",
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_fused_forward: only channels in {16, 32, 64} and <= %d levels",
                 kMaxSmemLevels);
   if (e != cudaSuccess)
     return fail(MSDA_ERR_CUDA, "msda_fused_forward launch failed: %s", cudaGetErrorString(e));
@@ -338,7 +338,7 @@ int msda_fused_backward(const void* d_value, const int64_t* d_spatial_shapes,
       d_grad_offsets, d_grad_logits, d_grad_loc, d, value_dtype, sms,
       static_cast<cudaStream_t>(stream));
   if (e == cudaErrorNotSupported)
-    return fail(MSDA_ERR_UNSUPPORTED, "msda_fused_backward: only channels == 32 and <= %d levels",
+    return fail(MSDA_ERR_UNSUPPORTED, "msda_fused_backward: only channels in {16, 32, 64} and <= %d levels",
                 kMaxSmemLevels);
   if (e != cudaSuccess)
     return fail(MSDA_ERR_CUDA, "msda_fused_backward launch failed: %s", cudaGetErrorString(e));

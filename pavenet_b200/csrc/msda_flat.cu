@@ -526,12 +526,21 @@ cudaError_t launch_forward_flat_fused(const void* value, const int64_t* shapes, 
                                       const FusedSource& src, float* out, const Dims& d,
                                       int value_dtype, int sm_count, void* clear,
                                       size_t clear_bytes, cudaStream_t st) {
-  if (d.D != 32) return cudaErrorNotSupported;
-  return value_dtype == MSDA_F32
-             ? launch_fwd_flat<32, float, FusedSource>(value, shapes, lsi, src, out, d, sm_count,
-                                                       clear, clear_bytes, st)
-             : launch_fwd_flat<32, __nv_bfloat16, FusedSource>(value, shapes, lsi, src, out, d,
-                                                               sm_count, clear, clear_bytes, st);
+#define MSDA_FLAT_CASE(DD)                                                                        \
+  case DD:                                                                                        \
+    return value_dtype == MSDA_F32                                                                \
+               ? launch_fwd_flat<DD, float, FusedSource>(value, shapes, lsi, src, out, d, sm_count, \
+                                                         clear, clear_bytes, st)                  \
+               : launch_fwd_flat<DD, __nv_bfloat16, FusedSource>(value, shapes, lsi, src, out, d, \
+                                                                 sm_count, clear, clear_bytes, st);
+  switch (d.D) {
+    MSDA_FLAT_CASE(16)
+    MSDA_FLAT_CASE(32)
+    MSDA_FLAT_CASE(64)
+    default: break;
+  }
+#undef MSDA_FLAT_CASE
+  return cudaErrorNotSupported;
 }
 
 cudaError_t launch_backward_flat(const void* value, const int64_t* shapes, const int64_t* lsi,
@@ -562,12 +571,23 @@ cudaError_t launch_backward_flat_fused(const void* value, const int64_t* shapes,
                                        const int64_t* lsi, const FusedIO& io,
                                        const float* grad_out, float* grad_value, const Dims& d,
                                        int value_dtype, int sm_count, cudaStream_t st) {
-  if (d.D != 32 || !io.out) return cudaErrorNotSupported;
-  return value_dtype == MSDA_F32
-             ? launch_bwd_flat<32, float, float, FusedIO>(value, shapes, lsi, io, grad_out,
-                                                          grad_value, d, sm_count, st)
-             : launch_bwd_flat<32, __nv_bfloat16, float, FusedIO>(value, shapes, lsi, io, grad_out,
-                                                                  grad_value, d, sm_count, st);
+  if (!io.out) return cudaErrorNotSupported;
+#define MSDA_FLAT_CASE(DD)                                                                         \
+  case DD:                                                                                         \
+    return value_dtype == MSDA_F32                                                                 \
+               ? launch_bwd_flat<DD, float, float, FusedIO>(value, shapes, lsi, io, grad_out,      \
+                                                            grad_value, d, sm_count, st)           \
+               : launch_bwd_flat<DD, __nv_bfloat16, float, FusedIO>(value, shapes, lsi, io,        \
+                                                                    grad_out, grad_value, d,       \
+                                                                    sm_count, st);
+  switch (d.D) {
+    MSDA_FLAT_CASE(16)
+    MSDA_FLAT_CASE(32)
+    MSDA_FLAT_CASE(64)
+    default: break;
+  }
+#undef MSDA_FLAT_CASE
+  return cudaErrorNotSupported;
 }
 
 }  // namespace msda

@@ -473,24 +473,31 @@ cudaError_t launch_forward(const void* value, const int64_t* shapes, const int64
   return cudaGetLastError();
 }
 
-// fused prologue: D = 32 only (PAVE-Net's head size), fp32 or bf16 value
+// fused prologue: D in {16, 32, 64}, fp32 or bf16 value
 cudaError_t launch_forward_fused(const void* value, const int64_t* shapes, const int64_t* lsi,
                                  const FusedSource& src, float* out, const Dims& d, int value_dtype,
                                  int sm_count, void* clear, size_t clear_bytes, cudaStream_t st) {
   g_fwd_sm_count = sm_count;
-  if (d.D != 32 || d.L > kMaxSmemLevels) return cudaErrorNotSupported;
-  if (value_dtype != MSDA_F32 && value_dtype != MSDA_BF16) return cudaErrorNotSupported;
-  if (flat_preferred(d, value_dtype == MSDA_F32 ? 8 : 4, sm_count))
+  if (!rows_supported(d.D, value_dtype) || d.L > kMaxSmemLevels) return cudaErrorNotSupported;
+  const int vec = value_dtype == MSDA_F32 ? 4 : 8;
+  if (flat_preferred(d, d.D / vec, sm_count))
     return launch_forward_flat_fused(value, shapes, lsi, src, out, d, value_dtype, sm_count,
                                      (clear_bytes % 16 == 0) ? clear : nullptr, clear_bytes, st);
   const cudaError_t ce = clear_by_memset(clear, clear_bytes, st);
   if (ce != cudaSuccess) return ce;
-  if (value_dtype == MSDA_F32)
-    return launch_rows<32, float, FusedSource>(value, shapes, lsi, src, out, d,
-                                               choose_split(d, 8, sm_count), st);
-  if (value_dtype == MSDA_BF16)
-    return launch_rows<32, __nv_bfloat16, FusedSource>(value, shapes, lsi, src, out, d,
-                                                       choose_split(d, 4, sm_count), st);
+  const int split = choose_split(d, d.D / vec, sm_count);
+#define MSDA_FUSED_CASE(DD)                                                                        \
+  case DD:                                                                                         \
+    return value_dtype == MSDA_F32                                                                 \
+               ? launch_rows<DD, float, FusedSource>(value, shapes, lsi, src, out, d, split, st)   \
+               : launch_rows<DD, __nv_bfloat16, FusedSource>(value, shapes, lsi, src, out, d, split, st);
+  switch (d.D) {
+    MSDA_FUSED_CASE(16)
+    MSDA_FUSED_CASE(32)
+    MSDA_FUSED_CASE(64)
+    default: break;
+  }
+#undef MSDA_FUSED_CASE
   return cudaErrorNotSupported;
 }
 

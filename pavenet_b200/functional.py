@@ -407,8 +407,8 @@ class HostWorkspace(object):
 # ---------------------------------------------------------------------------
 def fused_supported(value, offsets):
     """True when `FusedMultiScaleDeformableAttnFunction` has a kernel for these
-    tensors (CUDA, fp32 projections, fp32/bf16 value, 32 channels per head)."""
-    return (value.is_cuda and offsets.is_cuda and value.dim() == 4 and value.shape[-1] == 32
+    tensors (CUDA, fp32 projections, fp32/bf16 value, 16 / 32 / 64 channels per head)."""
+    return (value.is_cuda and offsets.is_cuda and value.dim() == 4 and value.shape[-1] in (16, 32, 64)
             and offsets.dtype == torch.float32
             and value.dtype in (torch.float32, torch.bfloat16)
             and offsets.dim() == 6 and 0 < offsets.shape[3] <= 64
@@ -458,13 +458,13 @@ class FusedMultiScaleDeformableAttnFunction(Function):
     written to or re-read from HBM.
 
     Args:
-        value (bs, num_keys, heads, 32), fp32 or bf16
+        value (bs, num_keys, heads, D), D in {16, 32, 64}, fp32 or bf16
         spatial_shapes (L, 2) int64, level_start_index (L,) int64, on the GPU
         offsets (bs, Q, heads, L, P, 2) fp32 — raw `sampling_offsets` output
         logits (bs, Q, heads, L*P) fp32 — raw `attention_weights` output
         ref_points (bs, Q, L, R, 2) fp32, R = 1 (one reference per level) or P (one per point)
         scale (bs, Q, L, 2) fp32 or None
-    Returns (bs, Q, heads*32).
+    Returns (bs, Q, heads*D).
     """
 
     @staticmethod
@@ -474,7 +474,7 @@ class FusedMultiScaleDeformableAttnFunction(Function):
         R = ref_points.shape[3]
         if not fused_supported(value, offsets):
             raise RuntimeError('fused deformable attention: unsupported tensors '
-                               '(need CUDA, fp32 projections, 32 channels per head)')
+                               '(need CUDA, fp32 projections, 16 / 32 / 64 channels per head)')
         if tuple(logits.shape) != (B, Q, M, L * P) or tuple(ref_points.shape) != (B, Q, L, R, 2) \
                 or R not in (1, P) or (scale is not None and tuple(scale.shape) != (B, Q, L, 2)):
             raise RuntimeError('fused deformable attention: inconsistent shapes value %s offsets %s '

@@ -164,12 +164,14 @@ def test_function_reuses_the_cleared_buffer_once():
 
 
 @pytest.mark.parametrize('flat', [2, 0])
-@pytest.mark.parametrize('Q,P,levels,R,with_scale', [
-    (40, 17, MID * 3, 17, True),      # pose decoder: one reference per point, box scale
-    (300, 4, MID, 1, False),          # encoder style: one reference per level, / (W, H)
-    (7, 15, MID * 5, 15, True),
+@pytest.mark.parametrize('Q,P,levels,R,with_scale,D', [
+    (40, 17, MID * 3, 17, True, 32),      # pose decoder: one reference per point, box scale
+    (300, 4, MID, 1, False, 32),          # encoder style: one reference per level, / (W, H)
+    (7, 15, MID * 5, 15, True, 32),
+    (90, 4, MID, 1, False, 16),           # other head sizes of the fused path
+    (33, 9, MID * 2, 9, True, 64),
 ])
-def test_fused_kernels_match_unfused_chain(lib_options, flat, Q, P, levels, R, with_scale):
+def test_fused_kernels_match_unfused_chain(lib_options, flat, Q, P, levels, R, with_scale, D):
     """softmax + location transform in the kernel (flat and rows families) against the
     op-by-op chain run through autograd on the plain op, all gradients."""
     import pavenet_b200
@@ -178,7 +180,7 @@ def test_fused_kernels_match_unfused_chain(lib_options, flat, Q, P, levels, R, w
     lib_options('flat', flat)
     g = torch.Generator().manual_seed(Q + P)
     shapes_t = torch.tensor(levels, dtype=torch.long)
-    L, B, M, D = len(levels), 2, 8, 32
+    L, B, M = len(levels), 2, 8
     S = int(shapes_t.prod(1).sum())
     lsi = O.level_start_index(shapes_t)
     dev = 'cuda'
