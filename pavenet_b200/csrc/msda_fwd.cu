@@ -423,9 +423,16 @@ cudaError_t launch_forward(const void* value, const int64_t* shapes, const int64
       if (ce != cudaSuccess) return ce;
       return launch_forward_tile(value, shapes, lsi, loc, aw, out, d, sm_count, st);
     }
-    if (flat_preferred(d, d.D / (value_dtype == MSDA_F32 ? 4 : 8), sm_count))
+    if (flat_preferred(d, d.D / (value_dtype == MSDA_F32 ? 4 : 8), sm_count)) {
+      // the persistent kernel folds the zero-fill in when it can be done in 16-byte stores
+      const bool fold = clear && clear_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(clear) & 15u) == 0;
+      if (!fold) {
+        const cudaError_t ce = clear_by_memset(clear, clear_bytes, st);
+        if (ce != cudaSuccess) return ce;
+      }
       return launch_forward_flat(value, shapes, lsi, src, outf, d, value_dtype, sm_count,
-                                 (clear_bytes % 16 == 0) ? clear : nullptr, clear_bytes, st) ;
+                                 fold ? clear : nullptr, fold ? clear_bytes : 0, st);
+    }
     const cudaError_t ce = clear_by_memset(clear, clear_bytes, st);
     if (ce != cudaSuccess) return ce;
 #define MSDA_ROWS_CASE(DD)                                                                   \
@@ -480,9 +487,15 @@ cudaError_t launch_forward_fused(const void* value, const int64_t* shapes, const
   g_fwd_sm_count = sm_count;
   if (!rows_supported(d.D, value_dtype) || d.L > kMaxSmemLevels) return cudaErrorNotSupported;
   const int vec = value_dtype == MSDA_F32 ? 4 : 8;
-  if (flat_preferred(d, d.D / vec, sm_count))
+  if (flat_preferred(d, d.D / vec, sm_count)) {
+    const bool fold = clear && clear_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(clear) & 15u) == 0;
+    if (!fold) {
+      const cudaError_t ce = clear_by_memset(clear, clear_bytes, st);
+      if (ce != cudaSuccess) return ce;
+    }
     return launch_forward_flat_fused(value, shapes, lsi, src, out, d, value_dtype, sm_count,
-                                     (clear_bytes % 16 == 0) ? clear : nullptr, clear_bytes, st);
+                                     fold ? clear : nullptr, fold ? clear_bytes : 0, st);
+  }
   const cudaError_t ce = clear_by_memset(clear, clear_bytes, st);
   if (ce != cudaSuccess) return ce;
   const int split = choose_split(d, d.D / vec, sm_count);

@@ -137,7 +137,7 @@ def test_forward_clear_zero_fills_the_buffer(lib_options):
     ref = O.c_forward(value, shapes_t, lsi, loc, aw)
     for flat in (2, 0):
         lib_options('flat', flat)
-        for n in (4, 1024, 4 * 1000 * 1000 + 4, 12345 * 4):
+        for n in (4, 1024, 4 * 1000 * 1000 + 4, 12345 * 4, 7, 1001):      # incl. sizes that are not 16-byte multiples
             buf = torch.full((n,), 3.0, device='cuda')
             guard = torch.full((64,), 5.0, device='cuda')
             out = ms_deform_attn_forward(*args, 64, clear=buf)
