@@ -48,6 +48,7 @@ static Tuning& tuning_mut() {
     if (x.copy_streams < 1) x.copy_streams = 1;
     if (x.copy_streams > 4) x.copy_streams = 4;
     x.flat = env_int("PAVENET_MSDA_FLAT", 1);
+    x.clear_mode = env_int("PAVENET_MSDA_CLEAR_MODE", x.clear_mode);
     x.l2_prefetch = env_int("PAVENET_MSDA_L2_PREFETCH", x.l2_prefetch);
     x.l2_prefetch_mb = env_int("PAVENET_MSDA_L2_PREFETCH_MB", x.l2_prefetch_mb);
     x.bwd_variant = env_int("PAVENET_MSDA_BWD_VARIANT", 0);
@@ -137,6 +138,54 @@ static bool entry_bytes_overflow(const Dims& d, int value_dtype) {
          (int64_t(1) << 31);
 }
 
+// ---- zero-fill on a side stream, concurrent with the forward kernel (knob clear_mode = 1) ----
+// fork: the side stream waits for everything enqueued on `st` so far (the buffer may be a block
+// the caller's allocator has just recycled from work still pending there), clears, and `st`
+// joins after the forward kernel has been enqueued, so the kernel and the memset overlap and
+// whatever the caller enqueues next (the backward) sees a cleared buffer.  One side stream and
+// one event pair per device, serialised by a mutex for the few host microseconds of the enqueue.
+// Capturable: the wait pulls the side stream into an ongoing capture (fork / join pattern).
+struct SideClear {
+  std::mutex mu;
+  cudaStream_t stream[64] = {};
+  cudaEvent_t fork[64] = {}, join[64] = {};
+  bool ready[64] = {};
+};
+static SideClear g_side;
+
+class SideClearScope {
+ public:
+  SideClearScope(void* clear, size_t bytes, cudaStream_t st) : st_(st) {
+    if (!clear || !bytes || tuning().clear_mode != 1) return;
+    if (cudaGetDevice(&dev_) != cudaSuccess || dev_ < 0 || dev_ >= 64) return;
+    g_side.mu.lock();
+    locked_ = true;
+    if (!g_side.ready[dev_]) {
+      if (cudaStreamCreateWithFlags(&g_side.stream[dev_], cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&g_side.fork[dev_], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&g_side.join[dev_], cudaEventDisableTiming) != cudaSuccess)
+        return;
+      g_side.ready[dev_] = true;
+    }
+    if (cudaEventRecord(g_side.fork[dev_], st) != cudaSuccess) return;
+    if (cudaStreamWaitEvent(g_side.stream[dev_], g_side.fork[dev_], 0) != cudaSuccess) return;
+    if (cudaMemsetAsync(clear, 0, bytes, g_side.stream[dev_]) != cudaSuccess) return;
+    if (cudaEventRecord(g_side.join[dev_], g_side.stream[dev_]) != cudaSuccess) return;
+    active_ = true;
+  }
+  // true: the clear is on its way, the launcher must not clear again
+  bool active() const { return active_; }
+  ~SideClearScope() {
+    if (active_) cudaStreamWaitEvent(st_, g_side.join[dev_], 0);
+    if (locked_) g_side.mu.unlock();
+  }
+
+ private:
+  cudaStream_t st_;
+  int dev_ = -1;
+  bool locked_ = false, active_ = false;
+};
+
 }  // namespace msda
 
 using namespace msda;
@@ -160,6 +209,7 @@ int msda_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "agg_min_level")) slot = &t.agg_min_level;
   else if (!std::strcmp(name, "flat_fwd_cfg")) slot = &t.flat_fwd_cfg;
   else if (!std::strcmp(name, "flat_bwd_cfg")) slot = &t.flat_bwd_cfg;
+  else if (!std::strcmp(name, "clear_mode")) slot = &t.clear_mode;
   else if (!std::strcmp(name, "l2_prefetch")) slot = &t.l2_prefetch;
   else if (!std::strcmp(name, "l2_prefetch_mb")) slot = &t.l2_prefetch_mb;
   else if (!std::strcmp(name, "bwd_variant")) slot = &t.bwd_variant;
@@ -215,10 +265,13 @@ int msda_forward_clear(const void* d_value, const int64_t* d_spatial_shapes,
   // ... and keep byte offsets inside a batch entry in 31 bits (the generic kernel indexes in int64)
   const int generic = tuning().force_generic || misaligned16(d_value) || misaligned16(d_output) ||
                       misaligned16(d_sampling_loc) || entry_bytes_overflow(d, value_dtype);
-  const cudaError_t e =
-      launch_forward(d_value, d_spatial_shapes, d_level_start_index, d_sampling_loc, d_attn_weight,
-                     d_output, d, dtype, value_dtype, sms, generic, d_clear, clear_bytes,
-                     static_cast<cudaStream_t>(stream));
+  cudaError_t e;
+  {
+    SideClearScope side(d_clear, clear_bytes, static_cast<cudaStream_t>(stream));
+    e = launch_forward(d_value, d_spatial_shapes, d_level_start_index, d_sampling_loc, d_attn_weight,
+                       d_output, d, dtype, value_dtype, sms, generic, side.active() ? nullptr : d_clear,
+                       side.active() ? 0 : clear_bytes, static_cast<cudaStream_t>(stream));
+  }
   if (e != cudaSuccess)
     return fail(MSDA_ERR_CUDA, "msda_forward launch failed: %s", cudaGetErrorString(e));
   return MSDA_OK;
@@ -294,9 +347,13 @@ int msda_fused_forward(const void* d_value, const int64_t* d_spatial_shapes,
   int sms = 0;
   rc = current_sm_count(&sms);
   if (rc) return rc;
-  const cudaError_t e = launch_forward_fused(d_value, d_spatial_shapes, d_level_start_index, src,
-                                             d_output, d, value_dtype, sms, d_clear, clear_bytes,
-                                             static_cast<cudaStream_t>(stream));
+  cudaError_t e;
+  {
+    SideClearScope side(d_clear, clear_bytes, static_cast<cudaStream_t>(stream));
+    e = launch_forward_fused(d_value, d_spatial_shapes, d_level_start_index, src, d_output, d,
+                             value_dtype, sms, side.active() ? nullptr : d_clear,
+                             side.active() ? 0 : clear_bytes, static_cast<cudaStream_t>(stream));
+  }
   if (e == cudaErrorNotSupported)
     return fail(MSDA_ERR_UNSUPPORTED, "msda_fused_forward: only channels in {16, 32, 64} and <= %d levels",
                 kMaxSmemLevels);

@@ -228,7 +228,10 @@ msda_fwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
 // --------------------------------------------------------------------------
 // backward
 // --------------------------------------------------------------------------
-template <int D, typename VT, typename GT, class IO, int BATCH, int MINB>
+// PIPE: the value rows of the next batch of samples are requested before the reductions of the
+// current batch are issued (their registers are free once the per-sample sums are formed), so
+// loads are in flight while the reductions drain instead of after them.
+template <int D, typename VT, typename GT, class IO, int BATCH, int MINB, bool PIPE = false>
 __global__ void __launch_bounds__(kFlatThreads, MINB)
 msda_bwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, IO io0, const float* __restrict__ grad_out,
@@ -326,61 +329,107 @@ msda_bwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
 #pragma unroll
       for (int j = 0; j < G; ++j) pw[j] = px[j] = py[j] = 0.f;
       const int nvalid = LP - (32 * k + grp * G);
+      // one batch = BATCH samples of this lane group: records, value rows, per-sample sums, reductions
+      auto read_recs = [&](int j0, int4 (&q)[BATCH], int2 (&ar)[BATCH]) {
 #pragma unroll
-      for (int j0 = 0; j0 < G; j0 += BATCH) {
-        if (j0 < nvalid) {
-          int4 q[BATCH];
-          int2 ar[BATCH];
-          float v[BATCH][4][VEC];
+        for (int t = 0; t < BATCH; ++t) {
+          q[t] = board[unit_of(j0 + t, grp, 0)];
+          ar[t] = *reinterpret_cast<const int2*>(&board[unit_of(j0 + t, grp, 1)]);
+        }
+      };
+      auto load_rows = [&](const int4 (&q)[BATCH], const int2 (&ar)[BATCH], float (&v)[BATCH][4][VEC]) {
 #pragma unroll
-          for (int t = 0; t < BATCH; ++t) {
-            q[t] = board[unit_of(j0 + t, grp, 0)];
-            ar[t] = *reinterpret_cast<const int2*>(&board[unit_of(j0 + t, grp, 1)]);
+        for (int t = 0; t < BATCH; ++t) {
+          const int meta = q[t].y;
+          const int rs = ar[t].y;
+          const VT* p = vbase + q[t].x;
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) v[t][0][i] = v[t][1][i] = v[t][2][i] = v[t][3][i] = 0.f;
+          if (meta & 1) VL::load(p, v[t][0]);
+          if (meta & 2) VL::load(p + MD, v[t][1]);
+          if (meta & 4) VL::load(p + rs, v[t][2]);
+          if (meta & 8) VL::load(p + rs + MD, v[t][3]);
+        }
+      };
+      auto sums = [&](int j0, const int4 (&q)[BATCH], const int2 (&ar)[BATCH],
+                      const float (&v)[BATCH][4][VEC]) {
+#pragma unroll
+        for (int t = 0; t < BATCH; ++t) {
+          const float a = __int_as_float(ar[t].x);
+          const float lh = __int_as_float(q[t].z), lw = __int_as_float(q[t].w);
+          const float hh = 1.f - lh, hw = 1.f - lw;
+          const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+          float sw = 0.f, sx = 0.f, sy = 0.f;
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            const float tg = g[i] * a;
+            const float val = w1 * v[t][0][i] + w2 * v[t][1][i] + w3 * v[t][2][i] + w4 * v[t][3][i];
+            const float gw = hh * (v[t][1][i] - v[t][0][i]) + lh * (v[t][3][i] - v[t][2][i]);
+            const float gh = hw * (v[t][2][i] - v[t][0][i]) + lw * (v[t][3][i] - v[t][1][i]);
+            sw += g[i] * val;
+            sx += gw * tg;
+            sy += gh * tg;
           }
+          pw[j0 + t] = sw; px[j0 + t] = sx; py[j0 + t] = sy;
+        }
+      };
+      auto scatter = [&](const int4 (&q)[BATCH], const int2 (&ar)[BATCH]) {
 #pragma unroll
-          for (int t = 0; t < BATCH; ++t) {
-            const int meta = q[t].y;
-            const int rs = ar[t].y;
-            const VT* p = vbase + q[t].x;
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) v[t][0][i] = v[t][1][i] = v[t][2][i] = v[t][3][i] = 0.f;
-            if (meta & 1) VL::load(p, v[t][0]);
-            if (meta & 2) VL::load(p + MD, v[t][1]);
-            if (meta & 4) VL::load(p + rs, v[t][2]);
-            if (meta & 8) VL::load(p + rs + MD, v[t][3]);
-          }
-#pragma unroll
-          for (int t = 0; t < BATCH; ++t) {
-            const int meta = q[t].y;
-            const int rs = ar[t].y;
-            const float a = __int_as_float(ar[t].x);
-            const float lh = __int_as_float(q[t].z), lw = __int_as_float(q[t].w);
-            const float hh = 1.f - lh, hw = 1.f - lw;
-            GT* gp = gvbase + q[t].x;
-            const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-            float sw = 0.f, sx = 0.f, sy = 0.f;
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-              const float tg = g[i] * a;
-              const float val = w1 * v[t][0][i] + w2 * v[t][1][i] + w3 * v[t][2][i] + w4 * v[t][3][i];
-              const float gw = hh * (v[t][1][i] - v[t][0][i]) + lh * (v[t][3][i] - v[t][2][i]);
-              const float gh = hw * (v[t][2][i] - v[t][0][i]) + lw * (v[t][3][i] - v[t][1][i]);
-              sw += g[i] * val;
-              sx += gw * tg;
-              sy += gh * tg;
-            }
-            pw[j0 + t] = sw; px[j0 + t] = sx; py[j0 + t] = sy;
-            float tt[VEC];
+        for (int t = 0; t < BATCH; ++t) {
+          const int meta = q[t].y;
+          const int rs = ar[t].y;
+          const float a = __int_as_float(ar[t].x);
+          const float lh = __int_as_float(q[t].z), lw = __int_as_float(q[t].w);
+          const float hh = 1.f - lh, hw = 1.f - lw;
+          GT* gp = gvbase + q[t].x;
+          float tt[VEC];
 #define MSDA_SCATTER(BIT, WK, PTR)                                              \
   if (meta & BIT) {                                                             \
     _Pragma("unroll") for (int i = 0; i < VEC; ++i) tt[i] = (WK) * a * g[i];   \
     red_add_row(PTR, tt);                                                       \
   }
-            MSDA_SCATTER(1, w1, gp)
-            MSDA_SCATTER(2, w2, gp + MD)
-            MSDA_SCATTER(4, w3, gp + rs)
-            MSDA_SCATTER(8, w4, gp + rs + MD)
+          MSDA_SCATTER(1, hh * hw, gp)
+          MSDA_SCATTER(2, hh * lw, gp + MD)
+          MSDA_SCATTER(4, lh * hw, gp + rs)
+          MSDA_SCATTER(8, lh * lw, gp + rs + MD)
 #undef MSDA_SCATTER
+        }
+      };
+      if constexpr (!PIPE) {
+#pragma unroll
+        for (int j0 = 0; j0 < G; j0 += BATCH) {
+          if (j0 < nvalid) {
+            int4 q[BATCH];
+            int2 ar[BATCH];
+            float v[BATCH][4][VEC];
+            read_recs(j0, q, ar);
+            load_rows(q, ar, v);
+            sums(j0, q, ar, v);
+            scatter(q, ar);
+          }
+        }
+      } else {
+        int4 q[BATCH], qn[BATCH];
+        int2 ar[BATCH], arn[BATCH];
+        float v[BATCH][4][VEC];
+        if (nvalid > 0) {
+          read_recs(0, q, ar);
+          load_rows(q, ar, v);
+        }
+#pragma unroll
+        for (int j0 = 0; j0 < G; j0 += BATCH) {
+          if (j0 < nvalid) {
+            sums(j0, q, ar, v);                       // v is free after this
+            const bool more = j0 + BATCH < G && j0 + BATCH < nvalid;
+            if (more) {
+              read_recs(j0 + BATCH < G ? j0 + BATCH : 0, qn, arn);
+              load_rows(qn, arn, v);                  // in flight while the reductions below drain
+            }
+            scatter(q, ar);
+            if (more) {
+#pragma unroll
+              for (int t = 0; t < BATCH; ++t) { q[t] = qn[t]; ar[t] = arn[t]; }
+            }
           }
         }
       }
@@ -490,6 +539,16 @@ static cudaError_t launch_bwd_flat(const void* value, const int64_t* shapes, con
       case 3: MSDA_BWD_FLAT_LAUNCH(4, 1); break;
       case 4: MSDA_BWD_FLAT_LAUNCH(1, 4); break;
       case 5: MSDA_BWD_FLAT_LAUNCH(4, 2); break;
+      case 6:     // software-pipelined: next batch's loads ahead of this batch's reductions
+        msda_bwd_flat_kernel<D, VT, GT, IO, 2, 2, true>
+            <<<static_cast<unsigned>(sm_count * 2), kFlatThreads, 0, st>>>(
+                static_cast<const VT*>(value), shapes, lsi, io, go, static_cast<GT*>(gv), d, C, NC, pf);
+        break;
+      case 7:
+        msda_bwd_flat_kernel<D, VT, GT, IO, 1, 3, true>
+            <<<static_cast<unsigned>(sm_count * 3), kFlatThreads, 0, st>>>(
+                static_cast<const VT*>(value), shapes, lsi, io, go, static_cast<GT*>(gv), d, C, NC, pf);
+        break;
       default: MSDA_BWD_FLAT_LAUNCH(BATCH, kFlatBlocksPerSM); break;
     }
   } else {
