@@ -49,6 +49,7 @@ static Tuning& tuning_mut() {
     if (x.copy_streams > 4) x.copy_streams = 4;
     x.flat = env_int("PAVENET_MSDA_FLAT", 1);
     x.clear_mode = env_int("PAVENET_MSDA_CLEAR_MODE", x.clear_mode);
+    x.flat_order = env_int("PAVENET_MSDA_FLAT_ORDER", x.flat_order);
     x.l2_prefetch = env_int("PAVENET_MSDA_L2_PREFETCH", x.l2_prefetch);
     x.l2_prefetch_mb = env_int("PAVENET_MSDA_L2_PREFETCH_MB", x.l2_prefetch_mb);
     x.bwd_variant = env_int("PAVENET_MSDA_BWD_VARIANT", 0);
@@ -209,6 +210,7 @@ int msda_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "agg_min_level")) slot = &t.agg_min_level;
   else if (!std::strcmp(name, "flat_fwd_cfg")) slot = &t.flat_fwd_cfg;
   else if (!std::strcmp(name, "flat_bwd_cfg")) slot = &t.flat_bwd_cfg;
+  else if (!std::strcmp(name, "flat_order")) slot = &t.flat_order;
   else if (!std::strcmp(name, "clear_mode")) slot = &t.clear_mode;
   else if (!std::strcmp(name, "l2_prefetch")) slot = &t.l2_prefetch;
   else if (!std::strcmp(name, "l2_prefetch_mb")) slot = &t.l2_prefetch_mb;

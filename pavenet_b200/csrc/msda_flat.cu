@@ -38,25 +38,48 @@ __device__ __forceinline__ void red_add_f4(float* p, float a, float b, float c, 
                : "memory");
 }
 
-// this warp's share of the optional zero-fill, spread over its n_iter chunk iterations
+// this warp's share of the optional zero-fill, spread over its n_iter chunk iterations (plain
+// streaming stores), or handed to the TMA engine up front (bulk stores from a zeroed tile of shared
+// memory: no LSU slots, no registers, the fill drains at DRAM write speed underneath the gathers)
+constexpr int kZeroTileBytes = 16384;
 struct ClearJob {
   uint4* base;       // NULL: nothing to clear
   long long begin;   // this warp's range, in 16-byte units
   long long end;
   long long step;    // units per chunk iteration
+  bool tma;
   __device__ __forceinline__ void bind(uint4* p, long long n16, long long w, long long W,
-                                       long long n_iter) {
+                                       long long n_iter, bool tma_) {
     base = p;
     begin = n16 * w / W;
     end = n16 * (w + 1) / W;
     step = (end - begin + n_iter - 1) / n_iter;
+    tma = tma_;
   }
   __device__ __forceinline__ void run(long long it, int lane) const {
-    if (!base) return;
+    if (!base || tma) return;
     const long long a = begin + step * it;
     const long long b = min(a + step, end);
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     for (long long i = a + lane; i < b; i += 32) __stcs(base + i, z);
+  }
+  // TMA form: lane 0 of the warp queues its whole share as bulk stores of the zero tile
+  __device__ __forceinline__ void issue_bulk(const uint4* zero_tile, int lane) const {
+    if (!base || !tma || lane != 0) return;
+    const uint32_t src = static_cast<uint32_t>(__cvta_generic_to_shared(zero_tile));
+    constexpr long long kTile16 = kZeroTileBytes / 16;
+    for (long long i = begin; i < end; i += kTile16) {
+      const uint32_t bytes = static_cast<uint32_t>(min(kTile16, end - i) * 16);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base + i),
+                   "r"(src), "r"(bytes)
+                   : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  // before the block may exit (its shared memory is the source of the queued stores)
+  __device__ __forceinline__ void drain_bulk(int lane) const {
+    if (!base || !tma || lane != 0) return;
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 };
 
@@ -84,7 +107,7 @@ __global__ void __launch_bounds__(kFlatThreads, MINB)
 msda_fwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, SRC src0, float* __restrict__ out, Dims d,
                      int C, long long NC, uint4* __restrict__ clear, long long clear_n16,
-                     long long prefetch_bytes) {
+                     long long prefetch_bytes, int clear_tma, int phase_align) {
   using VLD = RowLoad<VT, LB>;
   constexpr int VEC = VLD::VEC;
   constexpr int G = D / VEC;     // lanes per row
@@ -93,9 +116,14 @@ msda_fwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
 
   __shared__ LevelInfo s_lvl[kMaxSmemLevels];
   __shared__ int4 s_board[kFlatWarps][G * (2 * NG + 1)];
+  __shared__ __align__(128) uint4 s_zero[kZeroTileBytes / 16];   // source of the TMA zero-fill
 
   const int MD = d.M * D;
   for (int l = threadIdx.x; l < d.L; l += blockDim.x) s_lvl[l] = load_level(shapes, lsi, l, MD);
+  if (clear && clear_tma) {
+    for (int i = threadIdx.x; i < kZeroTileBytes / 16; i += blockDim.x) s_zero[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> TMA reads
+  }
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -108,9 +136,11 @@ msda_fwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   if (prefetch_bytes) l2_prefetch_share(value, prefetch_bytes, w, W, lane);
 
   ClearJob cj;
-  cj.bind(clear, clear_n16, w, W, c1 > c0 ? c1 - c0 : 1);
+  cj.bind(clear, clear_n16, w, W, c1 > c0 ? c1 - c0 : 1, clear_tma != 0);
+  cj.issue_bulk(s_zero, lane);
   if (c1 <= c0) {            // more warps than chunks: only the zero-fill share is left
     cj.run(0, lane);
+    cj.drain_bulk(lane);
     return;
   }
 
@@ -121,11 +151,18 @@ msda_fwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   auto unit_of = [](int j, int grp_, int half) { return j * (2 * NG + 1) + 2 * grp_ + half; };
   const FastDivP level_of(d.P);
 
-  long long c = c0;
-  while (c < c1) {
+  // Phase alignment: a piece usually starts inside a row (at chunk k0 > 0) and ends inside the next
+  // one.  Walking the part that starts at chunk 0 first makes every warp of the grid sweep the chunk
+  // index -- i.e. the frames / levels, the outer sample index -- upwards at the same time, so the
+  // grid's working set in L2 is about one frame of value (+ grad_value) instead of all of them.
+  const long long head_end = (phase_align && c0 % C != 0) ? min(c1, (c0 / C + 1) * C) : c0;
+  for (int pass = 0; pass < 2; ++pass) {
+  long long c = pass == 0 ? head_end : c0;
+  const long long ce = pass == 0 ? c1 : head_end;
+  while (c < ce) {
     const long long row = c / C;                 // (b*Q + q)*M + m
     const int k_first = static_cast<int>(c - row * C);
-    const int k_end = static_cast<int>(min(static_cast<long long>(C), k_first + (c1 - c)));
+    const int k_end = static_cast<int>(min(static_cast<long long>(C), k_first + (ce - c)));
     const int m = static_cast<int>(row % d.M);
     const long long bq = row / d.M;
     const long long b = bq / d.Q;
@@ -223,6 +260,8 @@ msda_fwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     }
     c += k_end - k_first;
   }
+  }
+  cj.drain_bulk(lane);
 }
 
 // --------------------------------------------------------------------------
@@ -236,7 +275,7 @@ __global__ void __launch_bounds__(kFlatThreads, MINB)
 msda_bwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, IO io0, const float* __restrict__ grad_out,
                      GT* __restrict__ grad_value, Dims d, int C, long long NC,
-                     long long prefetch_bytes) {
+                     long long prefetch_bytes, int phase_align) {
   using VL = BwdVec<VT, GT>;
   constexpr int VEC = VL::VEC;
   constexpr int G = D / VEC;
@@ -265,11 +304,18 @@ msda_bwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   auto unit_of = [](int j, int grp_, int half) { return j * (2 * NG + 1) + 2 * grp_ + half; };
   const FastDivP level_of(d.P);
 
-  long long c = c0;
-  while (c < c1) {
+  // Phase alignment: a piece usually starts inside a row (at chunk k0 > 0) and ends inside the next
+  // one.  Walking the part that starts at chunk 0 first makes every warp of the grid sweep the chunk
+  // index -- i.e. the frames / levels, the outer sample index -- upwards at the same time, so the
+  // grid's working set in L2 is about one frame of value (+ grad_value) instead of all of them.
+  const long long head_end = (phase_align && c0 % C != 0) ? min(c1, (c0 / C + 1) * C) : c0;
+  for (int pass = 0; pass < 2; ++pass) {
+  long long c = pass == 0 ? head_end : c0;
+  const long long ce = pass == 0 ? c1 : head_end;
+  while (c < ce) {
     const long long row = c / C;
     const int k_first = static_cast<int>(c - row * C);
-    const int k_end = static_cast<int>(min(static_cast<long long>(C), k_first + (c1 - c)));
+    const int k_end = static_cast<int>(min(static_cast<long long>(C), k_first + (ce - c)));
     const int m = static_cast<int>(row % d.M);
     const long long bq = row / d.M;
     const long long b = bq / d.Q;
@@ -441,6 +487,7 @@ msda_bwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     }
     c += k_end - k_first;
   }
+  }
 }
 
 // --------------------------------------------------------------------------
@@ -484,11 +531,13 @@ static cudaError_t launch_fwd_flat(const void* value, const int64_t* shapes, con
   constexpr int BATCH = G >= 4 ? 4 : G;
   const long long clear_n16 = static_cast<long long>(clear_bytes / 16);
   const long long pf = prefetch_bytes_for<VT>(d, 1);
+  const int clear_tma = tuning().clear_mode == 2;   // zero-fill by TMA bulk stores instead of STG
+  const int order = tuning().flat_order;
 #define MSDA_FWD_FLAT_LAUNCH(BATCH_, MINB_)                                                       \
   msda_fwd_flat_kernel<D, VT, SRC, BATCH_, MINB_>                                                 \
       <<<static_cast<unsigned>(sm_count * MINB_), kFlatThreads, 0, st>>>(                         \
           static_cast<const VT*>(value), shapes, lsi, src, out, d, C, NC,                         \
-          static_cast<uint4*>(clear), clear_n16, pf)
+          static_cast<uint4*>(clear), clear_n16, pf, clear_tma, order)
   // tuning sweep (knob flat_fwd_cfg), instantiated for the benchmark's kernel only
   if constexpr (D == 32 && std::is_same<VT, float>::value && std::is_same<SRC, PlainSource>::value) {
     switch (tuning().flat_fwd_cfg) {
@@ -502,7 +551,7 @@ static cudaError_t launch_fwd_flat(const void* value, const int64_t* shapes, con
           msda_fwd_flat_kernel<D, VT, SRC, 2, 2, 32>
               <<<static_cast<unsigned>(sm_count * 2), kFlatThreads, 0, st>>>(
                   static_cast<const VT*>(value), shapes, lsi, src, out, d, C, NC,
-                  static_cast<uint4*>(clear), clear_n16, pf);
+                  static_cast<uint4*>(clear), clear_n16, pf, clear_tma, order);
           break;
         }
         MSDA_FWD_FLAT_LAUNCH(BATCH, kFlatBlocksPerSM);
@@ -528,10 +577,11 @@ static cudaError_t launch_bwd_flat(const void* value, const int64_t* shapes, con
   constexpr int G = D / BwdVec<VT, GT>::VEC;
   constexpr int BATCH = G >= 2 ? 2 : 1;
   const long long pf = prefetch_bytes_for<VT>(d, 2);
+  const int order = tuning().flat_order;
 #define MSDA_BWD_FLAT_LAUNCH(BATCH_, MINB_)                                                       \
   msda_bwd_flat_kernel<D, VT, GT, IO, BATCH_, MINB_>                                              \
       <<<static_cast<unsigned>(sm_count * MINB_), kFlatThreads, 0, st>>>(                         \
-          static_cast<const VT*>(value), shapes, lsi, io, go, static_cast<GT*>(gv), d, C, NC, pf)
+          static_cast<const VT*>(value), shapes, lsi, io, go, static_cast<GT*>(gv), d, C, NC, pf, order)
   if constexpr (D == 32 && std::is_same<VT, float>::value && std::is_same<IO, PlainIO>::value) {
     switch (tuning().flat_bwd_cfg) {
       case 1: MSDA_BWD_FLAT_LAUNCH(1, 3); break;
@@ -542,12 +592,12 @@ static cudaError_t launch_bwd_flat(const void* value, const int64_t* shapes, con
       case 6:     // software-pipelined: next batch's loads ahead of this batch's reductions
         msda_bwd_flat_kernel<D, VT, GT, IO, 2, 2, true>
             <<<static_cast<unsigned>(sm_count * 2), kFlatThreads, 0, st>>>(
-                static_cast<const VT*>(value), shapes, lsi, io, go, static_cast<GT*>(gv), d, C, NC, pf);
+                static_cast<const VT*>(value), shapes, lsi, io, go, static_cast<GT*>(gv), d, C, NC, pf, order);
         break;
       case 7:
         msda_bwd_flat_kernel<D, VT, GT, IO, 1, 3, true>
             <<<static_cast<unsigned>(sm_count * 3), kFlatThreads, 0, st>>>(
-                static_cast<const VT*>(value), shapes, lsi, io, go, static_cast<GT*>(gv), d, C, NC, pf);
+                static_cast<const VT*>(value), shapes, lsi, io, go, static_cast<GT*>(gv), d, C, NC, pf, order);
         break;
       default: MSDA_BWD_FLAT_LAUNCH(BATCH, kFlatBlocksPerSM); break;
     }

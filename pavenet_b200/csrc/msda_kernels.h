@@ -22,8 +22,10 @@ struct Tuning {
   int flat = 1;          // flat small-Q kernels (msda_flat.cu): 0 never, 1 heuristic, 2 whenever legal
   int flat_fwd_cfg = 0;    // tuning sweep of the flat kernels (batch, blocks per SM), 0 = default
   int flat_bwd_cfg = 0;
+  int flat_order = 1;      // flat kernels: 1 = every warp walks its piece from chunk 0 upwards (frames in phase), 0 = in storage order
   int clear_mode = 0;      // msda_forward_clear: 0 fold into the flat kernel / memset ahead of the others,
-                           // 1 memset on a side stream concurrent with the forward kernel
+                           // 1 memset on a side stream concurrent with the forward kernel,
+                           // 2 flat kernel: TMA bulk stores of a zeroed shared-memory tile
   int l2_prefetch = 0;     // flat kernels stream value into L2 first: bit 0 forward, bit 1 backward
   int l2_prefetch_mb = 120;  // ... when value is at most this many MiB
   int agg_min_level = 0;   // bwd_variant 2: aggregate from this level on (0 = every level)

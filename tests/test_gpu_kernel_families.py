@@ -17,6 +17,7 @@ from oracle import msda_oracle as O
 pytestmark = pytest.mark.gpu
 
 MID = [(28, 40), (14, 20), (7, 10), (4, 5)]
+FLAT_ORDER_DEFAULT = 1   # library default of the flat kernels' piece order (msda_kernels.h)
 
 
 @pytest.fixture()
@@ -31,7 +32,7 @@ def lib_options():
 
     yield set_
     defaults = {'flat': 1, 'force_generic': 0, 'fwd_split': 0, 'bwd_split': 0,
-                'bwd_variant': 0, 'fwd_variant': 0}
+                'bwd_variant': 0, 'fwd_variant': 0, 'clear_mode': 0, 'flat_order': FLAT_ORDER_DEFAULT}
     for name in touched:
         _capi.set_option(name, defaults[name])
 
@@ -77,10 +78,13 @@ FLAT_SHAPES = [
 ]
 
 
+@pytest.mark.parametrize('order', [0, 1])
 @pytest.mark.parametrize('B,Q,M,D,P,shapes', FLAT_SHAPES)
-def test_flat_kernels_match_oracle(lib_options, B, Q, M, D, P, shapes):
+def test_flat_kernels_match_oracle(lib_options, B, Q, M, D, P, shapes, order):
+    """order 1: every warp walks its piece of the (row, chunk) space from chunk 0 upwards."""
     from pavenet_b200 import _capi
     lib_options('flat', 2)
+    lib_options('flat_order', order)
     prob = _problem(7 * Q + D, B, Q, M, D, P, shapes)
     before = _capi.family_counts()
     out, gv, gl, ga = _run(*prob)
@@ -135,13 +139,16 @@ def test_forward_clear_zero_fills_the_buffer(lib_options):
     value, shapes_t, lsi, loc, aw, _ = _problem(3, 1, 60, 8, 32, 17, MID * 2)
     args = (value.cuda(), shapes_t.cuda(), lsi.cuda(), loc.cuda(), aw.cuda())
     ref = O.c_forward(value, shapes_t, lsi, loc, aw)
-    for flat in (2, 0):
+    # clear_mode 0: streaming stores between the chunks of the flat kernel; 2: TMA bulk stores of a
+    # zeroed shared-memory tile queued at kernel start; 1: memset on a side stream
+    for flat, mode in ((2, 0), (2, 2), (2, 1), (0, 0)):
         lib_options('flat', flat)
+        lib_options('clear_mode', mode)
         for n in (4, 1024, 4 * 1000 * 1000 + 4, 12345 * 4, 7, 1001):      # incl. sizes that are not 16-byte multiples
             buf = torch.full((n,), 3.0, device='cuda')
             guard = torch.full((64,), 5.0, device='cuda')
             out = ms_deform_attn_forward(*args, 64, clear=buf)
-            assert float(buf.abs().max()) == 0.0, (flat, n)
+            assert float(buf.abs().max()) == 0.0, (flat, mode, n)
             assert float(guard.min()) == 5.0
             assert rel_err(out, ref) < 5e-6
 
