@@ -25,6 +25,11 @@ Prints ONE JSON line on stdout (rank 0).  Keys beyond the base contract:
                 the inputs and D2H of output and all gradients inside the timed
                 region, pipelined inside the library
   e2e_autograd  the same copies issued serially around the autograd Function
+  launch        how the timed steps were launched.  The small-Q (pose) workloads run 40-150 us of
+                kernels per step, less than the Python + ctypes cost of launching them one by one, so
+                their K steps are ALSO timed as replays of a CUDA graph holding `sets` steps (what the
+                library's own GraphedStage does for the pose decoder); `value` / `ms_per_step` then come
+                from that leg, `ms_per_step_eager` and the per-kernel event times from the eager leg
 Multi-GPU: clips are independent, so each rank runs its own clips (weak
 scaling) with no collective on the data path; one all-reduce(MAX) of the
 elapsed time at the end.
@@ -591,6 +596,13 @@ def main():
                     help='zero-fill grad_value inside the forward call (msda_forward_clear) instead of a '
                          'separate memset between forward and backward; auto = for the small-Q (pose) workloads, '
                          'whose persistent forward kernel folds the fill in')
+    ap.add_argument('--launch', default='auto', choices=['auto', 'eager', 'graph'],
+                    help='how the timed steps are launched: eager = one Python / C-ABI call per kernel with CUDA '
+                         'events around every kernel; graph = the same calls captured once into a CUDA graph '
+                         '(`sets` steps per graph) and replayed, which is what a launch-bound small-Q caller does '
+                         '(tools/exp_launch_bound.py: the host needs 45-57 us per step, PETR\'s kernels 39); '
+                         'auto = graph for the small-Q (pose) workloads.  The eager leg always runs: it provides '
+                         'the per-kernel times')
     ap.add_argument('--option', action='append', default=[], metavar='NAME=INT',
                     help='library kernel-selection knob (msda_set_option), e.g. flat=0, bwd_variant=2')
     args = ap.parse_args()
@@ -725,6 +737,48 @@ def main():
     launches = _capi.launch_count() - launches0
 
     elapsed_ms = t_start.elapsed_time(t_end)
+    eager_elapsed_ms = elapsed_ms
+    launch_mode = 'eager'
+    use_graph = args.launch == 'graph' or (args.launch == 'auto' and cfg['kind'] == 'pose')
+    if use_graph:
+        # second timed leg: the same K steps, captured `sets` at a time into one CUDA graph and replayed
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(args.sets):
+                step(i)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = _capi.launch_count()
+        with torch.cuda.graph(graph):
+            for i in range(args.sets):
+                step(i)
+        per_graph = _capi.launch_count() - n0
+        reps, rest = divmod(args.steps, args.sets)
+        for _ in range(max(3, -(-args.warmup // args.sets))):
+            graph.replay()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = ClockSampler(local)
+        clocks.start()
+        n0 = _capi.launch_count()
+        t_start.record()
+        for _ in range(reps):
+            graph.replay()
+        for i in range(rest):
+            step(i)
+        t_end.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clock_info = clocks.stop()
+        launches = reps * per_graph + (_capi.launch_count() - n0)   # replayed + directly launched
+        elapsed_ms = t_start.elapsed_time(t_end)
+        launch_mode = 'cuda_graph (%d steps per graph, %d replays + %d eager steps)' % (args.sets, reps, rest)
     fwd_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
     zero_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
     bwd_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
@@ -870,7 +924,10 @@ def main():
             'footprint_gb_per_gpu': footprint / 1e9,
             'roofline': roof(ab['bwd'], bwd_ms, 'msda_bwd_rows_kernel'),
             'roofline_fwd': roof(ab['fwd'], fwd_ms, 'msda_fwd_rows_kernel'),
-            'roofline_step': roof(ab['fwd'] + ab['bwd'], fwd_ms + zero_ms + bwd_ms, 'step'),
+            'roofline_step': roof(ab['fwd'] + ab['bwd'],
+                                  elapsed_max / args.steps if use_graph else fwd_ms + zero_ms + bwd_ms, 'step'),
+            'launch': launch_mode,
+            'ms_per_step_eager': eager_elapsed_ms / args.steps,
             'roofline_onchip': None if vdt != torch.float32 else {   # the peaks are fp32-row figures
                 'bwd': onchip(bwd_ms, 53.97, 'sm_to_l2_reduction',
                               'micro-benchmark, profiles/r01_microbench_scatter_rows.txt'),
