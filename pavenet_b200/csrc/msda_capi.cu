@@ -712,7 +712,8 @@ int pick_chunk(int num_query, size_t bytes_per_query, size_t target) {
 }
 }  // namespace
 
-int msda_forward_backward_host(msda_workspace* ws, const void* h_value,
+// the pipeline proper; on an error it returns at once, possibly with copies still in flight
+static int host_pipeline(msda_workspace* ws, const void* h_value,
                                const int64_t* h_spatial_shapes, const int64_t* h_level_start_index,
                                const void* h_sampling_loc, const void* h_attn_weight,
                                const void* h_grad_output, void* h_output, void* h_grad_value,
@@ -823,6 +824,28 @@ int msda_forward_backward_host(msda_workspace* ws, const void* h_value,
   MSDA_CU(cudaStreamSynchronize(ws->s_cmp));
   for (int i = 0; i < ws->n_copy; ++i) MSDA_CU(cudaStreamSynchronize(ws->s_in[i]));
   return MSDA_OK;
+}
+
+int msda_forward_backward_host(msda_workspace* ws, const void* h_value,
+                               const int64_t* h_spatial_shapes, const int64_t* h_level_start_index,
+                               const void* h_sampling_loc, const void* h_attn_weight,
+                               const void* h_grad_output, void* h_output, void* h_grad_value,
+                               void* h_grad_sampling_loc, void* h_grad_attn_weight, int batch,
+                               int spatial_size, int num_heads, int channels, int num_levels,
+                               int num_query, int num_point, int dtype, int value_dtype) {
+  const int rc = host_pipeline(ws, h_value, h_spatial_shapes, h_level_start_index, h_sampling_loc,
+                               h_attn_weight, h_grad_output, h_output, h_grad_value,
+                               h_grad_sampling_loc, h_grad_attn_weight, batch, spatial_size,
+                               num_heads, channels, num_levels, num_query, num_point, dtype,
+                               value_dtype);
+  if (rc != MSDA_OK && ws) {
+    // never hand the caller's host buffers back while a copy into or out of them is still queued
+    // (the message of the original failure stays in msda_last_error)
+    for (int i = 0; i < ws->n_copy; ++i) cudaStreamSynchronize(ws->s_out[i]);
+    cudaStreamSynchronize(ws->s_cmp);
+    for (int i = 0; i < ws->n_copy; ++i) cudaStreamSynchronize(ws->s_in[i]);
+  }
+  return rc;
 }
 
 int msda_forward_host(msda_workspace* ws, const void* h_value, const int64_t* h_spatial_shapes,

@@ -13,6 +13,8 @@
 //        4 plain LDS.128 / FADD / STS.128 (racy: the upper bound of any ownership scheme)
 //        5 integer ATOMS.ADD x4, bank-swizzled (what a fixed-point accumulator would cost)
 //        6 half of the rows by mode 0, half by mode 1 (the mix a privatised backward would issue)
+//        7 mode 0 plus one 128-byte value-row gather (ld.global.nc.v4.f32, 68 MB buffer) per reduction: the
+//          backward kernel's real mix        8 mode 6 plus the same gathers
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench_smem_acc microbench_smem_acc.cu
 #include <cstdio>
 #include <cstdint>
@@ -57,7 +59,8 @@ extern __shared__ float4 s_tile[];
 
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1)
-k(float* gbuf, uint32_t g_rows, uint32_t tile_rows, int iters, float* check) {
+k(float* gbuf, const float* gbuf2, uint32_t g_rows, uint32_t tile_rows, int iters, float* check) {
+  float acc = 0.f;
   float* tile = reinterpret_cast<float*>(s_tile);
   for (uint32_t i = threadIdx.x; i < tile_rows * 8; i += blockDim.x) s_tile[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
@@ -68,11 +71,15 @@ k(float* gbuf, uint32_t g_rows, uint32_t tile_rows, int iters, float* check) {
   for (int i = 0; i < iters; ++i) {
     const uint32_t h = mix(grp * 9781u + i * 7919u);
     const uint32_t r = __umulhi(h, tile_rows);
-    bool to_global = MODE == 0 || (MODE == 6 && (i & 1));
+    bool to_global = MODE == 0 || MODE == 7 || ((MODE == 6 || MODE == 8) && (i & 1));
+    if (MODE == 7 || MODE == 8) {
+      const float4 lv = __ldg(reinterpret_cast<const float4*>(gbuf2 + (size_t)__umulhi(h * 0x9E3779B1u, g_rows) * 32 + gl * 4));
+      acc += lv.x + lv.y + lv.z + lv.w;
+    }
     if (to_global) {
       float* row = gbuf + (size_t)__umulhi(h * 2654435761u, g_rows) * 32 + gl * 4;
       asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-    } else if (MODE == 1 || MODE == 6) {
+    } else if (MODE == 1 || MODE == 6 || MODE == 8) {
       smem_add_cas128(sbase + r * 128 + gl * 16, v);
     } else if (MODE == 2) {
       smem_add_cas64(tile + r * 32 + gl * 4, v.x, v.y);
@@ -95,30 +102,31 @@ k(float* gbuf, uint32_t g_rows, uint32_t tile_rows, int iters, float* check) {
   float s = 0.f;
   for (uint32_t i = threadIdx.x; i < tile_rows * 32; i += blockDim.x) s += tile[i];
   atomicAdd(check + blockIdx.x, s);
+  if (acc == 123.456f) check[1000] = acc;
 }
 
 template <int MODE>
-void run(const char* name, float* gbuf, uint32_t g_rows, uint32_t tile_rows, int threads, float* check, int sms) {
-  const int iters = 2048;
+void run(const char* name, float* gbuf, const float* gbuf2, uint32_t g_rows, uint32_t tile_rows, int threads, float* check, int sms) {
+  const int iters = 1024;
   cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tile_rows * 128));
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   cudaMemset(check, 0, sms * 4);
-  k<MODE><<<sms, threads, tile_rows * 128>>>(gbuf, g_rows, tile_rows, iters, check);
+  k<MODE><<<sms, threads, tile_rows * 128>>>(gbuf, gbuf2, g_rows, tile_rows, iters, check);
   cudaDeviceSynchronize();
   float h0 = 0; cudaMemcpy(&h0, check, 4, cudaMemcpyDeviceToHost);
   float best = 1e30f;
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(a);
-    k<MODE><<<sms, threads, tile_rows * 128>>>(gbuf, g_rows, tile_rows, iters, check);
+    k<MODE><<<sms, threads, tile_rows * 128>>>(gbuf, gbuf2, g_rows, tile_rows, iters, check);
     cudaEventRecord(b); cudaEventSynchronize(b);
     float ms; cudaEventElapsedTime(&ms, a, b); if (ms < best) best = ms;
   }
   const double rows_sm = (double)(threads / 8) * iters;
   int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
-  const double expect = rows_sm * 80.0 * (MODE == 6 ? 0.5 : 1.0);
+  const double expect = rows_sm * 80.0 * ((MODE == 6 || MODE == 8) ? 0.5 : 1.0);
   printf("%-44s tile=%4u rows thr=%4d  %7.3f ms  %6.2f Grows/s  %5.2f clk/row/SM  checksum %s\n", name, tile_rows,
          threads, best, rows_sm * sms / best * 1e-6, best * 1e-3 * khz * 1e3 / rows_sm,
-         (MODE == 1 || MODE == 2 || MODE == 6) ? (h0 == (float)expect ? "ok" : "MISMATCH") : "-");
+         (MODE == 1 || MODE == 2 || MODE == 6 || MODE == 8) ? (h0 == (float)expect ? "ok" : "MISMATCH") : "-");
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) printf("  CUDA error: %s\n", cudaGetErrorString(e));
 }
@@ -127,17 +135,20 @@ int main() {
   int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const uint32_t g_rows = 3u * 22223u * 8u;
   float* gbuf; float* check;
-  cudaMalloc(&gbuf, (size_t)g_rows * 128); cudaMalloc(&check, 4096);
+  cudaMalloc(&gbuf, (size_t)g_rows * 128); cudaMalloc(&check, 8192);
   cudaMemset(gbuf, 0, (size_t)g_rows * 128);
+  float* gbuf2; cudaMalloc(&gbuf2, (size_t)g_rows * 128); cudaMemset(gbuf2, 0, (size_t)g_rows * 128);
   for (int threads : {512, 1024}) {
     for (uint32_t tile_rows : {273u, 1323u}) {
-      run<0>("red.global.add.v4.f32", gbuf, g_rows, tile_rows, threads, check, sms);
-      run<1>("shared CAS.128 loop", gbuf, g_rows, tile_rows, threads, check, sms);
-      run<2>("shared CAS.64 loop x2", gbuf, g_rows, tile_rows, threads, check, sms);
-      run<3>("shared atomicAdd(float) x4 swizzled", gbuf, g_rows, tile_rows, threads, check, sms);
-      run<4>("shared LDS.128+STS.128 (racy bound)", gbuf, g_rows, tile_rows, threads, check, sms);
-      run<5>("shared ATOMS.ADD int x4 swizzled", gbuf, g_rows, tile_rows, threads, check, sms);
-      run<6>("half red.global, half shared CAS.128", gbuf, g_rows, tile_rows, threads, check, sms);
+      run<0>("red.global.add.v4.f32", gbuf, gbuf2, g_rows, tile_rows, threads, check, sms);
+      run<1>("shared CAS.128 loop", gbuf, gbuf2, g_rows, tile_rows, threads, check, sms);
+      run<2>("shared CAS.64 loop x2", gbuf, gbuf2, g_rows, tile_rows, threads, check, sms);
+      run<3>("shared atomicAdd(float) x4 swizzled", gbuf, gbuf2, g_rows, tile_rows, threads, check, sms);
+      run<4>("shared LDS.128+STS.128 (racy bound)", gbuf, gbuf2, g_rows, tile_rows, threads, check, sms);
+      run<5>("shared ATOMS.ADD int x4 swizzled", gbuf, gbuf2, g_rows, tile_rows, threads, check, sms);
+      run<6>("half red.global, half shared CAS.128", gbuf, gbuf2, g_rows, tile_rows, threads, check, sms);
+      run<7>("gather + red.global (the kernel's mix)", gbuf, gbuf2, g_rows, tile_rows, threads, check, sms);
+      run<8>("gather + half red.global, half CAS.128", gbuf, gbuf2, g_rows, tile_rows, threads, check, sms);
     }
   }
   return 0;
