@@ -603,12 +603,17 @@ struct msda_workspace {
   std::vector<cudaEvent_t> events;  // grow-only pool, reused across calls
   size_t next_event = 0;
   size_t piece_bytes = size_t(12) << 20;  // upload bytes per pipeline piece
+  // PAVENET_MSDA_TRACE_E2E=<file>: timing events at every pipeline stage, written as CSV after each call
+  const char* trace_path = nullptr;
+  struct Mark { cudaEvent_t ev; char kind; int b, piece; };
+  std::vector<Mark> marks;
 };
 
 int msda_workspace_create(msda_workspace** out_ws) {
   if (!out_ws) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_workspace_create: NULL out pointer");
   msda_workspace* ws = new msda_workspace();
   ws->n_copy = msda::tuning().copy_streams;
+  ws->trace_path = std::getenv("PAVENET_MSDA_TRACE_E2E");
   std::vector<cudaStream_t*> st = {&ws->s_cmp};
   for (int i = 0; i < ws->n_copy; ++i) {
     st.push_back(&ws->s_in[i]);
@@ -683,12 +688,37 @@ int ws_reserve(msda_workspace* ws, size_t bytes) {
 int ws_event(msda_workspace* ws, cudaEvent_t* out) {
   if (ws->next_event == ws->events.size()) {
     cudaEvent_t e;
-    const cudaError_t rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    const cudaError_t rc = cudaEventCreateWithFlags(&e, ws->trace_path ? cudaEventDefault : cudaEventDisableTiming);
     if (rc != cudaSuccess) return fail(MSDA_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(rc));
     ws->events.push_back(e);
   }
   *out = ws->events[ws->next_event++];
   return MSDA_OK;
+}
+
+// trace mode: remember an already recorded event, or record a fresh one on `st`
+int ws_mark(msda_workspace* ws, char kind, int b, int piece, cudaEvent_t ev, cudaStream_t st) {
+  if (!ws->trace_path) return MSDA_OK;
+  if (!ev) {
+    const int rc = ws_event(ws, &ev);
+    if (rc) return rc;
+    if (cudaEventRecord(ev, st) != cudaSuccess) return fail(MSDA_ERR_CUDA, "trace: cudaEventRecord");
+  }
+  ws->marks.push_back({ev, kind, b, piece});
+  return MSDA_OK;
+}
+void ws_write_trace(msda_workspace* ws) {
+  if (!ws->trace_path || ws->marks.empty()) return;
+  if (FILE* f = std::fopen(ws->trace_path, "w")) {
+    std::fprintf(f, "kind,batch,piece,ms\n");   // S start, V value up, I piece inputs up, C compute done, O piece outputs down, G grad_value down
+    for (const auto& m : ws->marks) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ws->marks[0].ev, m.ev);
+      std::fprintf(f, "%c,%d,%d,%.4f\n", m.kind, m.b, m.piece, ms);
+    }
+    std::fclose(f);
+  }
+  ws->marks.clear();
 }
 
 #define MSDA_CU(expr)                                                                     \
@@ -742,6 +772,8 @@ static int host_pipeline(msda_workspace* ws, const void* h_value,
   if (do_bwd) need += batch * (pad256(b_out) + pad256(b_gval) + pad256(b_loc) + pad256(b_aw));
   MSDA_RC(ws_reserve(ws, need));
   ws->next_event = 0;
+  ws->marks.clear();
+  MSDA_RC(ws_mark(ws, 'S', 0, 0, nullptr, ws->s_in[0]));
   Arena ar{static_cast<char*>(ws->buf)};
   int64_t* d_shp = static_cast<int64_t*>(ar.take(b_shp));
   int64_t* d_lsi = static_cast<int64_t*>(ar.take(b_lsi));
@@ -774,6 +806,7 @@ static int host_pipeline(msda_workspace* ws, const void* h_value,
     MSDA_RC(ws_event(ws, &ev_val));
     MSDA_CU(cudaEventRecord(ev_val, ws->s_in[0]));
     MSDA_CU(cudaStreamWaitEvent(ws->s_cmp, ev_val, 0));
+    MSDA_RC(ws_mark(ws, 'V', b, piece, ev_val, nullptr));
     cudaEvent_t ev_done = nullptr;
     for (int q0 = 0; q0 < num_query; q0 += chunk, ++piece) {
       cudaStream_t s_in = ws->s_in[piece % ws->n_copy], s_out = ws->s_out[piece % ws->n_copy];
@@ -791,6 +824,7 @@ static int host_pipeline(msda_workspace* ws, const void* h_value,
       MSDA_RC(ws_event(ws, &ev_in));
       MSDA_CU(cudaEventRecord(ev_in, s_in));
       MSDA_CU(cudaStreamWaitEvent(ws->s_cmp, ev_in, 0));
+      MSDA_RC(ws_mark(ws, 'I', b, piece, ev_in, nullptr));
       if (h_output)
         MSDA_RC(msda_forward(d_val, d_shp, d_lsi, d_loc + o_loc, d_aw + o_aw, d_out + o_out, 1,
                              spatial_size, num_heads, channels, num_levels, nq, num_point, dtype,
@@ -802,6 +836,7 @@ static int host_pipeline(msda_workspace* ws, const void* h_value,
       MSDA_RC(ws_event(ws, &ev_done));
       MSDA_CU(cudaEventRecord(ev_done, ws->s_cmp));
       MSDA_CU(cudaStreamWaitEvent(s_out, ev_done, 0));
+      MSDA_RC(ws_mark(ws, 'C', b, piece, ev_done, nullptr));
       if (h_output)
         MSDA_CU(cudaMemcpyAsync(hoffw(h_output, b * b_out + o_out), d_out + o_out, n_out,
                                 cudaMemcpyDeviceToHost, s_out));
@@ -811,6 +846,7 @@ static int host_pipeline(msda_workspace* ws, const void* h_value,
         MSDA_CU(cudaMemcpyAsync(hoffw(h_grad_attn_weight, b * b_aw + o_aw), d_gaw + o_aw, n_aw,
                                 cudaMemcpyDeviceToHost, s_out));
       }
+      MSDA_RC(ws_mark(ws, 'O', b, piece, nullptr, s_out));
     }
     if (do_bwd) {
       // every piece of this batch entry has been scattered once the last one's backward is done
@@ -818,11 +854,13 @@ static int host_pipeline(msda_workspace* ws, const void* h_value,
       MSDA_CU(cudaStreamWaitEvent(s_out, ev_done, 0));
       MSDA_CU(cudaMemcpyAsync(hoffw(h_grad_value, b * b_gval), d_gval, b_gval, cudaMemcpyDeviceToHost,
                               s_out));
+      MSDA_RC(ws_mark(ws, 'G', b, piece, nullptr, s_out));
     }
   }
   for (int i = 0; i < ws->n_copy; ++i) MSDA_CU(cudaStreamSynchronize(ws->s_out[i]));
   MSDA_CU(cudaStreamSynchronize(ws->s_cmp));
   for (int i = 0; i < ws->n_copy; ++i) MSDA_CU(cudaStreamSynchronize(ws->s_in[i]));
+  ws_write_trace(ws);
   return MSDA_OK;
 }
 
