@@ -63,6 +63,9 @@ WORKLOADS = {
                          levels=R50_LEVELS, kind='pose'),
     'petr_cfg1': dict(desc='PETR pose attention, 1 frame, 300 queries x 17 keypoints', B=1, T=1,
                       Q=300, P=17, levels=R50_LEVELS, kind='pose'),
+    'encoder_cfg2_rand': dict(desc='config 2 with ADVERSARIAL locations: every sample uniform in the image (no spatial '
+                                   'coherence between neighbouring queries; SURVEY.md section 8d)', B=3, T=1, Q=None,
+                              P=4, levels=R50_LEVELS, kind='encoder', rand_loc=True),
     'stress_cfg5': dict(desc='encoder stress: 8 frames at 800x1333, 4 levels x 4 points', B=8, T=1,
                         Q=None, P=4, levels=R50_LEVELS, kind='encoder'),
     'stress_cfg5_big': dict(desc='encoder stress: 8 frames at 1200x2000 (Swin-L high-res), 4 levels x 4 points',
@@ -119,6 +122,8 @@ def make_problem(wl, seed, device, value_dtype=torch.float32, frames=None):
         norm = torch.tensor([[w, h] for h, w in levels], dtype=torch.float32, device=device)
         loc = ref[None, :, None, None, None, :] + (
             off[None, None] + randn(B, Q, M, L, P, 2)) / norm[None, None, None, :, None, :]
+        if cfg.get('rand_loc'):
+            loc = rand(B, Q, M, L, P, 2)
         Lk = L
         # experiment: hand the queries to the op in patch order (PW x PH pixel patches inside each
         # level) instead of raster order, to measure what a patch-shaped block would gain in L1 hits

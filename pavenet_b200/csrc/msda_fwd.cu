@@ -90,6 +90,7 @@ constexpr int kRowsWarps = kRowsThreads / 32;
 // registers, more gathers in flight per lane) for the split small-Q shapes,
 // which are latency bound (measured on B200: pose cfg3 58 -> 48 us).
 constexpr int fwd_min_blocks(int split) { return split > 1 ? 3 : 4; }
+constexpr int kRowsZeroTile16 = 256;   // 4 KiB zero tile for the TMA zero-fill (16-byte units)
 
 // Shared-memory state of one rows block.
 template <int D, typename VT, int SPLIT, int LB = 16>
@@ -254,17 +255,38 @@ __device__ __forceinline__ void fwd_rows_item(const VT* __restrict__ value, SRC 
 template <int D, typename VT, int SPLIT, class SRC, int LB = 16, int MINB = (LB == 32 ? 3 : fwd_min_blocks(SPLIT))>
 __global__ void __launch_bounds__(kRowsThreads, MINB)
 msda_fwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
-                     const int64_t* __restrict__ lsi, SRC src, float* __restrict__ out, Dims d) {
+                     const int64_t* __restrict__ lsi, SRC src, float* __restrict__ out, Dims d,
+                     uint4* __restrict__ clear = nullptr, long long clear_n16 = 0) {
   __shared__ FwdRowsSmem<D, VT, SPLIT, LB> sm;
+  // optional zero-fill of the coming backward's grad_value (msda_forward_clear, knob clear_mode = 2):
+  // each block hands its share to the TMA engine as bulk stores of a zeroed shared-memory tile, so the
+  // fill costs no LSU slots and drains into DRAM, which this L1-bound kernel leaves ~85 % idle
+  __shared__ __align__(128) uint4 s_zero[kRowsZeroTile16];
   const int MD = d.M * D;
   for (int l = threadIdx.x; l < d.L; l += blockDim.x) sm.lvl[l] = load_level(shapes, lsi, l, MD);
+  if (clear) {
+    for (int i = threadIdx.x; i < kRowsZeroTile16; i += blockDim.x) s_zero[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   __syncthreads();
+  if (clear && threadIdx.x == 0) {
+    const long long a = clear_n16 * blockIdx.x / gridDim.x, b = clear_n16 * (blockIdx.x + 1LL) / gridDim.x;
+    const uint32_t src_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_zero));
+    for (long long i = a; i < b; i += kRowsZeroTile16) {
+      const uint32_t bytes = static_cast<uint32_t>(min(static_cast<long long>(kRowsZeroTile16), b - i) * 16);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(clear + i),
+                   "r"(src_addr), "r"(bytes)
+                   : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
   constexpr int QPB = kRowsThreads / (D / RowLoad<VT, LB>::VEC) / SPLIT;
   const int n_chunks = (d.Q + QPB - 1) / QPB;
   int blk = blockIdx.x;
   const int m = blk % d.M;
   blk /= d.M;
   fwd_rows_item<D, VT, SPLIT, SRC, LB>(value, src, out, d, sm, m, blk % n_chunks, blk / n_chunks);
+  if (clear && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // Forward variant 2 (large Q): persistent blocks, head-affine.  Every block of an SM serves
@@ -316,6 +338,10 @@ msda_fwd_rows_affine_kernel(const VT* __restrict__ value, const int64_t* __restr
 // launchers
 // --------------------------------------------------------------------------
 static thread_local int g_fwd_sm_count = 148;   // set by launch_forward* before dispatch
+// zero-fill folded into the default rows kernel (clear_mode = 2): set by launch_forward*, consumed by
+// launch_rows_split (cleared there so that no later launch repeats it)
+static thread_local void* g_fwd_clear = nullptr;
+static thread_local size_t g_fwd_clear_bytes = 0;
 
 template <int D, typename VT, int SPLIT, class SRC>
 static cudaError_t launch_rows_split(const void* value, const int64_t* shapes, const int64_t* lsi,
@@ -359,7 +385,10 @@ static cudaError_t launch_rows_split(const void* value, const int64_t* shapes, c
     }
   }
   msda_fwd_rows_kernel<D, VT, SPLIT, SRC><<<static_cast<unsigned>(blocks), kRowsThreads, 0, st>>>(
-      static_cast<const VT*>(value), shapes, lsi, src, out, d);
+      static_cast<const VT*>(value), shapes, lsi, src, out, d, static_cast<uint4*>(g_fwd_clear),
+      static_cast<long long>(g_fwd_clear_bytes / 16));
+  g_fwd_clear = nullptr;
+  g_fwd_clear_bytes = 0;
   note_launches(1);
   note_kernel(std::is_same<SRC, FusedSource>::value ? KF_FWD_ROWS_FUSED : KF_FWD_ROWS);
   return cudaGetLastError();
@@ -407,11 +436,20 @@ static cudaError_t clear_by_memset(void* clear, size_t clear_bytes, cudaStream_t
   return cudaMemsetAsync(clear, 0, clear_bytes, st);
 }
 
+// the default rows kernel can take the zero-fill along (TMA bulk stores) when it is 16-byte granular
+// and no alternative forward variant is selected
+static bool rows_fold_clear(const void* clear, size_t clear_bytes) {
+  return tuning().clear_mode == 2 && tuning().fwd_variant == 0 && clear && clear_bytes &&
+         clear_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(clear) & 15u) == 0;
+}
+
 cudaError_t launch_forward(const void* value, const int64_t* shapes, const int64_t* lsi,
                            const void* loc, const void* aw, void* out, const Dims& d, int dtype,
                            int value_dtype, int sm_count, int force_generic, void* clear,
                            size_t clear_bytes, cudaStream_t st) {
   g_fwd_sm_count = sm_count;
+  g_fwd_clear = nullptr;
+  g_fwd_clear_bytes = 0;
   if (dtype == MSDA_F32 && !force_generic && d.L <= kMaxSmemLevels &&
       rows_supported(d.D, value_dtype)) {
     PlainSource src;
@@ -433,8 +471,13 @@ cudaError_t launch_forward(const void* value, const int64_t* shapes, const int64
       return launch_forward_flat(value, shapes, lsi, src, outf, d, value_dtype, sm_count,
                                  fold ? clear : nullptr, fold ? clear_bytes : 0, st);
     }
-    const cudaError_t ce = clear_by_memset(clear, clear_bytes, st);
-    if (ce != cudaSuccess) return ce;
+    if (rows_fold_clear(clear, clear_bytes)) {
+      g_fwd_clear = clear;
+      g_fwd_clear_bytes = clear_bytes;
+    } else {
+      const cudaError_t ce = clear_by_memset(clear, clear_bytes, st);
+      if (ce != cudaSuccess) return ce;
+    }
 #define MSDA_ROWS_CASE(DD)                                                                   \
   case DD:                                                                                   \
     if (value_dtype == MSDA_F32) {                                                           \
