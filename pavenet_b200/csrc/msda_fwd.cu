@@ -348,6 +348,11 @@ static cudaError_t launch_rows_split(const void* value, const int64_t* shapes, c
                                      const SRC& src, float* out, const Dims& d, cudaStream_t st) {
   constexpr int G = D / Vec16<VT>::VEC;
   constexpr int QPB = kRowsThreads / G / SPLIT;
+  // take the pending zero-fill (if any) before anything can return: it must never outlive this call
+  uint4* const fold_clear = static_cast<uint4*>(g_fwd_clear);
+  const long long fold_n16 = static_cast<long long>(g_fwd_clear_bytes / 16);
+  g_fwd_clear = nullptr;
+  g_fwd_clear_bytes = 0;
   const int64_t blocks = static_cast<int64_t>(d.B) * ((d.Q + QPB - 1) / QPB) * d.M;
   if (blocks >= (int64_t(1) << 31)) return cudaErrorInvalidConfiguration;
   // variant 3: 256-bit value loads (fp32, 32-byte aligned rows), 8 rows per warp instruction
@@ -385,10 +390,7 @@ static cudaError_t launch_rows_split(const void* value, const int64_t* shapes, c
     }
   }
   msda_fwd_rows_kernel<D, VT, SPLIT, SRC><<<static_cast<unsigned>(blocks), kRowsThreads, 0, st>>>(
-      static_cast<const VT*>(value), shapes, lsi, src, out, d, static_cast<uint4*>(g_fwd_clear),
-      static_cast<long long>(g_fwd_clear_bytes / 16));
-  g_fwd_clear = nullptr;
-  g_fwd_clear_bytes = 0;
+      static_cast<const VT*>(value), shapes, lsi, src, out, d, fold_clear, fold_n16);
   note_launches(1);
   note_kernel(std::is_same<SRC, FusedSource>::value ? KF_FWD_ROWS_FUSED : KF_FWD_ROWS);
   return cudaGetLastError();
