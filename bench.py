@@ -845,11 +845,60 @@ def main():
                                  host['grad_out'], out=out_h, grad_value=gv_h,
                                  grad_sampling_loc=gl_h, grad_attn_weight=ga_h)
 
-        e2e = timed(e2e_capi)
+        e2e_blocking = timed(e2e_capi)
+        e2e_blocking['api'] = ('msda_forward_backward_host (C ABI, pinned host buffers; upload / kernels / '
+                               'download pipelined over batch entries x query chunks), one blocking call per step')
+
+        # (1b) the same entry point, queued: two calls in flight on two workspaces, each with its own
+        # result buffers.  Every step still uploads all its inputs and downloads all its results inside
+        # the timed region; the next step's first upload runs under this step's last download, which a
+        # blocking call leaves idle (0.9 ms of its 6.4, profiles/r02_e2e_link_analysis.txt)
+        hws2 = pavenet_b200.HostWorkspace()
+        if args.piece_mb > 0:
+            hws2.set_piece_bytes(int(args.piece_mb * (1 << 20)))
+        slots = [(hws, out_h, gv_h, gl_h, ga_h),
+                 (hws2, torch.empty_like(out_h).pin_memory(), torch.empty_like(gv_h).pin_memory(),
+                  torch.empty_like(gl_h).pin_memory(), torch.empty_like(ga_h).pin_memory())]
+        state = {'i': 0}
+
+        def e2e_queued():
+            ws_, o_, gv_, gl_, ga_ = slots[state['i'] % 2]
+            state['i'] += 1
+            ws_.wait()                  # the call queued on this workspace two steps ago
+            ws_.forward_backward(host['value'], shapes_h, lsi_h, host['loc'], host['aw'],
+                                 host['grad_out'], out=o_, grad_value=gv_, grad_sampling_loc=gl_,
+                                 grad_attn_weight=ga_, wait=False)
+
+        def timed_queued():
+            for _ in range(4):
+                e2e_queued()
+            for s_ in slots:
+                s_[0].wait()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                e2e_queued()
+            for s_ in slots:
+                s_[0].wait()            # every result of every step is in host memory
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            ms = clip_sharding.max_over_ranks(wall_ms, device)
+            tq = clip_sharding.sum_over_ranks(q_per_step * n_e2e, device)
+            return {'value': tq / (ms * 1e-3), 'unit': 'queries/s', 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': ms / n_e2e, 'steps': n_e2e}
+
+        e2e = timed_queued()
         e2e['host_affinity'] = host_affinity
-        e2e['api'] = ('msda_forward_backward_host (C ABI, pinned host buffers; upload / kernels / '
-                      'download pipelined over batch entries x query chunks)')
+        e2e['api'] = ('msda_forward_backward_host_async + msda_workspace_wait (C ABI, pinned host buffers): '
+                      'two calls in flight on two workspaces with separate result buffers; every step uploads '
+                      'all inputs and downloads output + all gradients; inside a call upload / kernels / download '
+                      'are pipelined over batch entries x query chunks')
+        e2e['blocking'] = e2e_blocking
+        # the last queued results must equal the blocking call's
+        e2e['max_abs_diff_vs_blocking'] = float(max((slots[1][k] - slots[0][k]).abs().max() for k in (1, 3, 4)))
         hws.close()
+        hws2.close()
 
         # (2) the autograd Function PyTorch callers use, copies issued around it on one stream
         gvb_h = torch.empty(p['value'].shape, dtype=p['value'].dtype).pin_memory()

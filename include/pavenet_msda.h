@@ -283,7 +283,8 @@ typedef struct msda_workspace msda_workspace;
 
 int msda_workspace_create(msda_workspace **out_ws);
 void msda_workspace_destroy(msda_workspace *ws);
-/* Upload bytes per pipeline piece of the staged calls (default 12 MiB). */
+/* Upload bytes per pipeline piece of the staged calls (defaults: 12 MiB for a
+ * blocking call, 32 MiB for a queued one). */
 int msda_workspace_set_piece_bytes(msda_workspace *ws, size_t bytes);
 
 /* Page-locked host memory for callers without their own CUDA binding.  With
@@ -312,6 +313,24 @@ int msda_forward_backward_host(
     void *h_grad_value, void *h_grad_sampling_loc, void *h_grad_attn_weight,
     int batch, int spatial_size, int num_heads, int channels, int num_levels,
     int num_query, int num_point, int dtype, int value_dtype);
+
+/* The same call, queued only: it returns as soon as every copy and kernel is
+ * enqueued on the workspace's streams; the host buffers must stay untouched
+ * (inputs) / unread (results) until msda_workspace_wait(ws) has returned.  One
+ * call may be in flight per workspace; a caller that alternates between two
+ * workspaces (and two sets of result buffers) keeps the link busy across calls:
+ * the next call's first upload runs under the previous call's last download.
+ * (Additive to ABI version 2.) */
+int msda_forward_backward_host_async(
+    msda_workspace *ws, const void *h_value, const int64_t *h_spatial_shapes,
+    const int64_t *h_level_start_index, const void *h_sampling_loc,
+    const void *h_attn_weight, const void *h_grad_output, void *h_output,
+    void *h_grad_value, void *h_grad_sampling_loc, void *h_grad_attn_weight,
+    int batch, int spatial_size, int num_heads, int channels, int num_levels,
+    int num_query, int num_point, int dtype, int value_dtype);
+/* Blocks until the call queued by msda_forward_backward_host_async is complete
+ * (no-op when nothing is in flight). */
+int msda_workspace_wait(msda_workspace *ws);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = (
     'msda_workspace_create', 'msda_workspace_destroy', 'msda_workspace_set_piece_bytes',
     'msda_host_alloc',
     'msda_host_free', 'msda_forward_host',
-    'msda_forward_backward_host',
+    'msda_forward_backward_host', 'msda_forward_backward_host_async', 'msda_workspace_wait',
 )
 
 _lib = None
@@ -97,6 +97,10 @@ def _declare(lib):
     lib.msda_forward_backward_host.restype = c_int
     lib.msda_forward_backward_host.argtypes = (
         [c_void_p] + [c_void_p] * 10 + [c_int] * 7 + [c_int, c_int])
+    lib.msda_forward_backward_host_async.restype = c_int
+    lib.msda_forward_backward_host_async.argtypes = lib.msda_forward_backward_host.argtypes
+    lib.msda_workspace_wait.restype = c_int
+    lib.msda_workspace_wait.argtypes = [c_void_p]
 
 
 def load():

@@ -295,6 +295,7 @@ class HostWorkspace(object):
         handle = ctypes.c_void_p()
         _capi.check(self._lib.msda_workspace_create(ctypes.byref(handle)), 'msda_workspace_create')
         self._ws = handle
+        self._keepalive = None
 
     def set_piece_bytes(self, nbytes):
         """Upload bytes per pipeline piece (default 12 MiB)."""
@@ -367,11 +368,21 @@ class HostWorkspace(object):
         _capi.check(status, 'msda_forward_host')
         return out
 
+    def wait(self):
+        """Complete the call queued with `forward_backward(..., wait=False)`."""
+        _capi.check(self._lib.msda_workspace_wait(self._ws), 'msda_workspace_wait')
+        self._keepalive = None
+
     def forward_backward(self, value, spatial_shapes, level_start_index, sampling_locations,
                          attention_weights, grad_output, out=None, grad_value=None,
-                         grad_sampling_loc=None, grad_attn_weight=None):
+                         grad_sampling_loc=None, grad_attn_weight=None, wait=True):
         """Returns (out, grad_value, grad_sampling_loc, grad_attn_weight); the
-        optional arguments are preallocated (pinned) result buffers."""
+        optional arguments are preallocated (pinned) result buffers.
+
+        wait=False queues the call (`msda_forward_backward_host_async`) and returns at once: the
+        result tensors are valid, and the inputs may be modified, only after `wait()`.  Alternating
+        between two workspaces keeps the link busy across calls (the next call's first upload runs
+        under this call's last download)."""
         B, S, M, D, L, Q, P = self._check_host(value, spatial_shapes, level_start_index,
                                                sampling_locations, attention_weights)
         dt = sampling_locations.dtype
@@ -392,7 +403,12 @@ class HostWorkspace(object):
         if grad_output.is_cuda or grad_output.dtype != dt or grad_output.numel() != B * Q * M * D:
             raise RuntimeError('grad_output must be a CPU %s tensor of %d elements' % (dt, B * Q * M * D))
         grad_output = grad_output.contiguous()
-        status = self._lib.msda_forward_backward_host(
+        entry = self._lib.msda_forward_backward_host if wait else self._lib.msda_forward_backward_host_async
+        if not wait:   # keep every buffer of the queued call alive until wait()
+            self._keepalive = (value, spatial_shapes, level_start_index, sampling_locations,
+                               attention_weights, grad_output, out, grad_value, grad_sampling_loc,
+                               grad_attn_weight)
+        status = entry(
             self._ws, value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             sampling_locations.data_ptr(), attention_weights.data_ptr(), grad_output.data_ptr(),
             out.data_ptr(), grad_value.data_ptr(), grad_sampling_loc.data_ptr(),

@@ -1038,6 +1038,37 @@ def test_host_buffer_entry_points(pinned):
     assert rel_err(ga, rga) < BWD_TOL_F32
 
 
+def test_host_buffer_async_calls_on_two_workspaces():
+    """msda_forward_backward_host_async + msda_workspace_wait: two calls in flight on two
+    workspaces (what bench.py's e2e leg does) give the same results as the blocking call; a
+    second call on a workspace that has not been waited for is refused."""
+    import pavenet_b200
+    probs = []
+    for seed in (31, 32, 33):
+        value, shapes_t, loc, aw, go = _random_problem(seed, 2, 3000, 8, 32, 4, MID_LEVELS)
+        probs.append([t.pin_memory() for t in (value, loc, aw, go)] + [shapes_t, O.level_start_index(shapes_t)])
+    wss = [pavenet_b200.HostWorkspace(), pavenet_b200.HostWorkspace()]
+    for ws in wss:
+        ws.set_piece_bytes(1 << 20)
+    results = []
+    for i, (value, loc, aw, go, shapes_t, lsi) in enumerate(probs):
+        ws = wss[i % 2]
+        ws.wait()                                   # the call queued two steps ago (no-op at first)
+        results.append(ws.forward_backward(value, shapes_t, lsi, loc, aw, go, wait=False))
+        if i == 0:
+            with pytest.raises(RuntimeError, match='not been waited for'):
+                ws.forward_backward(value, shapes_t, lsi, loc, aw, go, wait=False)
+    for ws in wss:
+        ws.wait()
+    for (value, loc, aw, go, shapes_t, lsi), (out, gv, gl, ga) in zip(probs, results):
+        ref = O.c_forward(value, shapes_t, lsi, loc, aw)
+        rgv, rgl, rga = O.c_backward(value, shapes_t, lsi, loc, aw, go)
+        assert rel_err(out, ref) < FWD_TOL_F32
+        assert rel_err(gv, rgv) < BWD_TOL_F32 and rel_err(gl, rgl) < BWD_TOL_F32 and rel_err(ga, rga) < BWD_TOL_F32
+    for ws in wss:
+        ws.close()
+
+
 def test_loaded_library_is_in_tree():
     import pavenet_b200
     lib = pavenet_b200._capi.load()
