@@ -888,13 +888,20 @@ def main():
             return {'value': tq / (ms * 1e-3), 'unit': 'queries/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': ms / n_e2e, 'steps': n_e2e}
 
-        e2e = timed_queued()
+        e2e_q = timed_queued()
+        e2e_q['api'] = ('msda_forward_backward_host_async + msda_workspace_wait (C ABI, pinned host buffers): '
+                        'two calls in flight on two workspaces with separate result buffers; every step uploads '
+                        'all inputs and downloads output + all gradients; inside a call upload / kernels / download '
+                        'are pipelined over batch entries x query chunks')
+        # both are the public entry point; a caller picks the form that suits its host.  With one GPU per
+        # host link the queued form wins (5.6 against 6.4 ms); when several ranks share one host memory
+        # system (N > 1 on this box) the extra concurrency costs more than the hidden head / tail saves.
+        # The two times are max-over-ranks, so every rank takes the same branch.
+        if e2e_q['ms_per_step'] <= e2e_blocking['ms_per_step']:
+            e2e = dict(e2e_q, mode='queued', blocking=e2e_blocking)
+        else:
+            e2e = dict(e2e_blocking, mode='blocking', queued=e2e_q)
         e2e['host_affinity'] = host_affinity
-        e2e['api'] = ('msda_forward_backward_host_async + msda_workspace_wait (C ABI, pinned host buffers): '
-                      'two calls in flight on two workspaces with separate result buffers; every step uploads '
-                      'all inputs and downloads output + all gradients; inside a call upload / kernels / download '
-                      'are pipelined over batch entries x query chunks')
-        e2e['blocking'] = e2e_blocking
         # the last queued results must equal the blocking call's
         e2e['max_abs_diff_vs_blocking'] = float(max((slots[1][k] - slots[0][k]).abs().max() for k in (1, 3, 4)))
         hws.close()
