@@ -48,8 +48,10 @@ struct ClearJob {
   long long end;
   long long step;    // units per chunk iteration
   bool tma;
+  int policy;        // store policy of the streaming form (knob clear_policy)
   __device__ __forceinline__ void bind(uint4* p, long long n16, long long w, long long W,
-                                       long long n_iter, bool tma_) {
+                                       long long n_iter, bool tma_, int policy_ = 0) {
+    policy = policy_;
     base = p;
     begin = n16 * w / W;
     end = n16 * (w + 1) / W;
@@ -61,7 +63,16 @@ struct ClearJob {
     const long long a = begin + step * it;
     const long long b = min(a + step, end);
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    for (long long i = a + lane; i < b; i += 32) __stcs(base + i, z);
+    if (policy == 0) {
+      for (long long i = a + lane; i < b; i += 32) __stcs(base + i, z);
+    } else if (policy == 1) {       // default cache policy
+      for (long long i = a + lane; i < b; i += 32) base[i] = z;
+    } else {                        // L2 evict-last: the zero lines are what the backward's reductions hit first
+      uint64_t pol;
+      asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      for (long long i = a + lane; i < b; i += 32)
+        asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %1, %1, %1}, %2;" ::"l"(base + i), "r"(0), "l"(pol) : "memory");
+    }
   }
   // TMA form: lane 0 of the warp queues its whole share as bulk stores of the zero tile
   __device__ __forceinline__ void issue_bulk(const uint4* zero_tile, int lane) const {
@@ -120,7 +131,7 @@ msda_fwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
 
   const int MD = d.M * D;
   for (int l = threadIdx.x; l < d.L; l += blockDim.x) s_lvl[l] = load_level(shapes, lsi, l, MD);
-  if (clear && clear_tma) {
+  if (clear && (clear_tma & 1)) {
     for (int i = threadIdx.x; i < kZeroTileBytes / 16; i += blockDim.x) s_zero[i] = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> TMA reads
   }
@@ -136,7 +147,7 @@ msda_fwd_flat_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   if (prefetch_bytes) l2_prefetch_share(value, prefetch_bytes, w, W, lane);
 
   ClearJob cj;
-  cj.bind(clear, clear_n16, w, W, c1 > c0 ? c1 - c0 : 1, clear_tma != 0);
+  cj.bind(clear, clear_n16, w, W, c1 > c0 ? c1 - c0 : 1, (clear_tma & 1) != 0, clear_tma >> 1);
   cj.issue_bulk(s_zero, lane);
   if (c1 <= c0) {            // more warps than chunks: only the zero-fill share is left
     cj.run(0, lane);
@@ -531,7 +542,7 @@ static cudaError_t launch_fwd_flat(const void* value, const int64_t* shapes, con
   constexpr int BATCH = G >= 4 ? 4 : G;
   const long long clear_n16 = static_cast<long long>(clear_bytes / 16);
   const long long pf = prefetch_bytes_for<VT>(d, 1);
-  const int clear_tma = tuning().clear_mode == 2;   // zero-fill by TMA bulk stores instead of STG
+  const int clear_tma = (tuning().clear_mode == 2 ? 1 : 0) | (tuning().clear_policy << 1);   // bit 0: TMA bulk stores instead of STG; bits 1..: store policy experiment
   const int order = tuning().flat_order;
 #define MSDA_FWD_FLAT_LAUNCH(BATCH_, MINB_)                                                       \
   msda_fwd_flat_kernel<D, VT, SRC, BATCH_, MINB_>                                                 \

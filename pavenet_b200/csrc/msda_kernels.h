@@ -22,6 +22,8 @@ struct Tuning {
   int flat = 1;          // flat small-Q kernels (msda_flat.cu): 0 never, 1 heuristic, 2 whenever legal
   int flat_fwd_cfg = 0;    // tuning sweep of the flat kernels (batch, blocks per SM), 0 = default
   int flat_bwd_cfg = 0;
+  int clear_policy = 2;    // stores of the folded zero-fill: 0 streaming (evict-first), 1 default, 2 L2 evict-last (measured best:
+                           // the backward's first reductions then hit resident zero lines; pose cfg3 step 0.149 -> 0.145 ms)
   int flat_order = 1;      // flat kernels: 1 = every warp walks its piece from chunk 0 upwards (frames in phase), 0 = in storage order
   int clear_mode = 0;      // msda_forward_clear: 0 fold into the flat kernel / memset ahead of the others,
                            // 1 memset on a side stream concurrent with the forward kernel,

@@ -32,7 +32,7 @@ def lib_options():
 
     yield set_
     defaults = {'flat': 1, 'force_generic': 0, 'fwd_split': 0, 'bwd_split': 0,
-                'bwd_variant': 0, 'fwd_variant': 0, 'clear_mode': 0, 'flat_order': FLAT_ORDER_DEFAULT}
+                'bwd_variant': 0, 'fwd_variant': 0, 'clear_mode': 0, 'flat_order': FLAT_ORDER_DEFAULT, 'clear_policy': 2}
     for name in touched:
         _capi.set_option(name, defaults[name])
 
@@ -141,14 +141,16 @@ def test_forward_clear_zero_fills_the_buffer(lib_options):
     ref = O.c_forward(value, shapes_t, lsi, loc, aw)
     # clear_mode 0: streaming stores between the chunks of the flat kernel; 2: TMA bulk stores of a
     # zeroed shared-memory tile queued at kernel start; 1: memset on a side stream
-    for flat, mode in ((2, 0), (2, 2), (2, 1), (0, 0)):
+    # clear_policy: cache policy of the streaming-store form (2 = L2 evict-last, the default)
+    for flat, mode, policy in ((2, 0, 2), (2, 0, 0), (2, 0, 1), (2, 2, 2), (2, 1, 2), (0, 0, 2), (0, 2, 2)):
         lib_options('flat', flat)
         lib_options('clear_mode', mode)
+        lib_options('clear_policy', policy)
         for n in (4, 1024, 4 * 1000 * 1000 + 4, 12345 * 4, 7, 1001):      # incl. sizes that are not 16-byte multiples
             buf = torch.full((n,), 3.0, device='cuda')
             guard = torch.full((64,), 5.0, device='cuda')
             out = ms_deform_attn_forward(*args, 64, clear=buf)
-            assert float(buf.abs().max()) == 0.0, (flat, mode, n)
+            assert float(buf.abs().max()) == 0.0, (flat, mode, policy, n)
             assert float(guard.min()) == 5.0
             assert rel_err(out, ref) < 5e-6
 
