@@ -597,6 +597,7 @@ def main():
     ap.add_argument('--frames', type=int, default=0, help='override the batch entries (frames) per step of an op workload: the batch sweep of BASELINE config 5')
     ap.add_argument('--fused', action='store_true', help='time the fused-prologue kernels (offsets/logits in, softmax + location transform in-kernel) on the same problem')
     ap.add_argument('--piece-mb', type=float, default=0, help='e2e: upload MiB per pipeline piece (0 = library default)')
+    ap.add_argument('--e2e-depth', type=int, default=2, help='e2e, queued form: host-buffer calls in flight (workspaces)')
     ap.add_argument('--fold-clear', default='auto', choices=['auto', '0', '1'],
                     help='zero-fill grad_value inside the forward call (msda_forward_clear) instead of a '
                          'separate memset between forward and backward; auto = for the small-Q (pose) workloads, '
@@ -853,16 +854,17 @@ def main():
         # result buffers.  Every step still uploads all its inputs and downloads all its results inside
         # the timed region; the next step's first upload runs under this step's last download, which a
         # blocking call leaves idle (0.9 ms of its 6.4, profiles/r02_e2e_link_analysis.txt)
-        hws2 = pavenet_b200.HostWorkspace()
-        if args.piece_mb > 0:
-            hws2.set_piece_bytes(int(args.piece_mb * (1 << 20)))
-        slots = [(hws, out_h, gv_h, gl_h, ga_h),
-                 (hws2, torch.empty_like(out_h).pin_memory(), torch.empty_like(gv_h).pin_memory(),
-                  torch.empty_like(gl_h).pin_memory(), torch.empty_like(ga_h).pin_memory())]
+        slots = [(hws, out_h, gv_h, gl_h, ga_h)]
+        for _ in range(max(2, args.e2e_depth) - 1):
+            w_ = pavenet_b200.HostWorkspace()
+            if args.piece_mb > 0:
+                w_.set_piece_bytes(int(args.piece_mb * (1 << 20)))
+            slots.append((w_, torch.empty_like(out_h).pin_memory(), torch.empty_like(gv_h).pin_memory(),
+                          torch.empty_like(gl_h).pin_memory(), torch.empty_like(ga_h).pin_memory()))
         state = {'i': 0}
 
         def e2e_queued():
-            ws_, o_, gv_, gl_, ga_ = slots[state['i'] % 2]
+            ws_, o_, gv_, gl_, ga_ = slots[state['i'] % len(slots)]
             state['i'] += 1
             ws_.wait()                  # the call queued on this workspace two steps ago
             ws_.forward_backward(host['value'], shapes_h, lsi_h, host['loc'], host['aw'],
@@ -870,7 +872,7 @@ def main():
                                  grad_attn_weight=ga_, wait=False)
 
         def timed_queued():
-            for _ in range(4):
+            for _ in range(2 * len(slots)):
                 e2e_queued()
             for s_ in slots:
                 s_[0].wait()
@@ -890,7 +892,7 @@ def main():
 
         e2e_q = timed_queued()
         e2e_q['api'] = ('msda_forward_backward_host_async + msda_workspace_wait (C ABI, pinned host buffers): '
-                        'two calls in flight on two workspaces with separate result buffers; every step uploads '
+                        '%d calls in flight on as many workspaces with separate result buffers; every step uploads ' % len(slots) +
                         'all inputs and downloads output + all gradients; inside a call upload / kernels / download '
                         'are pipelined over batch entries x query chunks')
         # both are the public entry point; a caller picks the form that suits its host.  With one GPU per
@@ -904,8 +906,8 @@ def main():
         e2e['host_affinity'] = host_affinity
         # the last queued results must equal the blocking call's
         e2e['max_abs_diff_vs_blocking'] = float(max((slots[1][k] - slots[0][k]).abs().max() for k in (1, 3, 4)))
-        hws.close()
-        hws2.close()
+        for s_ in slots:
+            s_[0].close()
 
         # (2) the autograd Function PyTorch callers use, copies issued around it on one stream
         gvb_h = torch.empty(p['value'].shape, dtype=p['value'].dtype).pin_memory()

@@ -284,7 +284,7 @@ typedef struct msda_workspace msda_workspace;
 int msda_workspace_create(msda_workspace **out_ws);
 void msda_workspace_destroy(msda_workspace *ws);
 /* Upload bytes per pipeline piece of the staged calls (defaults: 12 MiB for a
- * blocking call, 32 MiB for a queued one). */
+ * blocking call, 64 MiB for a queued one). */
 int msda_workspace_set_piece_bytes(msda_workspace *ws, size_t bytes);
 
 /* Page-locked host memory for callers without their own CUDA binding.  With

@@ -605,8 +605,9 @@ struct msda_workspace {
   size_t next_event = 0;
   size_t piece_bytes = size_t(12) << 20;  // upload bytes per pipeline piece of a blocking call
   // ... and of a queued call: its upload-only head and download-only tail overlap with the neighbouring
-  // calls, so larger copies (better duplex rate) win: 5.84 ms per step at 12 MiB, 5.60 at 32 MiB
-  size_t piece_bytes_async = size_t(32) << 20;
+  // calls, so larger copies (better duplex rate) win: 5.84 ms per step at 12 MiB, 5.60 at 32 MiB, 5.37-5.5 with
+  // one piece per batch entry (config 2: 57 MB)
+  size_t piece_bytes_async = size_t(64) << 20;
   // PAVENET_MSDA_TRACE_E2E=<file>: timing events at every pipeline stage, written as CSV after each call
   bool batch_copies = true;    // a piece's copies go out as one cudaMemcpyBatchAsync (e2e 5.78 -> 5.60 ms); PAVENET_MSDA_BATCH_COPIES=0 disables
   bool in_flight = false;   // an asynchronous call has been queued and not waited for yet

@@ -1,0 +1,13 @@
+#!/bin/bash
+OUT=gpurun_out/r3e
+mkdir -p $OUT
+for cfg in "2 0" "3 0" "3 64" "3 4096" "2 4096" "4 4096"; do
+set -- $cfg
+timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-gpu-baseline --model-steps 0 --e2e-depth $1 --piece-mb $2 > $OUT/bench_$1_$2.json 2> $OUT/bench_$1_$2.err
+python - <<PY
+import json
+d = json.load(open('$OUT/bench_$1_$2.json')); e = d['e2e']
+q = e if e['mode'] == 'queued' else e['queued']; b = e['blocking'] if e['mode'] == 'queued' else e
+print('depth $1 piece $2 MiB: queued %.3f ms/step   blocking %.3f ms/step' % (q['ms_per_step'], b['ms_per_step']))
+PY
+done
