@@ -597,7 +597,7 @@ def main():
     ap.add_argument('--frames', type=int, default=0, help='override the batch entries (frames) per step of an op workload: the batch sweep of BASELINE config 5')
     ap.add_argument('--fused', action='store_true', help='time the fused-prologue kernels (offsets/logits in, softmax + location transform in-kernel) on the same problem')
     ap.add_argument('--piece-mb', type=float, default=0, help='e2e: upload MiB per pipeline piece (0 = library default)')
-    ap.add_argument('--e2e-depth', type=int, default=2, help='e2e, queued form: host-buffer calls in flight (workspaces)')
+    ap.add_argument('--e2e-depth', type=int, default=3, help='e2e, queued form: host-buffer calls in flight (workspaces)')
     ap.add_argument('--fold-clear', default='auto', choices=['auto', '0', '1'],
                     help='zero-fill grad_value inside the forward call (msda_forward_clear) instead of a '
                          'separate memset between forward and backward; auto = for the small-Q (pose) workloads, '
@@ -854,13 +854,16 @@ def main():
         # result buffers.  Every step still uploads all its inputs and downloads all its results inside
         # the timed region; the next step's first upload runs under this step's last download, which a
         # blocking call leaves idle (0.9 ms of its 6.4, profiles/r02_e2e_link_analysis.txt)
+        # three calls in flight, each in the monolithic form (piece size >= the call: every tensor is one copy,
+        # 34-68 MB, and the kernels run once over the whole batch) -- 5.14 ms per step against 5.39 for two calls
+        # with one piece per batch entry (profiles/r02_e2e_link_analysis.txt)
         slots = [(hws, out_h, gv_h, gl_h, ga_h)]
         for _ in range(max(2, args.e2e_depth) - 1):
-            w_ = pavenet_b200.HostWorkspace()
-            if args.piece_mb > 0:
-                w_.set_piece_bytes(int(args.piece_mb * (1 << 20)))
-            slots.append((w_, torch.empty_like(out_h).pin_memory(), torch.empty_like(gv_h).pin_memory(),
-                          torch.empty_like(gl_h).pin_memory(), torch.empty_like(ga_h).pin_memory()))
+            slots.append((pavenet_b200.HostWorkspace(), torch.empty_like(out_h).pin_memory(),
+                          torch.empty_like(gv_h).pin_memory(), torch.empty_like(gl_h).pin_memory(),
+                          torch.empty_like(ga_h).pin_memory()))
+        for s_ in slots:     # (the blocking leg above has already run on slots[0]'s workspace)
+            s_[0].set_piece_bytes(int(args.piece_mb * (1 << 20)) if args.piece_mb > 0 else 1 << 40)
         state = {'i': 0}
 
         def e2e_queued():
@@ -893,8 +896,8 @@ def main():
         e2e_q = timed_queued()
         e2e_q['api'] = ('msda_forward_backward_host_async + msda_workspace_wait (C ABI, pinned host buffers): '
                         '%d calls in flight on as many workspaces with separate result buffers; every step uploads ' % len(slots) +
-                        'all inputs and downloads output + all gradients; inside a call upload / kernels / download '
-                        'are pipelined over batch entries x query chunks')
+                        'all inputs and downloads output + all gradients; each call moves every tensor as one copy '
+                        '(monolithic form), the overlap is between calls')
         # both are the public entry point; a caller picks the form that suits its host.  With one GPU per
         # host link the queued form wins (5.6 against 6.4 ms); when several ranks share one host memory
         # system (N > 1 on this box) the extra concurrency costs more than the hidden head / tail saves.

@@ -284,7 +284,10 @@ typedef struct msda_workspace msda_workspace;
 int msda_workspace_create(msda_workspace **out_ws);
 void msda_workspace_destroy(msda_workspace *ws);
 /* Upload bytes per pipeline piece of the staged calls (defaults: 12 MiB for a
- * blocking call, 64 MiB for a queued one). */
+ * blocking call, 64 MiB for a queued one).  A size of at least the call's total
+ * upload selects the monolithic form: every tensor moves as one copy and the
+ * kernels run once over the whole batch -- nothing overlaps inside the call, which
+ * suits callers that keep three or more queued calls in flight. */
 int msda_workspace_set_piece_bytes(msda_workspace *ws, size_t bytes);
 
 /* Page-locked host memory for callers without their own CUDA binding.  With

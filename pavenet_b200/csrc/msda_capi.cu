@@ -751,13 +751,13 @@ void ws_write_trace(msda_workspace* ws) {
     if (rc_) return rc_;       \
   } while (0)
 
-// up to 3 copies of one direction queued on `st`: as one cudaMemcpyBatchAsync (fewer gaps between the
+// up to 4 copies of one direction queued on `st`: as one cudaMemcpyBatchAsync (fewer gaps between the
 // copies of a piece: 3 % on the whole call) or one by one; sizes of 0 are skipped
 cudaError_t copy_group(msda_workspace* ws, void* const* dsts, const void* const* srcs,
                        const size_t* sizes, int n, cudaMemcpyKind kind, cudaStream_t st) {
-  void* d[3];
-  void* s_[3];
-  size_t z[3];
+  void* d[4];
+  void* s_[4];
+  size_t z[4];
   int m = 0;
   for (int i = 0; i < n; ++i)
     if (sizes[i]) {
@@ -822,11 +822,11 @@ static int host_pipeline(msda_workspace* ws, const void* h_value,
   size_t need = pad256(b_shp) + pad256(b_lsi) +
                 batch * (pad256(b_val) + pad256(b_loc) + pad256(b_aw) + pad256(b_out));
   if (do_bwd) need += batch * (pad256(b_out) + pad256(b_gval) + pad256(b_loc) + pad256(b_aw));
-  MSDA_RC(ws_reserve(ws, need));
-  if (ws->in_flight)
+  if (ws->in_flight)   // (checked before the arena may be re-allocated underneath the queued call)
     return fail(MSDA_ERR_INVALID_ARGUMENT,
                 "msda_*_host: the previous asynchronous call on this workspace has not been waited for "
                 "(msda_workspace_wait)");
+  MSDA_RC(ws_reserve(ws, need));
   ws->next_event = 0;
   ws->marks.clear();
   MSDA_RC(ws_mark(ws, 'S', 0, 0, nullptr, ws->s_in[0]));
@@ -840,6 +840,59 @@ static int host_pipeline(msda_workspace* ws, const void* h_value,
   const int chunk = pick_chunk(num_query, up_q, piece_bytes);
   auto hoff = [](const void* p, size_t bytes) { return static_cast<const char*>(p) + bytes; };
   auto hoffw = [](void* p, size_t bytes) { return static_cast<char*>(p) + bytes; };
+
+  // Monolithic form (piece size >= the whole call's uploads): every input tensor goes up as ONE copy (they are
+  // contiguous over the batch entries), all four in one batch, the kernels run once over the whole batch, and the
+  // results come back the same way.  Nothing overlaps inside the call; it is meant for callers that keep three or
+  // more calls in flight, for whom the link then sees only 34-68 MB copies.
+  const size_t up_total = (b_val + b_loc + b_aw + (do_bwd ? b_out : 0)) * static_cast<size_t>(batch);
+  if (piece_bytes >= up_total && batch > 1) {
+    const size_t nb = static_cast<size_t>(batch);
+    char* d_val = static_cast<char*>(ar.take(nb * b_val));
+    char* d_loc = static_cast<char*>(ar.take(nb * b_loc));
+    char* d_aw = static_cast<char*>(ar.take(nb * b_aw));
+    char* d_out = static_cast<char*>(ar.take(nb * b_out));
+    char *d_go = nullptr, *d_gval = nullptr, *d_gloc = nullptr, *d_gaw = nullptr;
+    if (do_bwd) {
+      d_go = static_cast<char*>(ar.take(nb * b_out));
+      d_gval = static_cast<char*>(ar.take(nb * b_gval));
+      d_gloc = static_cast<char*>(ar.take(nb * b_loc));
+      d_gaw = static_cast<char*>(ar.take(nb * b_aw));
+      MSDA_CU(cudaMemsetAsync(d_gval, 0, nb * b_gval, ws->s_cmp));
+    }
+    {
+      void* const dsts[4] = {d_val, d_loc, d_aw, d_go};
+      const void* const srcs[4] = {h_value, h_sampling_loc, h_attn_weight, h_grad_output};
+      const size_t sizes[4] = {nb * b_val, nb * b_loc, nb * b_aw, do_bwd ? nb * b_out : 0};
+      MSDA_CU(copy_group(ws, dsts, srcs, sizes, 4, cudaMemcpyHostToDevice, ws->s_in[0]));
+    }
+    cudaEvent_t ev_in, ev_done;
+    MSDA_RC(ws_event(ws, &ev_in));
+    MSDA_CU(cudaEventRecord(ev_in, ws->s_in[0]));
+    MSDA_CU(cudaStreamWaitEvent(ws->s_cmp, ev_in, 0));
+    MSDA_RC(ws_mark(ws, 'I', 0, 0, ev_in, nullptr));
+    if (h_output)
+      MSDA_RC(msda_forward(d_val, d_shp, d_lsi, d_loc, d_aw, d_out, batch, spatial_size, num_heads, channels,
+                           num_levels, num_query, num_point, dtype, value_dtype, ws->s_cmp));
+    if (do_bwd)
+      MSDA_RC(msda_backward(d_val, d_shp, d_lsi, d_loc, d_aw, d_go, d_gval, d_gloc, d_gaw, batch, spatial_size,
+                            num_heads, channels, num_levels, num_query, num_point, dtype, value_dtype, dtype,
+                            ws->s_cmp));
+    MSDA_RC(ws_event(ws, &ev_done));
+    MSDA_CU(cudaEventRecord(ev_done, ws->s_cmp));
+    MSDA_CU(cudaStreamWaitEvent(ws->s_out[0], ev_done, 0));
+    MSDA_RC(ws_mark(ws, 'C', 0, 0, ev_done, nullptr));
+    {
+      void* const dsts[4] = {h_output, h_grad_sampling_loc, h_grad_attn_weight, h_grad_value};
+      const void* const srcs[4] = {d_out, d_gloc, d_gaw, d_gval};
+      const size_t sizes[4] = {h_output ? nb * b_out : 0, do_bwd ? nb * b_loc : 0, do_bwd ? nb * b_aw : 0,
+                               do_bwd ? nb * b_gval : 0};
+      MSDA_CU(copy_group(ws, dsts, srcs, sizes, 4, cudaMemcpyDeviceToHost, ws->s_out[0]));
+    }
+    MSDA_RC(ws_mark(ws, 'G', 0, 0, nullptr, ws->s_out[0]));
+    ws->in_flight = true;
+    return MSDA_OK;
+  }
 
   int piece = 0;  // global piece counter: piece k uploads on s_in[k % n], downloads on s_out[k % n]
   for (int b = 0; b < batch; ++b) {

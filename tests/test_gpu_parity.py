@@ -1048,8 +1048,8 @@ def test_host_buffer_async_calls_on_two_workspaces():
         value, shapes_t, loc, aw, go = _random_problem(seed, 2, 3000, 8, 32, 4, MID_LEVELS)
         probs.append([t.pin_memory() for t in (value, loc, aw, go)] + [shapes_t, O.level_start_index(shapes_t)])
     wss = [pavenet_b200.HostWorkspace(), pavenet_b200.HostWorkspace()]
-    for ws in wss:
-        ws.set_piece_bytes(1 << 20)
+    wss[0].set_piece_bytes(1 << 20)      # several query chunks per batch entry
+    wss[1].set_piece_bytes(1 << 40)      # monolithic form: every tensor one copy, kernels once over the batch
     results = []
     for i, (value, loc, aw, go, shapes_t, lsi) in enumerate(probs):
         ws = wss[i % 2]
