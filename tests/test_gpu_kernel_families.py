@@ -99,6 +99,52 @@ def test_flat_kernels_match_oracle(lib_options, B, Q, M, D, P, shapes, order):
     assert rel_err(ga, rga) < 1e-3
 
 
+def test_flat_kernels_randomised_shapes(lib_options):
+    """30 seeded random problems forced through the flat family: D in {16, 32, 64}, ragged level
+    sizes incl. 1xN maps, 1..20 levels (frames-as-levels), 1..19 points, pieces that start and end
+    anywhere inside a row (both piece orders), locations far outside the map and a few non-finite
+    ones (they must contribute nothing, as in the reference) -- forward and all three gradients
+    against the C oracle, and the folded zero-fill checked on the way."""
+    import random
+    from pavenet_b200 import _capi
+    from pavenet_b200.functional import ms_deform_attn_backward, ms_deform_attn_forward
+    rng = random.Random(20261017)
+    lib_options('flat', 2)
+    for trial in range(30):
+        D = rng.choice([16, 32, 32, 64])
+        M = rng.choice([1, 2, 4, 8])
+        L = rng.choice([1, 2, 4, 5, 12, 20])
+        P = rng.randint(1, 19)
+        B = rng.randint(1, 3)
+        Q = rng.choice([1, 3, 17, 64, 300, 700])
+        shapes = [(rng.randint(1, 20), rng.randint(1, 20)) for _ in range(L)]
+        lib_options('flat_order', trial % 2)
+        value, shapes_t, lsi, loc, aw, go = _problem(5000 + trial, B, Q, M, D, P, shapes,
+                                                      spread=rng.choice([0.0, 0.15, 0.8]))
+        if trial % 3 == 0:      # non-finite locations: the range test fails, the sample is skipped
+            flat_loc = loc.view(-1)
+            idx = torch.randint(0, flat_loc.numel(), (min(7, flat_loc.numel()),),
+                                generator=torch.Generator().manual_seed(trial))
+            flat_loc[idx] = torch.tensor([float('nan'), float('inf'), -float('inf')])[idx % 3]
+        before = _capi.family_counts()
+        args = (value.cuda(), shapes_t.cuda(), lsi.cuda(), loc.cuda(), aw.cuda())
+        gv = torch.full(value.shape, 7.0, device='cuda')
+        out = ms_deform_attn_forward(*args, 64, clear=gv)
+        assert float(gv.abs().max()) == 0.0
+        gl, ga = torch.empty_like(args[3]), torch.empty_like(args[4])
+        ms_deform_attn_backward(*args, go.cuda(), gv, gl, ga, 64)
+        ran = _delta(before, _capi.family_counts())
+        assert ran == {'fwd_flat': 1, 'bwd_flat': 1}, (trial, ran)
+        ref = O.c_forward(value, shapes_t, lsi, loc, aw)
+        rgv, rgl, rga = O.c_backward(value, shapes_t, lsi, loc, aw, go)
+        tag = (trial, B, Q, M, D, L, P, shapes)
+        assert torch.isfinite(out).all() and torch.isfinite(gv).all(), tag
+        assert rel_err(out, ref) < 1e-4, tag
+        assert rel_err(gv, rgv) < 1e-3, tag
+        assert rel_err(gl, rgl) < 1e-3, tag
+        assert rel_err(ga, rga) < 1e-3, tag
+
+
 @pytest.mark.parametrize('B,Q,M,D,P,shapes', FLAT_SHAPES[:4] + FLAT_SHAPES[6:8])
 def test_rows_kernels_forced_on_the_same_shapes(lib_options, B, Q, M, D, P, shapes):
     from pavenet_b200 import _capi
