@@ -58,8 +58,14 @@ __device__ __forceinline__ void scatter_corner_aggregated(bool valid, int row_of
   }
 }
 
+// resident blocks per SM the fused-prologue instantiation is compiled for (its IO object carries ~16 more
+// live registers than the plain one, which fits three blocks at 80 registers by itself)
+#ifndef MSDA_FUSED_BWD_MINB
+#define MSDA_FUSED_BWD_MINB 2
+#endif
+
 template <int D, typename VT, typename GT, class IO, int AGG = 0>
-__global__ void __launch_bounds__(kRowsThreads, IO::kFused ? 2 : 0)
+__global__ void __launch_bounds__(kRowsThreads, IO::kFused ? MSDA_FUSED_BWD_MINB : 0)
 msda_bwd_rows_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, IO io, const float* __restrict__ grad_out,
                      GT* __restrict__ grad_value, Dims d, int nsplit, int agg_min_level) {

@@ -104,10 +104,7 @@ struct FusedIO {
   float dot;          // <grad_out[row], out[row]>
   static constexpr bool kFused = true;
   __device__ __forceinline__ void bind(int64_t unit, int LP, int M, int64_t bq) {
-    src.bind(unit, LP, M, bq);
-    grad_off += unit * LP * 2;
-    grad_logit += unit * LP;
-    if (grad_loc) grad_loc += unit * LP * 2;
+    src.bind(unit, LP, M, bq);     // the gradient pointers stay untouched (constant bank): src.so indexes them
     dot = 0.f;
   }
   // g: this lane's VEC channels (gl*VEC ...) of grad_out[row]; G lanes cover the row
@@ -128,14 +125,15 @@ struct FusedIO {
                                         float Wf, float Hf) {
     float2 go;
     if (src.scale) {
-      const float2 sc = __ldg(reinterpret_cast<const float2*>(src.scale) + l);
+      const float2 sc = __ldg(reinterpret_cast<const float2*>(src.scale) + (src.ro + l));
       go = make_float2(Wf * tx * sc.x, Hf * ty * sc.y);
     } else {
       go = make_float2(tx, ty);   // d loc / d off = 1 / (W, H) cancels the pixel scale
     }
-    __stcs(reinterpret_cast<float2*>(grad_off + 2 * s), go);
-    if (grad_loc) __stcs(reinterpret_cast<float2*>(grad_loc + 2 * s), make_float2(Wf * tx, Hf * ty));
-    __stcs(grad_logit + s, w * (gw - dot));
+    const int64_t e = src.so + s;
+    __stcs(reinterpret_cast<float2*>(grad_off + 2 * e), go);
+    if (grad_loc) __stcs(reinterpret_cast<float2*>(grad_loc + 2 * e), make_float2(Wf * tx, Hf * ty));
+    __stcs(grad_logit + e, w * (gw - dot));
   }
 };
 

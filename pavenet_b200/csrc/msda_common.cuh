@@ -144,6 +144,9 @@ struct PlainSource {
 };
 
 struct FusedSource {
+  // The base pointers are never modified: as members of a kernel parameter they stay in the constant bank and
+  // cost no registers.  Only the two element offsets of the bound row live in registers (the rows backward
+  // needs three resident blocks per SM, i.e. <= 85 registers, and every 64-bit pointer it keeps is two of them).
   const float* off;      // (B,Q,M,L,P,2)
   const float* logit;    // (B,Q,M,L*P)
   const float* ref;      // (B,Q,L,R,2)
@@ -153,50 +156,52 @@ struct FusedSource {
   int P;
   int stats_ready;       // backward: read stats instead of recomputing them
   float mx, inv;
+  int64_t so;            // first sample of the bound row: unit * L*P
+  int64_t ro;            // first (level) entry of the bound query in ref / scale: bq * L
+  int64_t su;            // the bound row (only prepass reads it, so it is dead right after bind + prepass)
   __device__ __forceinline__ void bind(int64_t unit, int LP, int M, int64_t bq) {
-    off += unit * LP * 2;
-    logit += unit * LP;
-    stats += unit * 2;
-    const int L = LP / P;
-    ref += bq * L * R * 2;
-    if (scale) scale += bq * L * 2;
+    su = unit;
+    so = unit * LP;
+    ro = bq * (LP / P);
     (void)M;
   }
   // max and sum over the row's logits, by the G lanes of the group
   template <int G>
   __device__ __forceinline__ void prepass(int LP, int gl, bool writer) {
+    float* st = stats + su * 2;
     if (stats_ready) {
-      mx = stats[0];
-      inv = stats[1];
+      mx = st[0];
+      inv = st[1];
       return;
     }
+    const float* lg = logit + so;
     float m_ = -INFINITY;
-    for (int s = gl; s < LP; s += G) m_ = fmaxf(m_, __ldg(logit + s));
+    for (int s = gl; s < LP; s += G) m_ = fmaxf(m_, __ldg(lg + s));
 #pragma unroll
     for (int o = G / 2; o >= 1; o >>= 1) m_ = fmaxf(m_, __shfl_xor_sync(0xffffffffu, m_, o));
     float sum = 0.f;
-    for (int s = gl; s < LP; s += G) sum += __expf(__ldg(logit + s) - m_);
+    for (int s = gl; s < LP; s += G) sum += __expf(__ldg(lg + s) - m_);
 #pragma unroll
     for (int o = G / 2; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     mx = m_;
     inv = 1.f / sum;
     if (writer && gl == 0) {
-      stats[0] = mx;
-      stats[1] = inv;
+      st[0] = mx;
+      st[1] = inv;
     }
   }
   __device__ __forceinline__ RawSample load(int s) const {
-    const float2 xy = ld_stream_f2(off + 2 * s);
+    const float2 xy = ld_stream_f2(off + 2 * (so + s));
     RawSample r;
-    r.x = xy.x; r.y = xy.y; r.w = __ldg(logit + s);
+    r.x = xy.x; r.y = xy.y; r.w = __ldg(logit + so + s);
     return r;
   }
   // offsets -> location, logit -> softmax weight
   __device__ __forceinline__ void finish(RawSample& r, int s, int l, const LevelInfo& lv) const {
     const int p = s - l * P;
-    const float2 rp = __ldg(reinterpret_cast<const float2*>(ref) + (l * R + (R == 1 ? 0 : p)));
+    const float2 rp = __ldg(reinterpret_cast<const float2*>(ref) + ((ro + l) * R + (R == 1 ? 0 : p)));
     if (scale) {
-      const float2 sc = __ldg(reinterpret_cast<const float2*>(scale) + l);
+      const float2 sc = __ldg(reinterpret_cast<const float2*>(scale) + (ro + l));
       r.x = rp.x + r.x * sc.x;
       r.y = rp.y + r.y * sc.y;
     } else {
