@@ -81,17 +81,16 @@ struct PlainIO {
   float* grad_aw;
   static constexpr bool kFused = false;
   __device__ __forceinline__ void bind(int64_t unit, int LP, int M, int64_t bq) {
-    src.bind(unit, LP, M, bq);
-    grad_loc += unit * LP * 2;
-    grad_aw += unit * LP;
+    src.bind(unit, LP, M, bq);     // grad_loc / grad_aw stay untouched (constant bank): src.so indexes them
   }
   template <int G, int VEC>
   __device__ __forceinline__ void row_dot(const float (&)[VEC], int64_t, int, int) {}
   // gw: d/d(attention weight); (tx, ty): d/d(pixel coordinate), so d/d(location) = (W tx, H ty)
   __device__ __forceinline__ void store(int s, int, float gw, float tx, float ty, float, float Wf,
                                         float Hf) {
-    __stcs(grad_aw + s, gw);
-    __stcs(reinterpret_cast<float2*>(grad_loc + 2 * s), make_float2(Wf * tx, Hf * ty));
+    const int64_t e = src.so + s;
+    __stcs(grad_aw + e, gw);
+    __stcs(reinterpret_cast<float2*>(grad_loc + 2 * e), make_float2(Wf * tx, Hf * ty));
   }
 };
 

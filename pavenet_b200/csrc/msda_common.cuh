@@ -126,18 +126,16 @@ struct RawSample {
 };
 
 struct PlainSource {
-  const float* loc;
+  const float* loc;      // never modified (constant bank); `so` indexes the bound row
   const float* aw;
-  __device__ __forceinline__ void bind(int64_t unit, int LP, int, int64_t) {
-    loc += unit * LP * 2;
-    aw += unit * LP;
-  }
+  int64_t so;            // first sample of the bound row: unit * L*P
+  __device__ __forceinline__ void bind(int64_t unit, int LP, int, int64_t) { so = unit * LP; }
   template <int G>
   __device__ __forceinline__ void prepass(int, int, bool) {}
   __device__ __forceinline__ RawSample load(int s) const {
-    const float2 xy = ld_stream_f2(loc + 2 * s);
+    const float2 xy = ld_stream_f2(loc + 2 * (so + s));
     RawSample r;
-    r.x = xy.x; r.y = xy.y; r.w = ld_stream_f(aw + s);
+    r.x = xy.x; r.y = xy.y; r.w = ld_stream_f(aw + so + s);
     return r;
   }
   __device__ __forceinline__ void finish(RawSample& r, int, int, const LevelInfo&) const {}
