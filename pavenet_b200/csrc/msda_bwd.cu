@@ -63,6 +63,9 @@ __device__ __forceinline__ void scatter_corner_aggregated(bool valid, int row_of
 #ifndef MSDA_FUSED_BWD_MINB
 #define MSDA_FUSED_BWD_MINB 2
 #endif
+#ifndef MSDA_BWD_D64_MINB
+#define MSDA_BWD_D64_MINB 2
+#endif
 
 // (plain, bf16 value with fp32 gradients, D <= 32: three resident blocks = 80 registers stated explicitly -- left to
 // itself the compiler gave this instantiation 93 registers after an unrelated change and config 2's bf16 backward went
@@ -70,6 +73,7 @@ __device__ __forceinline__ void scatter_corner_aggregated(bool valid, int row_of
 template <typename VT, typename GT, class IO, int D, int AGG>
 constexpr int bwd_rows_min_blocks() {
   if (IO::kFused) return MSDA_FUSED_BWD_MINB;
+  if (D == 64 && AGG == 0) return MSDA_BWD_D64_MINB;   // 130-144 registers unbounded = one block per SM; 128 fits two
   return (!std::is_same<VT, float>::value && std::is_same<GT, float>::value && D <= 32 && AGG == 0) ? 3 : 0;
 }
 
