@@ -19,7 +19,7 @@ LIB_DIR = os.path.join(_HERE, 'lib')
 LIB_PATH = os.environ.get('PAVENET_MSDA_LIB') or os.path.join(LIB_DIR, 'libpavenet_msda.so')
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), 'include')
 
-SOURCES = ['msda_fwd.cu', 'msda_fwd_tile.cu', 'msda_bwd.cu', 'msda_flat.cu', 'linear256_tc.cu', 'layernorm.cu', 'msda_capi.cu']
+SOURCES = ['msda_fwd.cu', 'msda_fwd_tile.cu', 'msda_bwd.cu', 'msda_bwd_priv.cu', 'msda_flat.cu', 'linear256_tc.cu', 'layernorm.cu', 'msda_capi.cu']
 HEADERS = ['msda_common.cuh', 'msda_bwd_io.cuh', 'msda_kernels.h']
 
 NVCC_FLAGS = [

@@ -409,6 +409,9 @@ cudaError_t launch_backward(const void* value, const int64_t* shapes, const int6
         return launch_backward_flat(value, shapes, lsi, io, gof, grad_value, d, value_dtype,
                                     grad_value_dtype, sm_count, st);
     }
+    // variant 3: coarsest level privatised in shared memory (the benchmark's kernel only)
+    if (tuning().bwd_variant == 3 && d.D == 32 && value_dtype == MSDA_F32 && grad_value_dtype == MSDA_F32)
+      return launch_backward_priv(value, shapes, lsi, io, gof, grad_value, d, sm_count, st);
 #define MSDA_BWD_CASE(DD)                                                                         \
   case DD:                                                                                        \
     if (value_dtype == MSDA_F32) {                                                                \

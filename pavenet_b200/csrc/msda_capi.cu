@@ -208,6 +208,7 @@ int msda_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "bwd_split")) slot = &t.bwd_split;
   else if (!std::strcmp(name, "flat")) slot = &t.flat;
   else if (!std::strcmp(name, "agg_min_level")) slot = &t.agg_min_level;
+  else if (!std::strcmp(name, "agg_tile_kb")) slot = &t.agg_tile_kb;
   else if (!std::strcmp(name, "flat_fwd_cfg")) slot = &t.flat_fwd_cfg;
   else if (!std::strcmp(name, "flat_bwd_cfg")) slot = &t.flat_bwd_cfg;
   else if (!std::strcmp(name, "flat_order")) slot = &t.flat_order;

@@ -30,6 +30,7 @@ struct Tuning {
                            // 2 flat kernel: TMA bulk stores of a zeroed shared-memory tile
   int l2_prefetch = 0;     // flat kernels stream value into L2 first: bit 0 forward, bit 1 backward
   int l2_prefetch_mb = 120;  // ... when value is at most this many MiB
+  int agg_tile_kb = 36;    // bwd_variant 3: shared-memory tile for the privatised coarsest level (KiB per block)
   int agg_min_level = 0;   // bwd_variant 2: aggregate from this level on (0 = every level)
   int bwd_variant = 0;   // large-Q backward: 0 default, 1 plain rows, 2 warp-aggregated, 3 tile
   int fwd_variant = 0;   // large-Q forward: 0 default, 2 head-affine, 3 / 4 256-bit loads, 5 shared-memory tiles
@@ -74,6 +75,10 @@ cudaError_t launch_backward_flat(const void* value, const int64_t* shapes, const
                                  const PlainIO& io, const float* grad_out, void* grad_value,
                                  const Dims& d, int value_dtype, int grad_value_dtype, int sm_count,
                                  cudaStream_t st);
+// variant 3 of the large-Q backward (msda_bwd_priv.cu): coarsest level privatised in shared memory
+cudaError_t launch_backward_priv(const void* value, const int64_t* shapes, const int64_t* lsi,
+                                 const PlainIO& io, const float* grad_out, void* grad_value,
+                                 const Dims& d, int sm_count, cudaStream_t st);
 cudaError_t launch_backward_flat_fused(const void* value, const int64_t* shapes,
                                        const int64_t* lsi, const FusedIO& io,
                                        const float* grad_out, float* grad_value, const Dims& d,

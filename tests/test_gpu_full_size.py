@@ -92,7 +92,7 @@ def _check(p, got, want, ftol=1e-4, btol=1e-3, etol=1e-3):
     assert float(gv.detach().cpu()[~touched].abs().max() if (~touched).any() else 0.0) == 0.0
 
 
-@pytest.mark.parametrize('options', [{}, {'bwd_variant': 2}, {'fwd_variant': 2}, {'fwd_variant': 5}, {'fwd_variant': 6}])
+@pytest.mark.parametrize('options', [{}, {'bwd_variant': 2}, {'bwd_variant': 3}, {'fwd_variant': 2}, {'fwd_variant': 5}, {'fwd_variant': 6}])
 def test_encoder_cfg2_one_frame_all_gradients_elementwise(options):
     """BASELINE config 2, one of its three frames at full size: Q = S = 22 223 queries,
     8 heads x 4 levels x 4 points, the benchmark's own spatially coherent locations (so the

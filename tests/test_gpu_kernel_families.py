@@ -280,11 +280,12 @@ def test_fused_kernels_match_unfused_chain(lib_options, flat, Q, P, levels, R, w
 ENC_LEVELS = [(50, 84), (25, 42), (13, 21), (7, 11)]
 
 
-@pytest.mark.parametrize('variant', [('fwd_variant', 2), ('bwd_variant', 2)])
+@pytest.mark.parametrize('variant', [('fwd_variant', 2), ('bwd_variant', 2), ('bwd_variant', 3)])
 def test_large_q_kernel_variants_match_oracle(lib_options, variant):
     """Encoder-shaped problem (queries = pixels, coherent locations so neighbouring queries DO
     collide on value rows) through the alternative large-Q kernels: the head-affine persistent
-    forward (fwd_variant 2) and the warp-aggregated-atomics backward (bwd_variant 2)."""
+    forward (fwd_variant 2), the warp-aggregated-atomics backward (bwd_variant 2) and the backward that
+    privatises the coarsest level in shared memory (bwd_variant 3, 128-bit CAS accumulation)."""
     from pavenet_b200 import _capi
     name, val = variant
     lib_options(name, val)
