@@ -226,12 +226,14 @@ cudaError_t launch_backward_priv(const void* value, const int64_t* shapes, const
                                  const Dims& d, int sm_count, cudaStream_t st) {
   const int tile_kb = tuning().agg_tile_kb;
   const int tile_bytes = tile_kb * 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};     // the opt-in to > 48 KB of dynamic shared memory is per device
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
+  if (dev < 0 || !attr_set[dev]) {
     const cudaError_t e = cudaFuncSetAttribute(msda_bwd_rows_priv_kernel,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (dev >= 0) attr_set[dev] = true;
   }
   // resident blocks per SM that the tile leaves room for (static shared memory ~ 10 KB per block)
   int per_sm = (220 * 1024) / (tile_bytes + 11 * 1024);
